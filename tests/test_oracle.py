@@ -1,0 +1,174 @@
+"""CPU tests of the oracle itself (no GPU).  The reference has no golden vectors and cannot run here
+(PARITY UNPINNED); these tests pin the C restatement the only ways available:
+  1. against the anchors of a third, separately written emulation made at survey time,
+  2. bit-for-bit against the independently structured numpy restatement (oracle/oracle_np.py),
+  3. against the committed golden vectors (regression),
+  4. against analytic properties of the constraint projection.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import oracle_np
+from util import DT600, DT1200, vec_rel_err
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "softbody_golden.npz"))
+
+
+def test_survey_anchors(dragon):
+    sb = oracle.SoftBodyOracle(dragon["tet_verts"], dragon["tet_ids"])
+    assert list(sb.tetIds[:4]) == [1, 0, 2, 521]
+    np.testing.assert_array_equal(sb.invRestPose[:9], np.float32(
+        [-10.637138, 0.8368553, -3.1084132, 5.9744034, -1.666426, -5.4478583, -0.014100595, -10.181579, 0.26633632]))
+    assert sb.invRestVolume[0] == np.float32(4695.7603)
+    np.testing.assert_array_equal(sb.invMass[:4], np.float32([0.93524957, 0.76354, 1.4777923, 0.8246292]))
+    want_vol = {1: -0.16658050127720742, 10: -0.15752738889947235, 100: -0.15737990687763845}
+    want_sum = {1: 1300.5853506604035, 10: 1298.7850487290088, 100: 1132.864895039551}
+    for s in range(1, 101):
+        sb.simulate(DT600)
+        if s in want_vol:
+            assert sb.volError == want_vol[s]
+            assert float(np.sum(sb.pos.astype(np.float64))) == want_sum[s]
+    np.testing.assert_array_equal(sb.pos[:3], np.float32([-0.06708563, 1.1470823, -0.081903815]))
+
+
+def test_two_restatements_agree_bitwise(dragon):
+    sb = oracle.SoftBodyOracle(dragon["tet_verts"], dragon["tet_ids"])
+    nb = oracle_np.SoftBodyNP(dragon["tet_verts"], dragon["tet_ids"])
+    assert np.array_equal(sb.invRestPose, nb.Q.reshape(-1))
+    assert np.array_equal(sb.invRestVolume, nb.irv)
+    assert np.array_equal(sb.invMass, nb.inv_mass)
+    assert len(nb.levels) == 703 and max(len(l) for l in nb.levels) == 22
+    for s in range(1, 11):
+        sb.simulate(DT600)
+        nb.simulate(DT600)
+        assert np.array_equal(sb.pos, nb.pos.reshape(-1)), s
+        assert np.array_equal(sb.vel, nb.vel.reshape(-1)), s
+        assert sb.volError == nb.volError
+    assert np.array_equal(nb.pos.reshape(-1), GOLD["gs_pos_10"])
+
+
+def test_two_restatements_agree_with_contact_and_params(dragon):
+    v = dragon["tet_verts"].reshape(-1, 3).copy()
+    v[:, 1] -= np.float32(0.4545)
+    kw = dict(gravity=-20.0, friction=250.0, devCompliance=2e-5, volCompliance=1e-6,
+              worldBounds=(-0.9, -1.0, -2.5, 0.8, 1.45, 0.3))
+    sb = oracle.SoftBodyOracle(v, dragon["tet_ids"], **kw)
+    nb = oracle_np.SoftBodyNP(v, dragon["tet_ids"], **kw)
+    for s in range(8):
+        sb.simulate(DT600)
+        nb.simulate(DT600)
+    assert np.any(sb.pos.reshape(-1, 3)[:, 1] == 0.0)
+    assert np.array_equal(sb.pos, nb.pos.reshape(-1))
+    assert np.array_equal(sb.vel, nb.vel.reshape(-1))
+
+
+def test_golden_regression(dragon):
+    sb = oracle.SoftBodyOracle(dragon["tet_verts"], dragon["tet_ids"])
+    assert np.array_equal(sb.invRestPose, GOLD["invRestPose"])
+    assert np.array_equal(sb.invMass, GOLD["invMass"])
+    for s in range(1, 101):
+        sb.simulate(DT600)
+        if s in (1, 10, 100):
+            assert np.array_equal(sb.pos, GOLD["gs_pos_%d" % s])
+            assert np.array_equal(sb.vel, GOLD["gs_vel_%d" % s])
+            assert sb.volError == float(GOLD["gs_vol_error_%d" % s])
+    jb = oracle.SoftBodyOracle(dragon["tet_verts"], dragon["tet_ids"])
+    po = oracle.PolarOracle(dragon["tet_verts"], dragon["tet_ids"])
+    for s in range(1, 101):
+        jb.simulate_jacobi(DT1200, 1)
+        po.simulate(DT1200)
+        if s in (10, 100):
+            assert np.array_equal(jb.pos, GOLD["jacobi1_pos_%d" % s])
+            assert np.array_equal(po.pos, GOLD["polar_bug1_pos_%d" % s])
+
+
+def test_level_order_equals_sequential_order(dragon):
+    """F4 of the survey: the dependency-level order is bit-identical to the in-order sweep."""
+    nb_levels = oracle_np.level_schedule(1234, dragon["tet_ids"])
+    order = np.concatenate(nb_levels).astype(np.int32)
+    a = oracle.SoftBodyOracle(dragon["tet_verts"], dragon["tet_ids"])
+    b = oracle.SoftBodyOracle(dragon["tet_verts"], dragon["tet_ids"])
+    for _ in range(20):
+        a.simulate(DT600)
+        b.simulate(DT600, order=order)
+    assert np.array_equal(a.pos, b.pos)
+    # ...whereas another order (reverse) is a different algorithm, far outside the 1e-4 tolerance
+    c = oracle.SoftBodyOracle(dragon["tet_verts"], dragon["tet_ids"])
+    a2 = oracle.SoftBodyOracle(dragon["tet_verts"], dragon["tet_ids"])
+    rev = np.arange(3840, dtype=np.int32)[::-1].copy()
+    for _ in range(100):
+        a2.simulate(DT600)
+        c.simulate(DT600, order=rev)
+    assert vec_rel_err(c.pos, a2.pos) > 1e-3
+
+
+def test_projection_properties():
+    """One tet: the projection conserves linear momentum (sum m_i dx_i = 0, since the gradients sum
+    to zero) and drives det F toward 1 with the default volCompliance = 0."""
+    v = np.array([0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1], np.float32)
+    t = np.array([0, 1, 2, 3], np.int32)
+    sb = oracle.SoftBodyOracle(v, t, gravity=0.0)
+    np.testing.assert_allclose(sb.invRestPose, np.eye(3, dtype=np.float32).reshape(-1), atol=0)
+    assert sb.invRestVolume[0] == np.float32(6.0)
+    sb.pos[:] = (sb.pos.reshape(4, 3) * np.float32([1.3, 0.9, 1.1]) + np.float32([0, 1, 0])).reshape(-1)  # stretch, off the floor
+    sb.prevPos[:] = sb.pos
+    before = sb.pos.copy()
+    sb.simulate(DT600)
+    m = 1.0 / sb.invMass.astype(np.float64)
+    dp = (sb.pos.astype(np.float64) - before.astype(np.float64)).reshape(4, 3)
+    assert np.max(np.abs((m[:, None] * dp).sum(0))) < 1e-6 * m.sum()
+    x = sb.pos.reshape(4, 3).astype(np.float64)
+    J = np.linalg.det((x[1:] - x[0]).T)
+    assert abs(J - 1.0) < abs(1.3 * 0.9 * 1.1 - 1.0) * 0.05
+
+
+def test_jacobi_is_order_independent_up_to_rounding(dragon):
+    a = oracle.SoftBodyOracle(dragon["tet_verts"], dragon["tet_ids"])
+    perm = np.random.default_rng(0).permutation(3840)
+    ids = dragon["tet_ids"].reshape(-1, 4)[perm].reshape(-1)
+    b = oracle.SoftBodyOracle(dragon["tet_verts"], ids)
+    for _ in range(10):
+        a.simulate_jacobi(DT1200, 2)
+        b.simulate_jacobi(DT1200, 2)
+    assert vec_rel_err(a.pos, b.pos) < 1e-5
+
+
+def test_polar_table_bug_only_touches_one_vertex(dragon):
+    a = oracle.PolarOracle(dragon["tet_verts"], dragon["tet_ids"], reference_table_bug=True)
+    b = oracle.PolarOracle(dragon["tet_verts"], dragon["tet_ids"], reference_table_bug=False)
+    assert a.tblEntries.size == b.tblEntries.size - 1
+    v = int(dragon["tet_ids"][0])          # tetIds[0] = 1: the vertex whose corner 0 of tet 0 is lost
+    na = np.diff(a.tblStart)
+    nb_ = np.diff(b.tblStart)
+    assert np.flatnonzero(na != nb_).tolist() == [v]
+    assert 0 not in a.tblEntries[a.tblStart[v]:a.tblStart[v + 1]]
+    assert nb_.max() == 32 <= 36
+
+
+def test_polar_free_fall_and_volume(dragon):
+    po = oracle.PolarOracle(dragon["tet_verts"], dragon["tet_ids"])
+    y0 = po.pos.reshape(-1, 3)[:, 1].min()
+    for _ in range(120):
+        po.simulate(DT1200)
+    y = po.pos.reshape(-1, 3)[:, 1].min()
+    t = 119 * DT1200  # gravity enters the velocity one substep late (src/SoftbodyGPU.js:367-371)
+    assert abs((y0 - y) - 0.5 * 9.81 * t * t) < 0.01
+    assert np.all(np.isfinite(po.pos))
+    q = po.quat.reshape(-1, 4)
+    np.testing.assert_allclose(np.linalg.norm(q, axis=1), 1.0, atol=1e-6)
+
+
+def test_skin_and_normals_oracle(dragon):
+    pos = dragon["tet_verts"]
+    s = oracle.skin(dragon["vis_verts"], dragon["tet_ids"], pos).reshape(-1, 3)
+    vv = dragon["vis_verts"].reshape(-1, 4).astype(np.float64)
+    ids = dragon["tet_ids"].reshape(-1, 4)[vv[:, 0].astype(int)]
+    b = np.concatenate([vv[:, 1:], 1.0 - vv[:, 1:2] - vv[:, 2:3] - vv[:, 3:4]], axis=1)
+    ref = (pos.reshape(-1, 3).astype(np.float64)[ids] * b[:, :, None]).sum(1)
+    assert np.max(np.abs(s - ref)) < 1e-6
+    n = oracle.vertex_normals(s.reshape(-1), dragon["vis_tri_ids"]).reshape(-1, 3)
+    ln = np.linalg.norm(n, axis=1)
+    assert np.all((np.abs(ln - 1.0) < 1e-6) | (ln == 0.0))

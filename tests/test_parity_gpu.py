@@ -1,0 +1,446 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Bars:
+  * BITEXACT arithmetic: bit-identical to the oracle (Gauss-Seidel in the reference order, colour
+    order, Jacobi gather, polar variant, initPhysics, collision, grab, skinning, normals);
+  * FAST_F32 arithmetic: vertex positions within 1e-4 (vector-relative) of the oracle after 100
+    substeps at dt = 1/600, the tolerance BASELINE.json's north_star states.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+import tetsim_b200 as ts
+from tetsim_b200 import mesh
+from util import DT600, DT1200, assert_bit_equal, vec_rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4  # north_star: "vertex positions within 1e-4 rel of the reference after 100 substeps"
+
+
+def new_body(m, cls=ts.SoftBody, params=None, **kw):
+    return cls(m["tet_verts"], m["tet_ids"], m.get("tet_edge_ids"), params, **kw)
+
+
+# ------------------------------------------------------------------------------------------------
+# initPhysics (src/Softbody.js:60-87)
+# ------------------------------------------------------------------------------------------------
+def test_init_physics_bit_exact(dragon):
+    ref = oracle.SoftBodyOracle(dragon["tet_verts"], dragon["tet_ids"])
+    sb = new_body(dragon)
+    assert_bit_equal(sb.invRestPose, ref.invRestPose, "invRestPose")
+    assert_bit_equal(sb.invRestVolume, ref.invRestVolume, "invRestVolume")
+    assert_bit_equal(sb.invMass, ref.invMass, "invMass")
+    assert_bit_equal(sb.pos, ref.pos, "pos")
+    assert np.all(sb.vel == 0)
+
+
+def test_init_physics_jittered_beam_bit_exact():
+    v, t = mesh.make_beam((12, 5, 4), jitter=0.2)
+    ref = oracle.SoftBodyOracle(v, t, density=250.0)
+    p = dict(ts.DEFAULT_PHYSICS_PARAMS, density=250.0)
+    sb = ts.SoftBody(v, t, None, p, solver="jacobi")
+    assert_bit_equal(sb.invRestPose, ref.invRestPose, "invRestPose")
+    assert_bit_equal(sb.invRestVolume, ref.invRestVolume, "invRestVolume")
+    assert_bit_equal(sb.invMass, ref.invMass, "invMass")
+
+
+# ------------------------------------------------------------------------------------------------
+# Gauss-Seidel, the reference order (BASELINE config 1 / 3(i))
+# ------------------------------------------------------------------------------------------------
+def test_gs_exact_bitexact_100_substeps(dragon):
+    ref = oracle.SoftBodyOracle(dragon["tet_verts"], dragon["tet_ids"])
+    sb = new_body(dragon, solver="gs_exact", arithmetic="bitexact")
+    info = sb.info()
+    assert info["numLevels"] == 703 and info["maxLevelSize"] == 22 and info["bodyKernel"] == 1
+    for s in range(1, 101):
+        ref.simulate(DT600)
+        sb.simulate(DT600)
+        if s in (1, 2, 10, 50, 100):
+            assert_bit_equal(sb.pos, ref.pos, "pos @%d" % s)
+            assert_bit_equal(sb.vel, ref.vel, "vel @%d" % s)
+            assert_bit_equal(sb.prevPos, ref.prevPos, "prevPos @%d" % s)
+            assert sb.volError == ref.volError, (s, sb.volError, ref.volError)
+
+
+def test_gs_exact_matches_golden(dragon):
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "softbody_golden.npz"))
+    sb = new_body(dragon, solver="gs_exact", arithmetic="bitexact")
+    for s in range(1, 101):
+        sb.simulate(DT600)
+        if s in (1, 10, 100):
+            assert_bit_equal(sb.pos, g["gs_pos_%d" % s], "golden pos @%d" % s)
+            assert sb.volError == float(g["gs_vol_error_%d" % s])
+
+
+def test_gs_exact_fast_within_tolerance(dragon):
+    ref = oracle.SoftBodyOracle(dragon["tet_verts"], dragon["tet_ids"])
+    sb = new_body(dragon, solver="gs_exact", arithmetic="fast")
+    for _ in range(100):
+        ref.simulate(DT600)
+        sb.simulate(DT600)
+    err = vec_rel_err(sb.pos, ref.pos)
+    assert err <= TOL, err
+    assert abs(sb.volError - ref.volError) < 1e-4
+
+
+def test_gs_level_kernel_path_bitexact(dragon, monkeypatch):
+    """The generic one-launch-per-level path (bodies too large for shared memory) on the same input."""
+    monkeypatch.setenv("TETSIM_FORCE_LEVEL_KERNEL", "1")
+    ref = oracle.SoftBodyOracle(dragon["tet_verts"], dragon["tet_ids"])
+    sb = new_body(dragon, solver="gs_exact", arithmetic="bitexact")
+    assert sb.info()["bodyKernel"] == 0
+    for _ in range(5):
+        ref.simulate(DT600)
+        sb.simulate(DT600)
+    assert_bit_equal(sb.pos, ref.pos, "pos")
+    assert sb.volError == ref.volError
+
+
+def test_step_graph_equals_repeated_simulate(dragon):
+    """tetsim_step (src/main.js:79-84 as one CUDA graph) == numSubsteps x simulate, and parameters
+    changed between frames (GUI sliders, src/main.js:37-42) are honoured without re-capture."""
+    a = new_body(dragon, solver="gs_exact", arithmetic="bitexact")
+    b = new_body(dragon, solver="gs_exact", arithmetic="bitexact")
+    p = dict(ts.DEFAULT_PHYSICS_PARAMS, numSubsteps=10)
+    for frame in range(3):
+        if frame == 2:
+            p["gravity"] = -3.0
+        a.step(p)
+        dt = (p["timeScale"] * p["timeStep"]) / p["numSubsteps"]
+        for _ in range(p["numSubsteps"]):
+            b.simulate(dt, p)
+    assert_bit_equal(a.pos, b.pos, "graph vs loop")
+    assert_bit_equal(a.vel, b.vel, "graph vs loop vel")
+
+
+# ------------------------------------------------------------------------------------------------
+# Gauss-Seidel via graph colouring (BASELINE config 3(ii))
+# ------------------------------------------------------------------------------------------------
+def test_gs_color_bitexact_vs_oracle_in_colour_order(dragon):
+    color, ncol = ts.greedy_colors(dragon["tet_ids"], 1234)
+    assert ncol == 32
+    order = np.argsort(color, kind="stable").astype(np.int32)
+    ref = oracle.SoftBodyOracle(dragon["tet_verts"], dragon["tet_ids"])
+    sb = new_body(dragon, solver="gs_color", arithmetic="bitexact")
+    assert sb.info()["numLevels"] == 32
+    for s in range(1, 101):
+        ref.simulate(DT600, order=order)
+        sb.simulate(DT600)
+        if s in (1, 10, 100):
+            assert_bit_equal(sb.pos, ref.pos, "pos @%d" % s)
+
+
+def test_gs_color_fast_within_tolerance(dragon):
+    color, _ = ts.greedy_colors(dragon["tet_ids"], 1234)
+    order = np.argsort(color, kind="stable").astype(np.int32)
+    ref = oracle.SoftBodyOracle(dragon["tet_verts"], dragon["tet_ids"])
+    sb = new_body(dragon, solver="gs_color", arithmetic="fast")
+    for _ in range(100):
+        ref.simulate(DT600, order=order)
+        sb.simulate(DT600)
+    assert vec_rel_err(sb.pos, ref.pos) <= TOL
+
+
+# ------------------------------------------------------------------------------------------------
+# Collision, bounds, friction, grab (src/Softbody.js:213-239, :279-298)
+# ------------------------------------------------------------------------------------------------
+def _low_dragon(dragon, shift=-0.44):
+    v = dragon["tet_verts"].reshape(-1, 3).copy()
+    v[:, 1] += np.float32(shift)
+    return dict(dragon, tet_verts=v.reshape(-1))
+
+
+def test_floor_friction_bounds_bitexact(dragon):
+    m = _low_dragon(dragon)
+    p = dict(ts.DEFAULT_PHYSICS_PARAMS, worldBounds=[-0.9, -1.0, -2.5, 0.8, 1.45, 0.3], friction=300.0)
+    ref = oracle.SoftBodyOracle(m["tet_verts"], m["tet_ids"], worldBounds=p["worldBounds"], friction=300.0)
+    sb = new_body(m, params=p, solver="gs_exact", arithmetic="bitexact")
+    touched = False
+    for s in range(60):
+        ref.simulate(DT600)
+        sb.simulate(DT600, p)
+        touched = touched or bool(np.any(ref.pos.reshape(-1, 3)[:, 1] == 0.0))
+    assert touched, "test must exercise floor contact"
+    assert_bit_equal(sb.pos, ref.pos, "pos")
+    assert_bit_equal(sb.vel, ref.vel, "vel")
+    fast = new_body(m, params=p, solver="gs_exact", arithmetic="fast")
+    for s in range(60):
+        fast.simulate(DT600, p)
+    assert vec_rel_err(fast.pos.reshape(-1, 3) + [0, 1, 0], ref.pos.reshape(-1, 3) + [0, 1, 0]) <= 5e-4
+
+
+def test_grab_bitexact(dragon):
+    ref = oracle.SoftBodyOracle(dragon["tet_verts"], dragon["tet_ids"])
+    sb = new_body(dragon, solver="gs_exact", arithmetic="bitexact")
+    for _ in range(3):
+        ref.simulate(DT600)
+        sb.simulate(DT600)
+    target = {"x": 0.31, "y": 1.62, "z": 0.07}
+    ref.startGrab([target["x"], target["y"], target["z"]])
+    sb.startGrab(target)
+    assert sb.grabId == ref.grabId >= 0
+    for k in range(10):
+        q = [0.31 + 0.01 * k, 1.62 + 0.02 * k, 0.07]
+        ref.moveGrabbed(q)
+        sb.moveGrabbed(q)
+        ref.simulate(DT600)
+        sb.simulate(DT600)
+    assert_bit_equal(sb.pos, ref.pos, "pos during grab")
+    ref.endGrab()
+    sb.endGrab()
+    assert sb.grabId == -1
+    for _ in range(3):
+        ref.simulate(DT600)
+        sb.simulate(DT600)
+    assert_bit_equal(sb.pos, ref.pos, "pos after release")
+
+
+def test_nearest_vertex_ties_and_far_points(dragon):
+    sb = new_body(dragon)
+    pos = sb.pos.reshape(-1, 3).astype(np.float64)
+    rng = np.random.default_rng(7)
+    for _ in range(20):
+        p = rng.uniform(-2, 2, 3) + [0, 1, 0]
+        sb.startGrab(p)
+        d2 = ((p - pos) ** 2)
+        d2 = d2[:, 0] + d2[:, 1] + d2[:, 2]
+        assert sb.grabId == int(np.argmin(d2))
+    sb.startGrab(pos[77])           # exactly on a vertex
+    assert sb.grabId == 77
+
+
+# ------------------------------------------------------------------------------------------------
+# Several bodies in one handle (BASELINE config 5, scaled down): one CTA per body
+# ------------------------------------------------------------------------------------------------
+def test_tiled_dragons_bitexact(dragon):
+    v, t = mesh.tile_bodies(dragon["tet_verts"], dragon["tet_ids"], 3, 2, y_shift=-0.40)
+    wb = list(mesh.wide_bounds(64.0))
+    p = dict(ts.DEFAULT_PHYSICS_PARAMS, worldBounds=wb)
+    ref = oracle.SoftBodyOracle(v, t, worldBounds=wb)
+    sb = ts.SoftBody(v, t, None, p, solver="gs_exact", arithmetic="bitexact")
+    info = sb.info()
+    assert info["numComponents"] == 6 and info["bodyKernel"] == 1 and info["launchesPerSubstep"] == 1
+    for _ in range(80):  # floor contact starts around substep 63
+        ref.simulate(DT600)
+        sb.simulate(DT600, p)
+    assert np.any(ref.pos.reshape(-1, 3)[:, 1] == 0.0)
+    assert_bit_equal(sb.pos, ref.pos, "tiled pos")
+    assert sb.volError == ref.volError
+
+
+def test_interleaved_bodies_are_renumbered(dragon):
+    """Bodies whose vertices interleave in the caller's numbering exercise the internal permutation."""
+    v1 = dragon["tet_verts"].reshape(-1, 3)
+    t1 = dragon["tet_ids"].reshape(-1, 4)
+    n = len(v1)
+    v = np.empty((2 * n, 3), np.float32)
+    v[0::2] = v1
+    v[1::2] = v1 + np.float32([3.0, 0.25, 0.0])
+    t = np.concatenate([2 * t1, 2 * t1[::-1] + 1]).astype(np.int32)
+    wb = list(mesh.wide_bounds(16.0))
+    p = dict(ts.DEFAULT_PHYSICS_PARAMS, worldBounds=wb)
+    ref = oracle.SoftBodyOracle(v, t, worldBounds=wb)
+    sb = ts.SoftBody(v, t, None, p, solver="gs_exact", arithmetic="bitexact")
+    assert sb.info()["numComponents"] == 2
+    sb.startGrab([3.1, 1.5, 0.0])
+    ref.startGrab([3.1, 1.5, 0.0])
+    assert sb.grabId == ref.grabId
+    for _ in range(10):
+        ref.simulate(DT600)
+        sb.simulate(DT600, p)
+    assert_bit_equal(sb.pos, ref.pos, "interleaved pos")
+    assert_bit_equal(sb.vel, ref.vel, "interleaved vel")
+
+
+# ------------------------------------------------------------------------------------------------
+# Jacobi Neo-Hookean (BASELINE config 4 semantics)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("iters", [1, 4])
+def test_jacobi_gather_bitexact(dragon, iters):
+    ref = oracle.SoftBodyOracle(dragon["tet_verts"], dragon["tet_ids"])
+    sb = new_body(dragon, solver="jacobi", arithmetic="bitexact", iters=iters)
+    for s in range(1, 51):
+        ref.simulate_jacobi(DT1200, iters)
+        sb.simulate(DT1200)
+        if s in (1, 10, 50):
+            assert_bit_equal(sb.pos, ref.pos, "pos @%d" % s)
+            assert sb.volError == ref.volError
+
+
+@pytest.mark.parametrize("cluster_size,reorder,deterministic", [(256, True, True), (128, False, True), (512, True, True),
+                                                               (256, True, False)])
+def test_jacobi_clustered_within_tolerance(dragon, cluster_size, reorder, deterministic):
+    ref = oracle.SoftBodyOracle(dragon["tet_verts"], dragon["tet_ids"])
+    sb = new_body(dragon, solver="jacobi", arithmetic="fast", cluster_size=cluster_size, reorder=reorder,
+                  deterministic=deterministic, track_vol_error=True)
+    for _ in range(100):
+        ref.simulate_jacobi(DT1200, 1)
+        sb.simulate(DT1200)
+    err = vec_rel_err(sb.pos, ref.pos)
+    assert err <= TOL, err
+    assert vec_rel_err(sb.prevPos, ref.prevPos) <= TOL
+    assert np.max(np.abs(sb.vel - ref.vel)) <= 2e-2
+    assert abs(sb.volError - ref.volError) < 1e-4
+
+
+def test_jacobi_clustered_step_fusion_and_determinism(dragon):
+    """Inside tetsim_step the post of substep s is fused with the predict of s+1; results must match
+    the unfused call-per-substep sequence, and two runs must agree bit for bit (no atomics)."""
+    p = dict(ts.DEFAULT_PHYSICS_PARAMS, numSubsteps=20)
+    a = new_body(dragon, params=p, solver="jacobi", iters=2)
+    b = new_body(dragon, params=p, solver="jacobi", iters=2)
+    c = new_body(dragon, params=p, solver="jacobi", iters=2)
+    for _ in range(3):
+        a.step(p)
+        c.step(p)
+        for _ in range(20):
+            b.simulate(DT1200, p)
+    assert_bit_equal(a.pos, c.pos, "run-to-run")
+    assert_bit_equal(a.vel, c.vel, "run-to-run vel")
+    assert vec_rel_err(a.pos, b.pos) <= 1e-5
+    ref = oracle.SoftBodyOracle(dragon["tet_verts"], dragon["tet_ids"])
+    for _ in range(60):
+        ref.simulate_jacobi(DT1200, 2)
+    assert vec_rel_err(a.pos, ref.pos) <= TOL
+
+
+def test_jacobi_clustered_beam_with_floor():
+    v, t = mesh.make_beam((24, 6, 6), h=0.05, y0=0.02, jitter=0.2)
+    p = dict(ts.DEFAULT_PHYSICS_PARAMS)
+    ref = oracle.SoftBodyOracle(v, t)
+    sb = ts.SoftBody(v, t, None, p, solver="jacobi", cluster_size=128)
+    for _ in range(100):
+        ref.simulate_jacobi(DT1200, 1)
+        sb.simulate(DT1200)
+    assert np.any(ref.pos.reshape(-1, 3)[:, 1] == 0.0)
+    assert vec_rel_err(sb.pos.reshape(-1, 3) + [0, 1, 0], ref.pos.reshape(-1, 3) + [0, 1, 0]) <= TOL
+
+
+# ------------------------------------------------------------------------------------------------
+# Polar-decomposition shape matching, the WebGL variant (BASELINE config 2)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bug", [True, False])
+def test_polar_bitexact(dragon, bug):
+    ref = oracle.PolarOracle(dragon["tet_verts"], dragon["tet_ids"], reference_table_bug=bug)
+    sb = new_body(dragon, cls=ts.SoftBodyGPU, arithmetic="bitexact", reference_table_bug=bug)
+    for s in range(1, 101):
+        ref.simulate(DT1200)
+        sb.simulate(DT1200)
+        if s in (1, 10, 100):
+            # sin() goes through double on both sides; a last-bit difference of the two libm's is
+            # possible in principle, so allow a 1e-6 escape hatch but report exactness
+            if not np.array_equal(sb.pos, ref.pos):
+                assert vec_rel_err(sb.pos, ref.pos) <= 1e-6, "polar @%d" % s
+    assert_bit_equal(sb.quats, ref.quat, "quats")
+    assert_bit_equal(sb.pos, ref.pos, "pos @100")
+    assert_bit_equal(sb.vel, ref.vel, "vel @100")
+    assert_bit_equal(sb.elems, ref.rest, "elems @100")
+
+
+def test_polar_fast_within_tolerance(dragon):
+    ref = oracle.PolarOracle(dragon["tet_verts"], dragon["tet_ids"])
+    sb = new_body(dragon, cls=ts.SoftBodyGPU, arithmetic="fast")
+    errs = {}
+    for s in range(1, 101):
+        ref.simulate(DT1200)
+        sb.simulate(DT1200)
+        if s in (50, 100):
+            errs[s] = vec_rel_err(sb.pos, ref.pos)
+    # this variant amplifies rounding (f32-vs-f64 1.7e-4 @100 substeps)
+    assert errs[50] <= 1e-4 and errs[100] <= 1e-3, errs
+
+
+def test_polar_long_run_with_contact(dragon):
+    m = _low_dragon(dragon, -0.40)
+    ref = oracle.PolarOracle(m["tet_verts"], m["tet_ids"])
+    sb = new_body(m, cls=ts.SoftBodyGPU, arithmetic="bitexact")
+    p = dict(ts.DEFAULT_PHYSICS_PARAMS, numSubsteps=20)
+    for _ in range(15):
+        for _ in range(20):
+            ref.simulate(DT1200)
+        sb.step(p)
+    assert np.any(ref.pos.reshape(-1, 3)[:, 1] == 0.0)
+    assert vec_rel_err(sb.pos.reshape(-1, 3) + [0, 1, 0], ref.pos.reshape(-1, 3) + [0, 1, 0]) <= 1e-6
+
+
+# ------------------------------------------------------------------------------------------------
+# State I/O, skinning, errors
+# ------------------------------------------------------------------------------------------------
+def test_checkpoint_resume(dragon):
+    a = new_body(dragon, solver="gs_exact", arithmetic="bitexact")
+    for _ in range(7):
+        a.simulate(DT600)
+    pos, prev, vel = a.pos.copy(), a.prevPos.copy(), a.vel.copy()
+    b = new_body(dragon, solver="gs_exact", arithmetic="bitexact")
+    b.set_state(pos, prev, vel)
+    assert_bit_equal(b.pos, pos, "roundtrip pos")
+    assert_bit_equal(b.vel, vel, "roundtrip vel")
+    for _ in range(5):
+        a.simulate(DT600)
+        b.simulate(DT600)
+    assert_bit_equal(a.pos, b.pos, "resume")
+
+
+def test_skinning_and_normals(dragon):
+    ref = oracle.SoftBodyOracle(dragon["tet_verts"], dragon["tet_ids"])
+    sb = ts.SoftBody(dragon["tet_verts"], dragon["tet_ids"], dragon["tet_edge_ids"], None, dragon["vis_verts"],
+                     dragon["vis_tri_ids"], None, solver="gs_exact", arithmetic="bitexact")
+    for _ in range(5):
+        ref.simulate(DT600)
+        sb.simulate(DT600)
+    sb.endFrame()
+    skinned = oracle.skin(dragon["vis_verts"], dragon["tet_ids"], ref.pos)
+    assert_bit_equal(sb.visMesh.positions, skinned, "skinned positions")
+    assert_bit_equal(sb.visMesh.normals, oracle.vertex_normals(skinned, dragon["vis_tri_ids"]), "normals")
+    assert_bit_equal(sb.edgeMesh.positions, ref.pos, "edge mesh")
+    fast = ts.SoftBody(dragon["tet_verts"], dragon["tet_ids"], None, None, dragon["vis_verts"], dragon["vis_tri_ids"])
+    fast.set_state(ref.pos, ref.prevPos, ref.vel)
+    fast.updateVisMesh()
+    assert np.max(np.abs(fast.visMesh.positions - skinned)) < 1e-6
+
+
+def test_errors_are_loud(dragon):
+    v, t = dragon["tet_verts"], dragon["tet_ids"].copy()
+    t[5] = 99999
+    with pytest.raises(ts.TetSimError) as e:
+        ts.SoftBody(v, t, None, None)
+    assert e.value.code == -1
+    t = dragon["tet_ids"].copy()
+    t[4] = t[5]
+    with pytest.raises(ts.TetSimError):
+        ts.SoftBody(v, t, None, None)
+    with pytest.raises(ts.TetSimError):
+        ts.SoftBody(v, dragon["tet_ids"], None, None, solver="gs_exact", world_size=2, rank=0)
+    sb = ts.SoftBodyGPU(v, dragon["tet_ids"], None, dict(ts.DEFAULT_PHYSICS_PARAMS))
+    with pytest.raises(ts.TetSimError):
+        _ = sb.volError
+
+
+def test_free_vertices_and_empty_mesh():
+    """Vertices no tet references still integrate and collide (src/Softbody.js:198-202 has no test)."""
+    v = np.array([0, 1, 0, 1, 1, 0, 0, 2, 0, 0, 1, 1, 0.5, 0.004, 0.5], np.float32)
+    t = np.array([0, 1, 2, 3], np.int32)
+    for solver, arith in (("gs_exact", "bitexact"), ("jacobi", "bitexact")):
+        ref = oracle.SoftBodyOracle(v, t)
+        sb = ts.SoftBody(v, t, None, None, solver=solver, arithmetic=arith)
+        for _ in range(40):
+            if solver == "jacobi":
+                ref.simulate_jacobi(DT600, 1)
+            else:
+                ref.simulate(DT600)
+            sb.simulate(DT600)
+        assert ref.pos[13] == 0.0
+        assert_bit_equal(sb.pos, ref.pos, solver)
+    fast = ts.SoftBody(v, t, None, None, solver="jacobi")
+    ref = oracle.SoftBodyOracle(v, t)
+    for _ in range(40):
+        ref.simulate_jacobi(DT600, 1)
+        fast.simulate(DT600)
+    assert np.max(np.abs(fast.pos - ref.pos)) < 1e-5
+    empty = ts.SoftBody(v, np.zeros(0, np.int32), None, None)
+    empty.simulate(DT600)
+    assert empty.pos[1] < 1.0

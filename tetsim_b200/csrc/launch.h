@@ -1,0 +1,95 @@
+// launch.h -- host-callable launchers for the kernels in kernels.cuh.  Each arithmetic flavour
+// lives in its own translation unit (kernels_exact.cu is built with -fmad=false) and exports one
+// table of launchers; the host code picks a table once at create time.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tsim {
+
+struct SubstepParams;
+// One connected component ("body") of the mesh for the one-CTA-per-body Gauss-Seidel kernel.
+struct BodyDesc {
+    int vertBegin, vertEnd;    // body's vertex range (internal numbering)
+    int tetBegin;              // first record of the body in the level-sorted stream
+    int levelBegin, levelEnd;  // range into levelStart[] (record offsets into the stream)
+};
+
+struct KernelTable {
+    void (*init_tets)(cudaStream_t, int M, const float4 *x4, const int4 *ids, double density, float *Q9, float *irv,
+                      double *pm);
+    void (*init_mass)(cudaStream_t, int N, const int *cStart, const int *cEnt, const double *pm, float4 *x4);
+    void (*predict)(cudaStream_t, int N, float4 *x4, float4 *prev4, float4 *vel4, const SubstepParams *sp);
+    void (*post)(cudaStream_t, int N, float4 *x4, const float4 *prev4, float4 *vel4, const SubstepParams *sp,
+                 const int *vertId);
+    void (*gs_level)(cudaStream_t, int begin, int end, float4 *x4, const int4 *I, const float4 *A, const float4 *B,
+                     const float4 *C, const int *order, double *volTerm, const SubstepParams *sp);
+    void (*gs_body)(cudaStream_t, int numBodies, int threads, size_t smemBytes, const BodyDesc *bodies,
+                    const int *levelStart, float4 *x4, float4 *prev4, float4 *vel4, const int4 *I, const float4 *A,
+                    const float4 *B, const float4 *C, const int *order, double *volTerm, const SubstepParams *sp,
+                    const int *vertId);
+    int (*gs_body_max_smem)();
+    void (*jacobi_tet)(cudaStream_t, int M, const float4 *x4, const int4 *I, const float4 *A, const float4 *B,
+                       const float4 *C, float4 *dx, double *volTerm, const SubstepParams *sp);
+    void (*jacobi_gather)(cudaStream_t, int N, float4 *x4, const int *cStart, const int *cEnt, const float4 *dx);
+    void (*polar_integrate)(cudaStream_t, int N, float4 *x4, float4 *prev4, const float4 *vel4,
+                            const SubstepParams *sp);
+    void (*polar_tet)(cudaStream_t, int M, const float4 *x4, const int4 *I, float4 *rest, float4 *quat);
+    void (*polar_vertex)(cudaStream_t, int N, float4 *x4, const float4 *prev4, float4 *vel4, const int *tStart,
+                         const int *tEnt, const float4 *rest, const SubstepParams *sp);
+    void (*skin)(cudaStream_t, int nVis, const float4 *vis, const int4 *ids, const float4 *x4, float *out);
+    void (*normals)(cudaStream_t, int nVis, const float *pos, const int *tri, const int *vtStart, const int *vtEnt,
+                    float *nrm);
+};
+
+const KernelTable *exact_kernels();
+const KernelTable *fast_kernels();
+
+// ---- FAST-only throughput path: clustered Jacobi (kernels_fast.cu) ----
+struct ClusterArgs {
+    const float4 *x4;
+    const float4 *A, *B, *C;        // tet stream, cluster-major, clusterSize records per cluster
+    const int *clVertStart;         // [numClusters + 1] offsets into clVerts / clVal / part
+    const int *clVerts;             // tile vertex list (handle-local vertex ids), descending tile valence
+    const uint8_t *clVal;           // tile valence of each tile vertex
+    const uint16_t *jds;            // [numClusters * 4 * clusterSize] corner lists, jagged-diagonal order
+    const uint16_t *colOff;         // [numClusters * colStride] column offsets of the jagged diagonals
+    int colStride;
+    float4 *part;                   // per-tile partial dx sums (deterministic flush), parallel to clVerts
+    float4 *acc;                    // global accumulator (atomic flush), or NULL
+    double *volAcc;                 // sum over tets of det F - 1, or NULL
+    const SubstepParams *sp;
+    int maxTileVerts;
+};
+void launch_jacobi_cluster(cudaStream_t, int clusterSize, int firstCluster, int numClusters, const ClusterArgs &a);
+size_t jacobi_cluster_smem(int clusterSize, int maxTileVerts, int colStride);
+
+struct ApplyArgs {
+    float4 *x4, *prev4, *vel4;
+    const int *vpStart, *vpSlot;    // vertex -> partial-sum slots (CSR into part[])
+    const float4 *part;
+    float4 *acc;                    // atomic-flush accumulator (read and re-zeroed) or NULL
+    const float *invVal;            // 1 / valence
+    const float4 *bsum;             // all-reduced boundary sums for vertices >= boundaryBegin, or NULL
+    int boundaryBegin;
+    const SubstepParams *sp;
+    const int *vertId;              // handle-local -> caller's vertex id (for the grab test)
+};
+// mode: 0 = apply only, 1 = apply + post, 2 = apply + post + predict of the next substep
+void launch_jacobi_apply(cudaStream_t, int begin, int end, int mode, const ApplyArgs &a);
+// boundary vertices: bsum[b] = sum of this rank's partials (input of the all-reduce)
+void launch_boundary_pack(cudaStream_t, int boundaryBegin, int numBoundary, const int *vpStart, const int *vpSlot,
+                          const float4 *part, float4 *bsum);
+
+// ---- utility kernels (kernels_fast.cu) ----
+void launch_pack3(cudaStream_t, int N, const float4 *src, const int *perm, float *dst3);       // dst[perm[i]] = src[i].xyz
+void launch_unpack3(cudaStream_t, int N, const float *src3, const int *perm, float4 *dst, int keepW);
+void launch_sum_sequential(cudaStream_t, int M, const double *terms, double *out);             // out = (sum in index order) / M
+void launch_nearest_vertex(cudaStream_t, int N, const float4 *x4, const int *vertId, const double *p3, int *outId,
+                           unsigned long long *scratch);
+void launch_fill_rest(cudaStream_t, int M, const float4 *x4, const int4 *I, const float *irv, float4 *rest,
+                      float4 *quat);
+void launch_build_stream(cudaStream_t, int count, const int *order, const float *Q9, const float *irv, float4 *A,
+                         float4 *B, float4 *C);
+
+}  // namespace tsim

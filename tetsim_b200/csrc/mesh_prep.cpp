@@ -1,0 +1,294 @@
+// mesh_prep.cpp -- see mesh_prep.h.
+#include "mesh_prep.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+namespace tsim {
+
+CornerTable build_corner_table(int numVerts, int numTets, const int *tetIds) {
+    CornerTable t;
+    t.start.assign((size_t)numVerts + 1, 0);
+    const size_t nc = 4 * (size_t)numTets;
+    for (size_t c = 0; c < nc; c++) t.start[(size_t)tetIds[c] + 1]++;
+    for (int v = 0; v < numVerts; v++) {
+        t.maxValence = std::max(t.maxValence, t.start[v + 1]);
+        t.start[v + 1] += t.start[v];
+    }
+    t.ent.resize(nc);
+    std::vector<int> fill(t.start.begin(), t.start.end() - 1);
+    for (size_t c = 0; c < nc; c++) t.ent[fill[tetIds[c]]++] = (int)c;  // c = 4*tet + corner, ascending
+    return t;
+}
+
+CornerTable build_reference_table(int numVerts, int numTets, const int *tetIds, bool referenceBug, int capacity) {
+    // Per vertex the reference scans its 36 slots for the first value <= 0.0 (src/SoftbodyGPU.js:566-573).
+    // Only the encoded value 0 (tet 0, corner 0) can be non-negative and still "free"; it can sit in
+    // exactly one vertex's list, so the general rule reduces to: append, except that vertex's slot
+    // holding 0 is reused once.
+    std::vector<std::vector<int>> lists((size_t)numVerts);
+    for (int e = 0; e < numTets; e++)
+        for (int k = 0; k < 4; k++) {
+            std::vector<int> &L = lists[tetIds[4 * (size_t)e + k]];
+            const int v = 4 * e + k;
+            size_t slot = L.size();
+            if (referenceBug)
+                for (size_t j = 0; j < L.size(); j++)
+                    if (L[j] <= 0) { slot = j; break; }
+            if (capacity > 0 && slot >= (size_t)capacity) continue;
+            if (slot == L.size()) L.push_back(v);
+            else L[slot] = v;
+        }
+    CornerTable t;
+    t.start.assign((size_t)numVerts + 1, 0);
+    for (int v = 0; v < numVerts; v++) {
+        t.start[v + 1] = t.start[v] + (int)lists[v].size();
+        t.maxValence = std::max(t.maxValence, (int)lists[v].size());
+    }
+    t.ent.reserve((size_t)t.start[numVerts]);
+    for (int v = 0; v < numVerts; v++) t.ent.insert(t.ent.end(), lists[v].begin(), lists[v].end());
+    return t;
+}
+
+int connected_components(int numVerts, int numTets, const int *tetIds, std::vector<int> &vertComp) {
+    std::vector<int> parent((size_t)numVerts);
+    std::iota(parent.begin(), parent.end(), 0);
+    auto find = [&](int a) {
+        while (parent[a] != a) { parent[a] = parent[parent[a]]; a = parent[a]; }
+        return a;
+    };
+    for (int e = 0; e < numTets; e++) {
+        int r = find(tetIds[4 * (size_t)e]);
+        for (int k = 1; k < 4; k++) {
+            int s = find(tetIds[4 * (size_t)e + k]);
+            if (s != r) { if (s < r) std::swap(s, r); parent[s] = r; }  // smallest vertex id is the root
+        }
+    }
+    vertComp.assign((size_t)numVerts, -1);
+    int count = 0;
+    for (int v = 0; v < numVerts; v++) {  // roots are met before their members: components numbered by first vertex
+        int r = find(v);
+        if (vertComp[r] < 0) vertComp[r] = count++;
+        vertComp[v] = vertComp[r];
+    }
+    return count;
+}
+
+int level_schedule(int numVerts, int numTets, const int *tetIds, int *level) {
+    std::vector<int> last((size_t)numVerts, -1);
+    int maxLevel = -1;
+    for (int e = 0; e < numTets; e++) {
+        const int *t = tetIds + 4 * (size_t)e;
+        int lv = 1 + std::max(std::max(last[t[0]], last[t[1]]), std::max(last[t[2]], last[t[3]]));
+        level[e] = lv;
+        last[t[0]] = last[t[1]] = last[t[2]] = last[t[3]] = lv;
+        maxLevel = std::max(maxLevel, lv);
+    }
+    return maxLevel + 1;
+}
+
+int greedy_colors(int numVerts, int numTets, const int *tetIds, int *color) {
+    struct Mask { uint64_t w[4]; };
+    std::vector<Mask> used((size_t)numVerts, Mask{{0, 0, 0, 0}});
+    int numColors = 0;
+    for (int e = 0; e < numTets; e++) {
+        const int *t = tetIds + 4 * (size_t)e;
+        int c = -1;
+        for (int w = 0; w < 4 && c < 0; w++) {
+            uint64_t m = used[t[0]].w[w] | used[t[1]].w[w] | used[t[2]].w[w] | used[t[3]].w[w];
+            if (~m) c = 64 * w + __builtin_ctzll(~m);
+        }
+        if (c < 0) return -1;
+        color[e] = c;
+        for (int k = 0; k < 4; k++) used[t[k]].w[c >> 6] |= 1ull << (c & 63);
+        numColors = std::max(numColors, c + 1);
+    }
+    return numColors;
+}
+
+static inline uint64_t spread21(uint64_t x) {  // 21 bits -> every third bit
+    x &= 0x1fffffull;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
+std::vector<int> morton_order(int numVerts, int numTets, const float *verts, const int *tetIds) {
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int v = 0; v < numVerts; v++)
+        for (int c = 0; c < 3; c++) {
+            float x = verts[3 * (size_t)v + c];
+            if (x == x) { lo[c] = std::min(lo[c], x); hi[c] = std::max(hi[c], x); }
+        }
+    // one cubic cell size for all axes so the curve follows the shape of the domain
+    double ext = 0.0;
+    for (int c = 0; c < 3; c++) ext = std::max(ext, (double)hi[c] - (double)lo[c]);
+    const double scale = ext > 0.0 ? (double)((1 << 21) - 1) / ext : 0.0;
+    std::vector<std::pair<uint64_t, int>> keys((size_t)numTets);
+    for (int e = 0; e < numTets; e++) {
+        const int *t = tetIds + 4 * (size_t)e;
+        uint64_t q[3];
+        for (int c = 0; c < 3; c++) {
+            double m = 0.25 * ((double)verts[3 * (size_t)t[0] + c] + (double)verts[3 * (size_t)t[1] + c] +
+                               (double)verts[3 * (size_t)t[2] + c] + (double)verts[3 * (size_t)t[3] + c]);
+            double g = (m - (double)lo[c]) * scale;
+            q[c] = (g == g && g > 0.0) ? (uint64_t)std::min(g, (double)((1 << 21) - 1)) : 0;
+        }
+        keys[e] = {spread21(q[0]) | spread21(q[1]) << 1 | spread21(q[2]) << 2, e};
+    }
+    std::sort(keys.begin(), keys.end());  // ties broken by tet index
+    std::vector<int> order((size_t)numTets);
+    for (int e = 0; e < numTets; e++) order[e] = keys[e].second;
+    return order;
+}
+
+bool build_cluster_plan(int numVerts, int numTets, const int *tetIds, const std::vector<int> &order, int T, int rank,
+                        int worldSize, ClusterPlan &P, std::string &err) {
+    P = ClusterPlan();
+    P.T = T;
+    const int totalClusters = (numTets + T - 1) / T;
+    auto firstClusterOf = [&](int r) { return (int)((int64_t)totalClusters * r / worldSize); };
+    const int c0 = firstClusterOf(rank), c1 = firstClusterOf(rank + 1);
+    P.numClusters = c1 - c0;
+
+    // global valence and rank-shared (boundary) vertices
+    std::vector<int> valence((size_t)numVerts, 0);
+    std::vector<int> rmin, rmax;
+    if (worldSize > 1) { rmin.assign((size_t)numVerts, worldSize); rmax.assign((size_t)numVerts, -1); }
+    {
+        int r = 0;
+        for (int pos = 0; pos < numTets; pos++) {
+            if (worldSize > 1) {
+                int cl = pos / T;
+                while (cl >= firstClusterOf(r + 1)) r++;
+            }
+            const int *t = tetIds + 4 * (size_t)order[pos];
+            for (int k = 0; k < 4; k++) {
+                valence[t[k]]++;
+                if (worldSize > 1) { rmin[t[k]] = std::min(rmin[t[k]], r); rmax[t[k]] = std::max(rmax[t[k]], r); }
+            }
+        }
+    }
+    for (int v = 0; v < numVerts; v++) P.maxValence = std::max(P.maxValence, valence[v]);
+
+    // local numbering: interior vertices by first touch along the tile sequence, then every boundary vertex
+    std::vector<int> local((size_t)numVerts, -1);
+    std::vector<int> boundary;
+    if (worldSize > 1)
+        for (int v = 0; v < numVerts; v++)
+            if (rmax[v] > rmin[v]) boundary.push_back(v);
+    P.numBoundary = (int)boundary.size();
+    const int posBegin = c0 * T, posEnd = std::min(numTets, c1 * T);
+    P.localTets = std::max(0, posEnd - posBegin);
+    for (int v : boundary) local[v] = -2;
+    int nI = 0;
+    for (int pos = posBegin; pos < posEnd; pos++) {
+        const int *t = tetIds + 4 * (size_t)order[pos];
+        for (int k = 0; k < 4; k++)
+            if (local[t[k]] == -1) { local[t[k]] = nI++; P.localToCaller.push_back(t[k]); }
+    }
+    // vertices no tet references still fall and collide in the reference (src/Softbody.js:198-202 has
+    // no valence test): keep them resident (rank 0 of a multi-GPU job), with no correction to apply
+    if (rank == 0)
+        for (int v = 0; v < numVerts; v++)
+            if (valence[v] == 0) { local[v] = nI++; P.localToCaller.push_back(v); }
+    P.numInterior = nI;
+    for (size_t b = 0; b < boundary.size(); b++) { local[boundary[b]] = nI + (int)b; P.localToCaller.push_back(boundary[b]); }
+    P.numLocalVerts = nI + P.numBoundary;
+    P.invValence.resize((size_t)P.numLocalVerts);
+    for (int i = 0; i < P.numLocalVerts; i++) {
+        int val = valence[P.localToCaller[i]];
+        P.invValence[i] = val > 0 ? 1.0f / (float)val : 0.0f;
+    }
+
+    // tiles
+    const size_t nRec = (size_t)P.numClusters * T;
+    P.recordTet.assign(nRec, -1);
+    P.recordSlots.assign(2 * nRec, 0u);
+    P.clVertStart.assign((size_t)P.numClusters + 1, 0);
+    P.jds.assign(4 * nRec, 0);
+    std::vector<int> stamp((size_t)P.numLocalVerts, -1), tileIdx((size_t)P.numLocalVerts, 0);
+    std::vector<int> tileVerts, tileVal, perm, rank_of;
+    std::vector<std::vector<uint16_t>> colOffs((size_t)P.numClusters);
+    std::vector<int> cornerStart, cornerFill;
+    std::vector<uint16_t> corners;
+    int maxTileVal = 0;
+    for (int c = 0; c < P.numClusters; c++) {
+        const int pb = (c0 + c) * T, pe = std::min(numTets, pb + T);
+        tileVerts.clear(); tileVal.clear();
+        for (int pos = pb; pos < pe; pos++) {
+            const int *t = tetIds + 4 * (size_t)order[pos];
+            P.recordTet[(size_t)c * T + (pos - pb)] = order[pos];
+            for (int k = 0; k < 4; k++) {
+                int lv = local[t[k]];
+                if (stamp[lv] != c) { stamp[lv] = c; tileIdx[lv] = (int)tileVerts.size(); tileVerts.push_back(lv); tileVal.push_back(0); }
+                tileVal[tileIdx[lv]]++;
+            }
+        }
+        const int nl = (int)tileVerts.size();
+        // sort tile vertices by descending tile valence (stable)
+        perm.resize(nl);
+        std::iota(perm.begin(), perm.end(), 0);
+        std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return tileVal[a] > tileVal[b]; });
+        rank_of.resize(nl);
+        for (int j = 0; j < nl; j++) rank_of[perm[j]] = j;
+        const int tv = nl ? tileVal[perm[0]] : 0;
+        if (tv > 255) { err = "a vertex has more than 255 tet corners inside one tile"; return false; }
+        maxTileVal = std::max(maxTileVal, tv);
+        P.clVertStart[c + 1] = P.clVertStart[c] + nl;
+        for (int j = 0; j < nl; j++) { P.clVerts.push_back(tileVerts[perm[j]]); P.clVal.push_back((uint8_t)tileVal[perm[j]]); }
+        P.maxTileVerts = std::max(P.maxTileVerts, nl);
+        // per-vertex corner lists (ascending 4*tetLocal + corner), then jagged-diagonal layout
+        cornerStart.assign((size_t)nl + 1, 0);
+        for (int j = 0; j < nl; j++) cornerStart[j + 1] = cornerStart[j] + tileVal[perm[j]];
+        cornerFill.assign(cornerStart.begin(), cornerStart.end() - 1);
+        corners.resize((size_t)cornerStart[nl]);
+        for (int pos = pb; pos < pe; pos++) {
+            const int *t = tetIds + 4 * (size_t)order[pos];
+            uint32_t s[4];
+            for (int k = 0; k < 4; k++) {
+                int j = rank_of[tileIdx[local[t[k]]]];
+                s[k] = (uint32_t)j;
+                corners[cornerFill[j]++] = (uint16_t)(4 * (pos - pb) + k);
+            }
+            size_t r = (size_t)c * T + (pos - pb);
+            P.recordSlots[2 * r] = s[0] | s[1] << 16;
+            P.recordSlots[2 * r + 1] = s[2] | s[3] << 16;
+        }
+        std::vector<uint16_t> &co = colOffs[c];
+        co.assign((size_t)tv + 1, 0);
+        uint16_t *jd = P.jds.data() + (size_t)c * 4 * T;
+        int off = 0;
+        for (int i = 0; i < tv; i++) {
+            co[i] = (uint16_t)off;
+            int cnt = 0;
+            while (cnt < nl && tileVal[perm[cnt]] > i) {  // vertices are valence-sorted: a prefix qualifies
+                jd[off + cnt] = corners[cornerStart[cnt] + i];
+                cnt++;
+            }
+            off += cnt;
+        }
+        co[tv] = (uint16_t)off;
+    }
+    P.colStride = ((maxTileVal + 1 + 7) / 8) * 8;
+    P.colOff.assign((size_t)P.numClusters * P.colStride, 0);
+    for (int c = 0; c < P.numClusters; c++)
+        std::copy(colOffs[c].begin(), colOffs[c].end(), P.colOff.begin() + (size_t)c * P.colStride);
+    if (P.maxTileVerts < 1) P.maxTileVerts = 1;
+
+    // vertex -> partial-sum slots, ascending tile order
+    P.vpStart.assign((size_t)P.numLocalVerts + 1, 0);
+    for (int v : P.clVerts) P.vpStart[(size_t)v + 1]++;
+    for (int i = 0; i < P.numLocalVerts; i++) P.vpStart[i + 1] += P.vpStart[i];
+    P.vpSlot.resize(P.clVerts.size());
+    std::vector<int> fill(P.vpStart.begin(), P.vpStart.end() - 1);
+    for (size_t s = 0; s < P.clVerts.size(); s++) P.vpSlot[fill[P.clVerts[s]]++] = (int)s;
+    return true;
+}
+
+}  // namespace tsim

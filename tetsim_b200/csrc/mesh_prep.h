@@ -1,0 +1,65 @@
+// mesh_prep.h -- host-side, once-per-mesh topology pre-pass (pure C++, no CUDA).
+// The reference's counterpart is the table builder in SoftBodyGPU.initPhysics
+// (src/SoftbodyGPU.js:553-577: forward tet->vertex table and the 9x4 reverse tables); graph
+// colouring is a README TODO there (README.md:25).  Everything numeric stays on the device.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace tsim {
+
+// vertex -> incident tet corners, encoded 4*tet + corner, ascending; CSR.
+struct CornerTable {
+    std::vector<int> start;  // numVerts + 1
+    std::vector<int> ent;    // 4 * numTets
+    int maxValence = 0;
+};
+CornerTable build_corner_table(int numVerts, int numTets, const int *tetIds);
+
+// The reference's reverse table semantics (src/SoftbodyGPU.js:559-577) as CSR: 36 slots per vertex,
+// a slot holding a value <= 0 counts as free, corners beyond the capacity are dropped.
+CornerTable build_reference_table(int numVerts, int numTets, const int *tetIds, bool referenceBug, int capacity);
+
+// Connected components over shared vertices.  comp[v] in [0, count); isolated vertices get their own.
+int connected_components(int numVerts, int numTets, const int *tetIds, std::vector<int> &vertComp);
+
+// Order-preserving dependency levels of the sequential sweep: level[j] = 1 + max level of any
+// earlier tet sharing a vertex (0-based levels returned).  Sweeping level by level is
+// bit-identical to the reference's in-order Gauss-Seidel loop (src/Softbody.js:207-208).
+int level_schedule(int numVerts, int numTets, const int *tetIds, int *level);
+
+// Greedy colouring in tet order: smallest colour not used by any earlier tet sharing a vertex.
+// Returns the number of colours, or -1 if more than 256 would be needed.
+int greedy_colors(int numVerts, int numTets, const int *tetIds, int *color);
+
+// Tets sorted along a Morton curve of their centroids (stable for equal keys).
+std::vector<int> morton_order(int numVerts, int numTets, const float *verts, const int *tetIds);
+
+// Tiling of a tet sequence into CTA tiles for the clustered Jacobi kernel.
+struct ClusterPlan {
+    int T = 0;                          // tets per tile
+    int numClusters = 0;                // tiles on this rank
+    int numLocalVerts = 0;              // interior + all boundary vertices
+    int numInterior = 0;
+    int numBoundary = 0;                // global count of rank-shared vertices (same on every rank)
+    std::vector<int> localToCaller;     // [numLocalVerts]
+    std::vector<int> recordTet;         // [numClusters * T] caller tet index, -1 = padding
+    std::vector<uint32_t> recordSlots;  // [numClusters * T * 2] packed 16-bit tile slots
+    std::vector<int> clVertStart;       // [numClusters + 1]
+    std::vector<int> clVerts;           // local vertex ids per tile, descending tile valence
+    std::vector<uint8_t> clVal;         // tile valence per tile vertex
+    std::vector<uint16_t> jds;          // [numClusters * 4T]
+    std::vector<uint16_t> colOff;       // [numClusters * colStride]
+    int colStride = 0;
+    int maxTileVerts = 0;
+    std::vector<int> vpStart, vpSlot;   // local vertex -> indices into the partial-sum array
+    std::vector<float> invValence;      // [numLocalVerts] 1 / GLOBAL valence
+    int localTets = 0;
+    int maxValence = 0;
+};
+// order: the global tet sequence (caller tet indices); rank/worldSize select a contiguous run of tiles.
+bool build_cluster_plan(int numVerts, int numTets, const int *tetIds, const std::vector<int> &order, int T, int rank,
+                        int worldSize, ClusterPlan &plan, std::string &err);
+
+}  // namespace tsim

@@ -1,0 +1,1014 @@
+// tetsim_capi.cu -- the C ABI of libtetsim_b200.so (include/tetsim_b200.h): handle, device state,
+// solver scheduling, CUDA-graph capture of the substep loop, multi-GPU exchange.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/tetsim_b200.h"
+#include "device_math.cuh"
+#include "launch.h"
+#include "mesh_prep.h"
+
+using namespace tsim;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(TETSIM_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + \
+                                           std::to_string(__LINE__) + ")");                              \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, loaded lazily (the library must load on hosts without it; a torch process already has
+// libnccl.so.2 mapped and dlopen returns that copy).
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct NcclUniqueId { char internal[128]; };
+typedef void *NcclComm;
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(NcclUniqueId *) = nullptr;
+    int (*CommInitRank)(NcclComm *, int, NcclUniqueId, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*CommDestroy)(NcclComm) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    std::string why;
+    bool load() {
+        if (lib) return true;
+        const char *env = getenv("TETSIM_NCCL_LIB");
+        const char *names[] = {env, "libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) {
+            if (!n) continue;
+            lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) { why = std::string("cannot dlopen libnccl.so.2: ") + dlerror(); return false; }
+        GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+        AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+        CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy || !GetErrorString) {
+            why = "libnccl is missing a required symbol";
+            lib = nullptr;
+            return false;
+        }
+        return true;
+    }
+};
+NcclApi g_nccl;
+constexpr int kNcclFloat = 7, kNcclSum = 0;
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc((void **)&p, count * sizeof(T));
+    }
+    cudaError_t upload(const std::vector<T> &h, cudaStream_t s) {
+        cudaError_t e = alloc(h.size());
+        if (e != cudaSuccess || h.empty()) return e;
+        return cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    size_t bytes() const { return n * sizeof(T); }
+};
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+struct tetsim {
+    TetSimOptions opt{};
+    TetSimParams params{};
+    int N = 0, M = 0;          // caller's mesh
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool ownStream = false;
+    const KernelTable *K = nullptr;   // flavour of the substep kernels
+    const KernelTable *KX = nullptr;  // exact flavour (init, skinning)
+
+    // vertex state in the handle's internal numbering
+    int nInt = 0;
+    DevBuf<float4> x4, prev4, vel4;
+    DevBuf<int> vertId;               // internal -> caller id; empty when identity
+    std::vector<int> h_vertId;
+
+    // caller-order rest data (initPhysics)
+    DevBuf<float> Q9, irv, invMass;
+    DevBuf<int4> ids;                 // caller tet order; vertex ids in INTERNAL numbering
+    DevBuf<int> cStart, cEnt;         // vertex -> corners (internal numbering), when the solver needs it
+
+    // solver streams
+    DevBuf<float4> A, B, C;
+    DevBuf<int4> I;
+    DevBuf<int> order, levelStart;
+    std::vector<int> h_levelStart;
+    DevBuf<BodyDesc> bodies;
+    int numLevels = 0, maxLevelSize = 0, numComponents = 1, numBodies = 0, bodyThreads = 0;
+    size_t bodySmem = 0;
+    bool bodyKernel = false;
+    DevBuf<double> volTerm, volOut;
+    bool trackVol = false;
+    // Jacobi gather path
+    DevBuf<float4> dx;
+    // Jacobi cluster path
+    ClusterPlan plan;
+    DevBuf<int> clVertStart, clVerts, vpStart, vpSlot;
+    DevBuf<uint8_t> clVal;
+    DevBuf<uint16_t> jds, colOff;
+    DevBuf<float4> part, acc, bsum;
+    DevBuf<float> invVal;
+    bool clustered = false;
+    // polar
+    DevBuf<float4> rest, quat;
+    DevBuf<int> tStart, tEnt;
+    // per-launch parameters, staging, grab
+    DevBuf<SubstepParams> sp;
+    DevBuf<float> stage3;
+    DevBuf<double> grabP;
+    DevBuf<int> grabOut;
+    DevBuf<unsigned long long> grabScratch;
+    int grabId = -1;
+    double grabPos[3] = {0, 0, 0};
+    // skinning cache
+    DevBuf<float4> visV;
+    DevBuf<int> visTri, vtStart, vtEnt;
+    DevBuf<float> visPos, visNrm;
+    const void *visKeyV = nullptr, *visKeyT = nullptr;
+    int visN = 0, visT = 0;
+    // graphs
+    std::map<int, cudaGraphExec_t> graphs;
+    std::map<int, int64_t> graphLaunches;   // kernels inside each captured graph
+    int64_t enq = 0;                        // kernels enqueued by the enqueue_substeps call in progress
+    int64_t totalLaunches = 0;              // kernels launched by simulate/step since create
+    int launchesPerSubstep = 0;
+    // multi-GPU
+    NcclComm comm = nullptr;
+    int maxValence = 0;
+
+    int64_t deviceBytes() const {
+        return (int64_t)(x4.bytes() + prev4.bytes() + vel4.bytes() + vertId.bytes() + Q9.bytes() + irv.bytes() +
+                         invMass.bytes() + ids.bytes() + cStart.bytes() + cEnt.bytes() + A.bytes() + B.bytes() +
+                         C.bytes() + I.bytes() + order.bytes() + levelStart.bytes() + bodies.bytes() +
+                         volTerm.bytes() + dx.bytes() + clVertStart.bytes() + clVerts.bytes() + vpStart.bytes() +
+                         vpSlot.bytes() + clVal.bytes() + jds.bytes() + colOff.bytes() + part.bytes() + acc.bytes() +
+                         bsum.bytes() + invVal.bytes() + rest.bytes() + quat.bytes() + tStart.bytes() + tEnt.bytes() +
+                         stage3.bytes() + visV.bytes() + visTri.bytes() + vtStart.bytes() + vtEnt.bytes() +
+                         visPos.bytes() + visNrm.bytes());
+    }
+};
+
+namespace {
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+void fill_substep_params(SubstepParams &s, double dt, const TetSimParams &p, int grabId, const double grab[3]) {
+    memset(&s, 0, sizeof(s));
+    s.dt = dt; s.gravity = p.gravity; s.friction = p.friction;
+    s.devCompliance = p.devCompliance; s.volCompliance = p.volCompliance;
+    for (int c = 0; c < 3; c++) { s.lo[c] = p.worldBounds[c]; s.hi[c] = p.worldBounds[3 + c]; s.grab[c] = grab[c]; }
+    s.grabId = grabId;
+    s.dtF = (float)dt;
+    s.gDt = (float)(p.gravity * dt);
+    s.invDt = (float)(1.0 / dt);
+    double k = dt * p.friction;
+    s.fric = (float)(k < 1.0 ? k : 1.0);
+    s.alphaDev = (float)(p.devCompliance / dt / dt);
+    s.alphaVol = (float)(p.volCompliance / dt / dt);
+    s.gammaVol = (float)(1.0 + p.volCompliance / p.devCompliance);
+    s.gravityF = (float)p.gravity;
+    s.frictionF = (float)p.friction;
+    for (int c = 0; c < 3; c++) { s.loF[c] = (float)p.worldBounds[c]; s.hiF[c] = (float)p.worldBounds[3 + c]; s.grabF[c] = (float)grab[c]; }
+}
+
+// ---- solver builders -----------------------------------------------------------------------------
+
+// Gauss-Seidel schedules (EXACT levels or greedy colours).
+int build_gs(tetsim *h, const std::vector<float> &verts, const std::vector<int> &tetIds) {
+    const int N = h->N, M = h->M;
+    std::vector<int> level((size_t)M);
+    int nl;
+    if (h->opt.solver == TETSIM_NH_GS_EXACT) nl = level_schedule(N, M, tetIds.data(), level.data());
+    else {
+        nl = greedy_colors(N, M, tetIds.data(), level.data());
+        if (nl < 0) return fail(TETSIM_E_INVALID, "greedy colouring needs more than 256 colours");
+    }
+    std::vector<int> comp;
+    h->numComponents = connected_components(N, M, tetIds.data(), comp);
+    // component sizes -> can every body live in one CTA's shared memory?
+    std::vector<int> compVerts((size_t)h->numComponents, 0);
+    for (int v = 0; v < N; v++) compVerts[comp[v]]++;
+    int maxCompVerts = 0;
+    for (int c : compVerts) maxCompVerts = std::max(maxCompVerts, c);
+    const char *forceLevel = getenv("TETSIM_FORCE_LEVEL_KERNEL");
+    h->bodyKernel = (size_t)maxCompVerts * sizeof(float4) <= (size_t)h->K->gs_body_max_smem() && !(forceLevel && forceLevel[0] == '1');
+
+    // internal vertex numbering: bodies contiguous
+    std::vector<int> c2i((size_t)N);
+    if (h->bodyKernel && h->numComponents > 1) {
+        h->h_vertId.resize((size_t)N);
+        std::iota(h->h_vertId.begin(), h->h_vertId.end(), 0);
+        std::stable_sort(h->h_vertId.begin(), h->h_vertId.end(), [&](int a, int b) { return comp[a] < comp[b]; });
+        bool identity = true;
+        for (int i = 0; i < N; i++) { c2i[h->h_vertId[i]] = i; identity = identity && h->h_vertId[i] == i; }
+        if (identity) h->h_vertId.clear();
+    } else {
+        std::iota(c2i.begin(), c2i.end(), 0);
+    }
+    // solver order: (body, level, tet) when bodies are separate CTAs, else (level, tet)
+    std::vector<int> order((size_t)M);
+    std::iota(order.begin(), order.end(), 0);
+    auto tetComp = [&](int e) { return comp[tetIds[4 * (size_t)e]]; };
+    if (h->bodyKernel)
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            int ca = tetComp(a), cb = tetComp(b);
+            return ca != cb ? ca < cb : level[a] < level[b];
+        });
+    else
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return level[a] < level[b]; });
+
+    std::vector<int4> I((size_t)M);
+    h->h_levelStart.clear();
+    std::vector<BodyDesc> bodies;
+    h->maxLevelSize = 0;
+    if (h->bodyKernel) {
+        std::vector<int> vertBegin((size_t)h->numComponents + 1, 0);
+        for (int c = 0; c < h->numComponents; c++) vertBegin[c + 1] = vertBegin[c] + compVerts[c];
+        int pos = 0;
+        for (int c = 0; c < h->numComponents; c++) {
+            BodyDesc bd;
+            bd.vertBegin = vertBegin[c]; bd.vertEnd = vertBegin[c + 1];
+            bd.tetBegin = pos;
+            bd.levelBegin = (int)h->h_levelStart.size();
+            int lastLevel = -1, runStart = pos;
+            while (pos < M && tetComp(order[pos]) == c) {
+                int e = order[pos];
+                if (level[e] != lastLevel) {
+                    if (lastLevel >= 0) h->maxLevelSize = std::max(h->maxLevelSize, pos - runStart);
+                    h->h_levelStart.push_back(pos);
+                    lastLevel = level[e];
+                    runStart = pos;
+                }
+                const int *t = tetIds.data() + 4 * (size_t)e;
+                I[pos] = make_int4(c2i[t[0]] - bd.vertBegin, c2i[t[1]] - bd.vertBegin, c2i[t[2]] - bd.vertBegin, c2i[t[3]] - bd.vertBegin);
+                pos++;
+            }
+            if (lastLevel >= 0) h->maxLevelSize = std::max(h->maxLevelSize, pos - runStart);
+            bd.levelEnd = (int)h->h_levelStart.size();
+            h->h_levelStart.push_back(pos);  // sentinel: end of this body's last level
+            if (bd.tetBegin != pos || bd.vertEnd > bd.vertBegin) bodies.push_back(bd);
+        }
+        h->numBodies = (int)bodies.size();
+        h->numLevels = nl;
+        h->bodyThreads = maxCompVerts > 512 ? 128 : 64;
+        h->bodyThreads = std::max(h->bodyThreads, std::min(256, 32 * ((h->maxLevelSize + 31) / 32)));
+        h->bodySmem = (size_t)maxCompVerts * sizeof(float4);
+        h->launchesPerSubstep = 1;
+    } else {
+        int lastLevel = -1, runStart = 0;
+        for (int pos = 0; pos < M; pos++) {
+            int e = order[pos];
+            if (level[e] != lastLevel) {
+                if (lastLevel >= 0) h->maxLevelSize = std::max(h->maxLevelSize, pos - runStart);
+                h->h_levelStart.push_back(pos);
+                lastLevel = level[e];
+                runStart = pos;
+            }
+            const int *t = tetIds.data() + 4 * (size_t)e;
+            I[pos] = make_int4(t[0], t[1], t[2], t[3]);
+        }
+        if (M > 0) h->maxLevelSize = std::max(h->maxLevelSize, M - runStart);
+        h->h_levelStart.push_back(M);
+        h->numLevels = nl;
+        h->launchesPerSubstep = 2 + nl;
+    }
+    cudaStream_t s = h->stream;
+    CK(h->order.upload(order, s));
+    CK(h->I.upload(I, s));
+    CK(h->levelStart.upload(h->h_levelStart, s));
+    if (h->bodyKernel) CK(h->bodies.upload(bodies, s));
+    CK(h->A.alloc((size_t)M)); CK(h->B.alloc((size_t)M)); CK(h->C.alloc((size_t)M));
+    CK(cudaMemsetAsync(h->C.p, 0, h->C.bytes(), s));
+    launch_build_stream(s, M, h->order.p, h->Q9.p, h->irv.p, h->A.p, h->B.p, h->C.p);
+    if (h->trackVol) { CK(h->volTerm.alloc((size_t)M)); CK(cudaMemsetAsync(h->volTerm.p, 0, h->volTerm.bytes(), s)); }
+    (void)verts;
+    return TETSIM_OK;
+}
+
+int build_jacobi_gather(tetsim *h, const std::vector<int> &tetIds) {
+    const int M = h->M;
+    cudaStream_t s = h->stream;
+    CK(h->A.alloc((size_t)M)); CK(h->B.alloc((size_t)M)); CK(h->C.alloc((size_t)M));
+    CK(cudaMemsetAsync(h->C.p, 0, h->C.bytes(), s));
+    launch_build_stream(s, M, nullptr, h->Q9.p, h->irv.p, h->A.p, h->B.p, h->C.p);
+    CK(h->dx.alloc(4 * (size_t)M));
+    if (h->trackVol) { CK(h->volTerm.alloc((size_t)M)); CK(cudaMemsetAsync(h->volTerm.p, 0, h->volTerm.bytes(), s)); }
+    h->launchesPerSubstep = 2 + 2 * h->opt.iters;
+    (void)tetIds;
+    return TETSIM_OK;
+}
+
+int build_jacobi_cluster(tetsim *h, const std::vector<float> &verts, const std::vector<int> &tetIds) {
+    const int N = h->N, M = h->M;
+    std::vector<int> order;
+    if (h->opt.reorder) order = morton_order(N, M, verts.data(), tetIds.data());
+    else { order.resize((size_t)M); std::iota(order.begin(), order.end(), 0); }
+    std::string err;
+    if (!build_cluster_plan(N, M, tetIds.data(), order, h->opt.clusterSize, h->opt.rank, h->opt.worldSize, h->plan, err))
+        return fail(TETSIM_E_INVALID, err);
+    ClusterPlan &P = h->plan;
+    h->clustered = true;
+    cudaStream_t s = h->stream;
+    const size_t nRec = (size_t)P.numClusters * P.T;
+    CK(h->order.upload(P.recordTet, s));
+    CK(h->A.alloc(nRec)); CK(h->B.alloc(nRec)); CK(h->C.alloc(nRec));
+    {
+        std::vector<float4> Ch(nRec);
+        for (size_t r = 0; r < nRec; r++) {
+            float z, w;
+            memcpy(&z, &P.recordSlots[2 * r], 4);
+            memcpy(&w, &P.recordSlots[2 * r + 1], 4);
+            Ch[r] = make_float4(0.f, 0.f, z, w);
+        }
+        if (nRec) CK(cudaMemcpyAsync(h->C.p, Ch.data(), nRec * sizeof(float4), cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    launch_build_stream(s, (int)nRec, h->order.p, h->Q9.p, h->irv.p, h->A.p, h->B.p, h->C.p);
+    CK(h->clVertStart.upload(P.clVertStart, s));
+    CK(h->clVerts.upload(P.clVerts, s));
+    CK(h->clVal.upload(P.clVal, s));
+    CK(h->jds.upload(P.jds, s));
+    CK(h->colOff.upload(P.colOff, s));
+    CK(h->vpStart.upload(P.vpStart, s));
+    CK(h->vpSlot.upload(P.vpSlot, s));
+    CK(h->invVal.upload(P.invValence, s));
+    if (h->opt.deterministic) CK(h->part.alloc(P.clVerts.size()));
+    else { CK(h->acc.alloc((size_t)P.numLocalVerts)); CK(cudaMemsetAsync(h->acc.p, 0, h->acc.bytes(), s)); }
+    if (P.numBoundary > 0) CK(h->bsum.alloc((size_t)P.numBoundary));
+    if (h->trackVol) { CK(h->volTerm.alloc(1)); CK(cudaMemsetAsync(h->volTerm.p, 0, sizeof(double), s)); }
+    h->h_vertId = P.localToCaller;
+    bool identity = (int)h->h_vertId.size() == N;
+    for (int i = 0; identity && i < N; i++) identity = h->h_vertId[i] == i;
+    if (identity) h->h_vertId.clear();
+    h->maxValence = P.maxValence;
+    h->launchesPerSubstep = 2 * h->opt.iters + (h->opt.worldSize > 1 ? 2 * h->opt.iters : 0);
+    CK(cudaStreamSynchronize(s));
+    return TETSIM_OK;
+}
+
+int build_polar(tetsim *h, const std::vector<int> &tetIds) {
+    cudaStream_t s = h->stream;
+    CornerTable t = build_reference_table(h->N, h->M, tetIds.data(), h->opt.referenceTableBug != 0, 36);
+    CK(h->tStart.upload(t.start, s));
+    CK(h->tEnt.upload(t.ent, s));
+    CK(h->rest.alloc(4 * (size_t)h->M));
+    CK(h->quat.alloc((size_t)h->M));
+    launch_fill_rest(s, h->M, h->x4.p, h->ids.p, h->irv.p, h->rest.p, h->quat.p);
+    h->launchesPerSubstep = 3;
+    CK(cudaStreamSynchronize(s));
+    return TETSIM_OK;
+}
+
+// ---- substep scheduling --------------------------------------------------------------------------
+
+// Enqueue `count` substeps.  Inside one call dt and the parameters are constant, which is what lets
+// the clustered Jacobi path fuse a substep's post with the next substep's predict.
+int enqueue_substeps(tetsim *h, int count) {
+    cudaStream_t s = h->stream;
+    h->enq = 0;
+    const KernelTable *K = h->K;
+    const SubstepParams *sp = h->sp.p;
+    const int *vid = h->vertId.p;
+    for (int step = 0; step < count; step++) {
+        switch (h->opt.solver) {
+            case TETSIM_NH_GS_EXACT:
+            case TETSIM_NH_GS_COLOR:
+                if (h->bodyKernel) {
+                    h->enq += h->numBodies > 0;
+                    K->gs_body(s, h->numBodies, h->bodyThreads, h->bodySmem, h->bodies.p, h->levelStart.p, h->x4.p,
+                               h->prev4.p, h->vel4.p, h->I.p, h->A.p, h->B.p, h->C.p, h->order.p, h->volTerm.p, sp, vid);
+                } else {
+                    K->predict(s, h->nInt, h->x4.p, h->prev4.p, h->vel4.p, sp);
+                    h->enq += 2 + (int64_t)h->h_levelStart.size() - 1;
+                    for (size_t l = 0; l + 1 < h->h_levelStart.size(); l++)
+                        K->gs_level(s, h->h_levelStart[l], h->h_levelStart[l + 1], h->x4.p, h->I.p, h->A.p, h->B.p,
+                                    h->C.p, h->order.p, h->volTerm.p, sp);
+                    K->post(s, h->nInt, h->x4.p, h->prev4.p, h->vel4.p, sp, vid);
+                }
+                break;
+            case TETSIM_NH_JACOBI:
+                if (!h->clustered) {
+                    K->predict(s, h->nInt, h->x4.p, h->prev4.p, h->vel4.p, sp);
+                    h->enq += 2 + 2 * h->opt.iters;
+                    for (int it = 0; it < h->opt.iters; it++) {
+                        K->jacobi_tet(s, h->M, h->x4.p, h->ids.p, h->A.p, h->B.p, h->C.p, h->dx.p, h->volTerm.p, sp);
+                        K->jacobi_gather(s, h->nInt, h->x4.p, h->cStart.p, h->cEnt.p, h->dx.p);
+                    }
+                    K->post(s, h->nInt, h->x4.p, h->prev4.p, h->vel4.p, sp, vid);
+                } else {
+                    const ClusterPlan &P = h->plan;
+                    if (step == 0) { K->predict(s, h->nInt, h->x4.p, h->prev4.p, h->vel4.p, sp); h->enq++; }
+                    ClusterArgs ca{};
+                    ca.x4 = h->x4.p; ca.A = h->A.p; ca.B = h->B.p; ca.C = h->C.p;
+                    ca.clVertStart = h->clVertStart.p; ca.clVerts = h->clVerts.p; ca.clVal = h->clVal.p;
+                    ca.jds = h->jds.p; ca.colOff = h->colOff.p; ca.colStride = P.colStride;
+                    ca.part = h->part.p; ca.acc = h->acc.p; ca.volAcc = h->volTerm.p; ca.sp = sp;
+                    ca.maxTileVerts = P.maxTileVerts;
+                    ApplyArgs aa{};
+                    aa.x4 = h->x4.p; aa.prev4 = h->prev4.p; aa.vel4 = h->vel4.p;
+                    aa.vpStart = h->vpStart.p; aa.vpSlot = h->vpSlot.p; aa.part = h->part.p; aa.acc = h->acc.p;
+                    aa.invVal = h->invVal.p; aa.sp = sp; aa.vertId = vid;
+                    aa.boundaryBegin = P.numInterior;
+                    const bool multi = h->opt.worldSize > 1 && P.numBoundary > 0;
+                    for (int it = 0; it < h->opt.iters; it++) {
+                        if (h->trackVol) CK(cudaMemsetAsync(h->volTerm.p, 0, sizeof(double), s));
+                        launch_jacobi_cluster(s, P.T, 0, P.numClusters, ca);
+                        h->enq += 2;  // tile kernel + vertex kernel
+                        const bool last = it == h->opt.iters - 1;
+                        const int mode = !last ? 0 : (step + 1 < count ? 2 : 1);
+                        if (multi) {
+                            // boundary dx: pack this rank's sums, all-reduce over NVLink, then apply everywhere
+                            if (h->acc.p) {
+                                CK(cudaMemcpyAsync(h->bsum.p, h->acc.p + P.numInterior, h->bsum.bytes(), cudaMemcpyDeviceToDevice, s));
+                                CK(cudaMemsetAsync(h->acc.p + P.numInterior, 0, h->bsum.bytes(), s));
+                            } else {
+                                h->enq++;
+                                launch_boundary_pack(s, P.numInterior, P.numBoundary, h->vpStart.p, h->vpSlot.p, h->part.p, h->bsum.p);
+                            }
+                            int rc = g_nccl.AllReduce(h->bsum.p, h->bsum.p, (size_t)P.numBoundary * 4, kNcclFloat, kNcclSum, h->comm, s);
+                            if (rc != 0) return fail(TETSIM_E_NCCL, std::string("ncclAllReduce: ") + g_nccl.GetErrorString(rc));
+                            aa.bsum = h->bsum.p;
+                        }
+                        launch_jacobi_apply(s, 0, h->nInt, mode, aa);
+                    }
+                }
+                break;
+            case TETSIM_POLAR_JACOBI:
+                h->enq += 3;
+                K->polar_integrate(s, h->nInt, h->x4.p, h->prev4.p, h->vel4.p, sp);
+                K->polar_tet(s, h->M, h->x4.p, h->ids.p, h->rest.p, h->quat.p);
+                K->polar_vertex(s, h->nInt, h->x4.p, h->prev4.p, h->vel4.p, h->tStart.p, h->tEnt.p, h->rest.p, sp);
+                break;
+            default:
+                return fail(TETSIM_E_STATE, "unknown solver");
+        }
+    }
+    CK(cudaGetLastError());
+    return TETSIM_OK;
+}
+
+int run_substeps(tetsim *h, double dt, int count, const TetSimParams *params) {
+    if (!h) return fail(TETSIM_E_INVALID, "null handle");
+    if (count < 1) return fail(TETSIM_E_INVALID, "numSubsteps must be >= 1");
+    if (!(dt == dt)) return fail(TETSIM_E_INVALID, "dt is NaN");
+    DeviceGuard g(h->device);
+    if (params) h->params = *params;
+    SubstepParams hs;
+    fill_substep_params(hs, dt, h->params, h->grabId, h->grabPos);
+    // pageable source: the runtime stages the 300 bytes before returning, so `hs` may die here
+    CK(cudaMemcpyAsync(h->sp.p, &hs, sizeof(hs), cudaMemcpyHostToDevice, h->stream));
+    const char *noGraph = getenv("TETSIM_NO_GRAPH");
+    if (noGraph && noGraph[0] == '1') {
+        int rc = enqueue_substeps(h, count);
+        h->totalLaunches += h->enq;
+        return rc;
+    }
+    auto it = h->graphs.find(count);
+    if (it == h->graphs.end()) {
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_substeps(h, count);
+        cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+        if (rc != TETSIM_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) return fail(TETSIM_E_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+        cudaGraphExec_t exec = nullptr;
+        ce = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) return fail(TETSIM_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+        it = h->graphs.emplace(count, exec).first;
+        h->graphLaunches[count] = h->enq;
+    }
+    CK(cudaGraphLaunch(it->second, h->stream));
+    h->totalLaunches += h->graphLaunches[count];
+    return TETSIM_OK;
+}
+
+int fetch3(tetsim *h, const float4 *src, float *out) {
+    if (!h || !out) return fail(TETSIM_E_INVALID, "null argument");
+    DeviceGuard g(h->device);
+    if (h->nInt != h->N) CK(cudaMemsetAsync(h->stage3.p, 0xff, h->stage3.bytes(), h->stream));  // non-resident -> NaN
+    launch_pack3(h->stream, h->nInt, src, h->vertId.p, h->stage3.p);
+    CK(cudaMemcpyAsync(out, h->stage3.p, h->stage3.bytes(), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return TETSIM_OK;
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *tetsim_last_error(void) { return g_err.c_str(); }
+int tetsim_version(void) { return TETSIM_VERSION; }
+
+int tetsim_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { fail(TETSIM_E_CUDA, cudaGetErrorString(e)); return TETSIM_E_CUDA; }
+    int ok = 0;
+    for (int d = 0; d < n; d++) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ok++;
+    }
+    return ok;
+}
+
+void tetsim_default_params(TetSimParams *p) {
+    if (!p) return;
+    p->gravity = -9.81;
+    p->friction = 1000.0;
+    p->density = 1000.0;
+    p->devCompliance = 1.0 / 100000.0;
+    p->volCompliance = 0.0;
+    const double wb[6] = {-2.5, -1.0, -2.5, 2.5, 10.0, 2.5};
+    memcpy(p->worldBounds, wb, sizeof(wb));
+}
+
+void tetsim_default_options(TetSimOptions *o) {
+    if (!o) return;
+    memset(o, 0, sizeof(*o));
+    o->solver = TETSIM_NH_GS_EXACT;
+    o->arithmetic = TETSIM_ARITH_FAST_F32;
+    o->iters = 1;
+    o->deterministic = 1;
+    o->referenceTableBug = 1;
+    o->reorder = 1;
+    o->clusterSize = 256;
+    o->trackVolError = -1;
+    o->device = -1;
+    o->rank = 0;
+    o->worldSize = 1;
+    o->exchange = 0;
+    o->stream = nullptr;
+    o->ncclUniqueId = nullptr;
+}
+
+int tetsim_create(const float *verts, int32_t numVerts, const int32_t *tetIds, int32_t numTets,
+                  const TetSimParams *params, const TetSimOptions *options, tetsim_t **out) {
+    if (!out) return fail(TETSIM_E_INVALID, "out is null");
+    *out = nullptr;
+    if (numVerts < 0 || numTets < 0 || (numVerts > 0 && !verts) || (numTets > 0 && !tetIds))
+        return fail(TETSIM_E_INVALID, "null or negative-sized mesh arrays");
+    if ((int64_t)numTets * 4 > INT32_MAX) return fail(TETSIM_E_INVALID, "more than 2^29 tets");
+    TetSimOptions opt;
+    tetsim_default_options(&opt);
+    if (options) opt = *options;
+    TetSimParams prm;
+    tetsim_default_params(&prm);
+    if (params) prm = *params;
+    if (opt.solver < TETSIM_NH_GS_EXACT || opt.solver > TETSIM_POLAR_JACOBI) return fail(TETSIM_E_INVALID, "unknown solver");
+    if (opt.arithmetic != TETSIM_ARITH_FAST_F32 && opt.arithmetic != TETSIM_ARITH_BITEXACT)
+        return fail(TETSIM_E_INVALID, "unknown arithmetic");
+    if (opt.iters < 1) return fail(TETSIM_E_INVALID, "iters must be >= 1");
+    if (opt.clusterSize != 128 && opt.clusterSize != 256 && opt.clusterSize != 512)
+        return fail(TETSIM_E_INVALID, "clusterSize must be 128, 256 or 512");
+    if (opt.worldSize < 1 || opt.rank < 0 || opt.rank >= opt.worldSize) return fail(TETSIM_E_INVALID, "bad rank/worldSize");
+    const bool clustered = opt.solver == TETSIM_NH_JACOBI && opt.arithmetic == TETSIM_ARITH_FAST_F32;
+    if (opt.worldSize > 1 && !clustered)
+        return fail(TETSIM_E_STATE, "worldSize > 1 is only supported by the FAST_F32 Jacobi solver; shard independent bodies across processes instead");
+    if (opt.worldSize > 1 && !opt.ncclUniqueId) return fail(TETSIM_E_INVALID, "worldSize > 1 needs ncclUniqueId");
+    for (int64_t c = 0; c < 4 * (int64_t)numTets; c++)
+        if (tetIds[c] < 0 || tetIds[c] >= numVerts) return fail(TETSIM_E_INVALID, "tet " + std::to_string(c / 4) + " references vertex " + std::to_string(tetIds[c]) + " outside [0, numVerts)");
+    for (int e = 0; e < numTets; e++) {
+        const int32_t *t = tetIds + 4 * (size_t)e;
+        if (t[0] == t[1] || t[0] == t[2] || t[0] == t[3] || t[1] == t[2] || t[1] == t[3] || t[2] == t[3])
+            return fail(TETSIM_E_INVALID, "tet " + std::to_string(e) + " repeats a vertex");
+    }
+
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(TETSIM_E_CUDA, std::string("no CUDA device: ") + (ce != cudaSuccess ? cudaGetErrorString(ce) : "device count is 0") + " (this library has no CPU path)");
+    int dev = opt.device;
+    if (dev < 0) CK(cudaGetDevice(&dev));
+    if (dev >= ndev) return fail(TETSIM_E_INVALID, "device ordinal out of range");
+    int ccMajor = 0;
+    CK(cudaDeviceGetAttribute(&ccMajor, cudaDevAttrComputeCapabilityMajor, dev));
+    if (ccMajor != 10) return fail(TETSIM_E_CUDA, "device " + std::to_string(dev) + " is not compute capability 10.x (kernels are built for sm_100a only)");
+
+    DeviceGuard guard(dev);
+    tetsim *h = new (std::nothrow) tetsim();
+    if (!h) return fail(TETSIM_E_NOMEM, "out of host memory");
+    struct Cleanup { tetsim *h; bool armed = true; ~Cleanup() { if (armed) tetsim_destroy(h); } } cleanup{h};
+    h->opt = opt; h->params = prm; h->N = numVerts; h->M = numTets; h->device = dev;
+    h->KX = exact_kernels();
+    h->K = opt.arithmetic == TETSIM_ARITH_BITEXACT ? exact_kernels() : fast_kernels();
+    if (opt.stream) h->stream = (cudaStream_t)opt.stream;
+    else { CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->ownStream = true; }
+    h->trackVol = opt.trackVolError < 0 ? (opt.solver == TETSIM_NH_GS_EXACT || opt.solver == TETSIM_NH_GS_COLOR || (opt.solver == TETSIM_NH_JACOBI && !clustered))
+                                        : opt.trackVolError != 0;
+    if (opt.solver == TETSIM_POLAR_JACOBI) h->trackVol = false;
+    cudaStream_t s = h->stream;
+
+    std::vector<float> hv(verts, verts + 3 * (size_t)numVerts);
+    std::vector<int> ht(tetIds, tetIds + 4 * (size_t)numTets);
+
+    // ---- initPhysics on the device, caller numbering (src/Softbody.js:60-87) ----
+    {
+        std::vector<float4> hx((size_t)numVerts);
+        for (int v = 0; v < numVerts; v++) hx[v] = make_float4(hv[3 * (size_t)v], hv[3 * (size_t)v + 1], hv[3 * (size_t)v + 2], 0.0f);
+        DevBuf<float4> gx;
+        DevBuf<int4> gids;
+        DevBuf<double> pm;
+        DevBuf<int> gcs, gce;
+        CK(gx.upload(hx, s));
+        CK(gids.alloc((size_t)numTets));
+        if (numTets) CK(cudaMemcpyAsync(gids.p, ht.data(), (size_t)numTets * sizeof(int4), cudaMemcpyHostToDevice, s));
+        CornerTable ct = build_corner_table(numVerts, numTets, ht.data());
+        h->maxValence = ct.maxValence;
+        CK(gcs.upload(ct.start, s));
+        CK(gce.upload(ct.ent, s));
+        CK(h->Q9.alloc(9 * (size_t)numTets)); CK(h->irv.alloc((size_t)numTets)); CK(pm.alloc((size_t)numTets));
+        h->KX->init_tets(s, numTets, gx.p, gids.p, prm.density, h->Q9.p, h->irv.p, pm.p);
+        h->KX->init_mass(s, numVerts, gcs.p, gce.p, pm.p, gx.p);
+        CK(cudaGetLastError());
+        // pull invMass back once: it is part of every solver's vertex record and of get_rest
+        CK(cudaMemcpyAsync(hx.data(), gx.p, (size_t)numVerts * sizeof(float4), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        std::vector<float> im((size_t)numVerts);
+        for (int v = 0; v < numVerts; v++) im[v] = hx[v].w;
+        CK(h->invMass.upload(im, s));
+
+        // ---- solver-specific build (decides the internal vertex numbering) ----
+        int rc = TETSIM_OK;
+        if (opt.solver == TETSIM_NH_GS_EXACT || opt.solver == TETSIM_NH_GS_COLOR) rc = build_gs(h, hv, ht);
+        else if (clustered) {
+            if (opt.worldSize > 1) {
+                if (!g_nccl.load()) return fail(TETSIM_E_NCCL, g_nccl.why);
+                NcclUniqueId id;
+                memcpy(&id, opt.ncclUniqueId, sizeof(id));
+                int nrc = g_nccl.CommInitRank(&h->comm, opt.worldSize, id, opt.rank);
+                if (nrc != 0) return fail(TETSIM_E_NCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(nrc));
+            }
+            rc = build_jacobi_cluster(h, hv, ht);
+        }
+        if (rc != TETSIM_OK) return rc;
+
+        // vertex state in internal numbering
+        const bool identity = h->h_vertId.empty();
+        h->nInt = identity ? numVerts : (int)h->h_vertId.size();
+        std::vector<float4> hxi((size_t)h->nInt);
+        for (int i = 0; i < h->nInt; i++) hxi[i] = hx[identity ? i : h->h_vertId[i]];
+        CK(h->x4.upload(hxi, s));
+        CK(h->prev4.upload(hxi, s));
+        CK(h->vel4.alloc((size_t)h->nInt));
+        if (h->nInt) CK(cudaMemsetAsync(h->vel4.p, 0, h->vel4.bytes(), s));
+        if (!identity) CK(h->vertId.upload(h->h_vertId, s));
+        // tet ids in internal numbering (caller tet order) for the gather solvers / skinning
+        if (!clustered || opt.worldSize == 1) {
+            std::vector<int> c2i;
+            const int *map = nullptr;
+            if (!identity) {
+                c2i.assign((size_t)numVerts, -1);
+                for (int i = 0; i < h->nInt; i++) c2i[h->h_vertId[i]] = i;
+                map = c2i.data();
+            }
+            std::vector<int4> hi((size_t)numTets);
+            for (int e = 0; e < numTets; e++) {
+                const int *t = ht.data() + 4 * (size_t)e;
+                hi[e] = map ? make_int4(map[t[0]], map[t[1]], map[t[2]], map[t[3]]) : make_int4(t[0], t[1], t[2], t[3]);
+            }
+            CK(h->ids.upload(hi, s));
+            CK(cudaStreamSynchronize(s));
+        }
+        if (opt.solver == TETSIM_NH_JACOBI && !clustered) {
+            h->cStart.p = gcs.p; h->cStart.n = gcs.n; gcs.p = nullptr;  // adopt the corner table
+            h->cEnt.p = gce.p; h->cEnt.n = gce.n; gce.p = nullptr;
+            rc = build_jacobi_gather(h, ht);
+        } else if (opt.solver == TETSIM_POLAR_JACOBI) {
+            rc = build_polar(h, ht);
+        }
+        CK(cudaStreamSynchronize(s));
+        gx.release(); gids.release(); pm.release(); gcs.release(); gce.release();
+        if (rc != TETSIM_OK) return rc;
+    }
+    CK(h->sp.alloc(1));
+    CK(h->stage3.alloc(3 * (size_t)std::max(numVerts, 1)));
+    CK(h->volOut.alloc(1));
+    CK(h->grabP.alloc(3)); CK(h->grabOut.alloc(1)); CK(h->grabScratch.alloc(1));
+    CK(cudaStreamSynchronize(s));
+    cleanup.armed = false;
+    *out = h;
+    return TETSIM_OK;
+}
+
+void tetsim_destroy(tetsim_t *h) {
+    if (!h) return;
+    DeviceGuard g(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second);
+    if (h->comm) g_nccl.CommDestroy(h->comm);
+    DevBuf<float4> *f4[] = {&h->x4, &h->prev4, &h->vel4, &h->A, &h->B, &h->C, &h->dx, &h->part, &h->acc, &h->bsum, &h->rest, &h->quat, &h->visV};
+    for (auto *b : f4) b->release();
+    DevBuf<int> *i1[] = {&h->vertId, &h->cStart, &h->cEnt, &h->order, &h->levelStart, &h->clVertStart, &h->clVerts, &h->vpStart, &h->vpSlot, &h->tStart, &h->tEnt, &h->grabOut, &h->visTri, &h->vtStart, &h->vtEnt};
+    for (auto *b : i1) b->release();
+    DevBuf<float> *f1[] = {&h->Q9, &h->irv, &h->invMass, &h->invVal, &h->stage3, &h->visPos, &h->visNrm};
+    for (auto *b : f1) b->release();
+    h->ids.release(); h->I.release(); h->bodies.release(); h->volTerm.release(); h->volOut.release();
+    h->clVal.release(); h->jds.release(); h->colOff.release(); h->sp.release(); h->grabP.release(); h->grabScratch.release();
+    if (h->ownStream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int tetsim_simulate(tetsim_t *h, double dt, const TetSimParams *params) { return run_substeps(h, dt, 1, params); }
+
+int tetsim_step(tetsim_t *h, double frameDt, int32_t numSubsteps, const TetSimParams *params) {
+    if (numSubsteps < 1) return fail(TETSIM_E_INVALID, "numSubsteps must be >= 1");
+    return run_substeps(h, frameDt / (double)numSubsteps, numSubsteps, params);  // src/main.js:79
+}
+
+int tetsim_synchronize(tetsim_t *h) {
+    if (!h) return fail(TETSIM_E_INVALID, "null handle");
+    DeviceGuard g(h->device);
+    CK(cudaStreamSynchronize(h->stream));
+    return TETSIM_OK;
+}
+
+int tetsim_get_positions(tetsim_t *h, float *out) { return h ? fetch3(h, h->x4.p, out) : fail(TETSIM_E_INVALID, "null handle"); }
+int tetsim_get_prev_positions(tetsim_t *h, float *out) { return h ? fetch3(h, h->prev4.p, out) : fail(TETSIM_E_INVALID, "null handle"); }
+int tetsim_get_velocities(tetsim_t *h, float *out) { return h ? fetch3(h, h->vel4.p, out) : fail(TETSIM_E_INVALID, "null handle"); }
+
+int tetsim_get_resident(tetsim_t *h, uint8_t *out) {
+    if (!h || !out) return fail(TETSIM_E_INVALID, "null argument");
+    if (h->h_vertId.empty()) { memset(out, 1, (size_t)h->N); return TETSIM_OK; }
+    memset(out, 0, (size_t)h->N);
+    for (int v : h->h_vertId) out[v] = 1;
+    return TETSIM_OK;
+}
+
+int tetsim_set_state(tetsim_t *h, const float *pos, const float *prevPos, const float *vel) {
+    if (!h) return fail(TETSIM_E_INVALID, "null handle");
+    DeviceGuard g(h->device);
+    const float *src[3] = {pos, prevPos, vel};
+    float4 *dst[3] = {h->x4.p, h->prev4.p, h->vel4.p};
+    for (int k = 0; k < 3; k++) {
+        if (!src[k]) continue;
+        CK(cudaMemcpyAsync(h->stage3.p, src[k], (size_t)3 * h->N * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        launch_unpack3(h->stream, h->nInt, h->stage3.p, h->vertId.p, dst[k], k == 0 ? 1 : 0);
+    }
+    CK(cudaGetLastError());
+    return TETSIM_OK;
+}
+
+int tetsim_get_rest(tetsim_t *h, float *invRestPose, float *invRestVolume, float *invMass) {
+    if (!h) return fail(TETSIM_E_INVALID, "null handle");
+    DeviceGuard g(h->device);
+    CK(cudaStreamSynchronize(h->stream));
+    if (invRestPose && h->M) CK(cudaMemcpy(invRestPose, h->Q9.p, h->Q9.bytes(), cudaMemcpyDeviceToHost));
+    if (invRestVolume && h->M) CK(cudaMemcpy(invRestVolume, h->irv.p, h->irv.bytes(), cudaMemcpyDeviceToHost));
+    if (invMass && h->N) CK(cudaMemcpy(invMass, h->invMass.p, h->invMass.bytes(), cudaMemcpyDeviceToHost));
+    return TETSIM_OK;
+}
+
+int tetsim_get_vol_error(tetsim_t *h, double *out) {
+    if (!h || !out) return fail(TETSIM_E_INVALID, "null argument");
+    if (!h->trackVol) return fail(TETSIM_E_STATE, "volError tracking is off for this handle (TetSimOptions.trackVolError)");
+    DeviceGuard g(h->device);
+    if (h->clustered) {
+        double sum = 0.0;
+        CK(cudaMemcpyAsync(&sum, h->volTerm.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        *out = sum / (double)h->M;  // this rank's tets over the GLOBAL tet count
+        return TETSIM_OK;
+    }
+    launch_sum_sequential(h->stream, h->M, h->volTerm.p, h->volOut.p);
+    CK(cudaMemcpyAsync(out, h->volOut.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return TETSIM_OK;
+}
+
+int tetsim_get_polar_state(tetsim_t *h, float *rest12, float *quat4) {
+    if (!h) return fail(TETSIM_E_INVALID, "null handle");
+    if (h->opt.solver != TETSIM_POLAR_JACOBI) return fail(TETSIM_E_STATE, "not a POLAR_JACOBI handle");
+    DeviceGuard g(h->device);
+    CK(cudaStreamSynchronize(h->stream));
+    if (rest12) {
+        std::vector<float4> r(4 * (size_t)h->M);
+        if (h->M) CK(cudaMemcpy(r.data(), h->rest.p, h->rest.bytes(), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < r.size(); i++) { rest12[3 * i] = r[i].x; rest12[3 * i + 1] = r[i].y; rest12[3 * i + 2] = r[i].z; }
+    }
+    if (quat4 && h->M) CK(cudaMemcpy(quat4, h->quat.p, h->quat.bytes(), cudaMemcpyDeviceToHost));
+    return TETSIM_OK;
+}
+
+int tetsim_start_grab(tetsim_t *h, const double p[3], int32_t *outGrabId) {
+    if (!h || !p) return fail(TETSIM_E_INVALID, "null argument");
+    DeviceGuard g(h->device);
+    CK(cudaMemcpyAsync(h->grabP.p, p, 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    launch_nearest_vertex(h->stream, h->nInt, h->x4.p, h->vertId.p, h->grabP.p, h->grabOut.p, h->grabScratch.p);
+    int id = -1;
+    CK(cudaMemcpyAsync(&id, h->grabOut.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (id < 0 || id >= h->N) id = -1;  // no finite distance: grabId stays -1 like the reference loop
+    h->grabId = id;
+    memcpy(h->grabPos, p, sizeof(h->grabPos));
+    if (outGrabId) *outGrabId = id;
+    return TETSIM_OK;
+}
+
+int tetsim_move_grabbed(tetsim_t *h, const double p[3]) {
+    if (!h || !p) return fail(TETSIM_E_INVALID, "null argument");
+    memcpy(h->grabPos, p, sizeof(h->grabPos));
+    return TETSIM_OK;
+}
+
+int tetsim_end_grab(tetsim_t *h) {
+    if (!h) return fail(TETSIM_E_INVALID, "null handle");
+    h->grabId = -1;
+    return TETSIM_OK;
+}
+
+int tetsim_skin(tetsim_t *h, const float *visVerts, int32_t numVis, const int32_t *triIds, int32_t numTris,
+                float *outPos, float *outNormals) {
+    if (!h || !visVerts || !outPos || numVis < 0) return fail(TETSIM_E_INVALID, "null argument");
+    if (h->ids.n == 0 && h->M > 0) return fail(TETSIM_E_STATE, "skinning is not available on a multi-GPU handle");
+    DeviceGuard g(h->device);
+    cudaStream_t s = h->stream;
+    const bool wantN = outNormals && triIds && numTris > 0;
+    if (visVerts != h->visKeyV || numVis != h->visN) {
+        for (int i = 0; i < numVis; i++) {
+            float t = visVerts[4 * (size_t)i];
+            if (!(t >= 0.0f && t < (float)h->M)) return fail(TETSIM_E_INVALID, "visVerts tet index out of range");
+        }
+        CK(h->visV.alloc((size_t)numVis));
+        if (numVis) CK(cudaMemcpyAsync(h->visV.p, visVerts, (size_t)numVis * sizeof(float4), cudaMemcpyHostToDevice, s));
+        CK(h->visPos.alloc(3 * (size_t)std::max(numVis, 1)));
+        CK(h->visNrm.alloc(3 * (size_t)std::max(numVis, 1)));
+        h->visKeyV = visVerts; h->visN = numVis; h->visKeyT = nullptr;
+    }
+    if (wantN && (triIds != h->visKeyT || numTris != h->visT)) {
+        // vertex -> triangles, each (vertex, triangle) pair once, ascending triangle order
+        std::vector<int> start((size_t)numVis + 1, 0), ent;
+        for (int t = 0; t < numTris; t++) {
+            const int *v = triIds + 3 * (size_t)t;
+            for (int k = 0; k < 3; k++) {
+                if (v[k] < 0 || v[k] >= numVis) return fail(TETSIM_E_INVALID, "triangle index out of range");
+                bool dup = false;
+                for (int j = 0; j < k; j++) dup = dup || v[j] == v[k];
+                if (!dup) start[(size_t)v[k] + 1]++;
+            }
+        }
+        for (int v = 0; v < numVis; v++) start[v + 1] += start[v];
+        ent.resize((size_t)start[numVis]);
+        std::vector<int> fill(start.begin(), start.end() - 1);
+        for (int t = 0; t < numTris; t++) {
+            const int *v = triIds + 3 * (size_t)t;
+            for (int k = 0; k < 3; k++) {
+                bool dup = false;
+                for (int j = 0; j < k; j++) dup = dup || v[j] == v[k];
+                if (!dup) ent[fill[v[k]]++] = t;
+            }
+        }
+        std::vector<int> tri(triIds, triIds + 3 * (size_t)numTris);
+        CK(h->visTri.upload(tri, s));
+        CK(h->vtStart.upload(start, s));
+        CK(h->vtEnt.upload(ent, s));
+        CK(cudaStreamSynchronize(s));
+        h->visKeyT = triIds; h->visT = numTris;
+    }
+    h->K->skin(s, numVis, h->visV.p, h->ids.p, h->x4.p, h->visPos.p);
+    if (numVis) CK(cudaMemcpyAsync(outPos, h->visPos.p, 3 * (size_t)numVis * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (wantN) {
+        h->KX->normals(s, numVis, h->visPos.p, h->visTri.p, h->vtStart.p, h->vtEnt.p, h->visNrm.p);
+        if (numVis) CK(cudaMemcpyAsync(outNormals, h->visNrm.p, 3 * (size_t)numVis * sizeof(float), cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));
+    return TETSIM_OK;
+}
+
+int tetsim_get_info(tetsim_t *h, TetSimInfo *info) {
+    if (!h || !info) return fail(TETSIM_E_INVALID, "null argument");
+    memset(info, 0, sizeof(*info));
+    info->numVerts = h->N; info->numTets = h->M;
+    info->solver = h->opt.solver; info->arithmetic = h->opt.arithmetic; info->iters = h->opt.iters;
+    info->numLevels = h->numLevels; info->maxLevelSize = h->maxLevelSize;
+    info->numComponents = h->numComponents; info->bodyKernel = h->bodyKernel ? 1 : 0;
+    info->numClusters = h->plan.numClusters; info->clusterSize = h->clustered ? h->plan.T : 0;
+    info->localTets = h->clustered ? h->plan.localTets : h->M;
+    info->localVerts = h->nInt;
+    info->boundaryVerts = h->plan.numBoundary;
+    info->maxValence = h->maxValence;
+    info->launchesPerSubstep = h->launchesPerSubstep;
+    info->deviceBytes = h->deviceBytes();
+    info->sumLocalVerts = (int64_t)h->plan.clVerts.size();
+    info->kernelLaunches = h->totalLaunches;
+    return TETSIM_OK;
+}
+
+int tetsim_time_kernel(tetsim_t *h, int32_t reps, double *msPerLaunch, int64_t *algorithmicBytes) {
+    if (!h || !msPerLaunch || reps < 1) return fail(TETSIM_E_INVALID, "bad argument");
+    if (!h->clustered) return fail(TETSIM_E_STATE, "tetsim_time_kernel times the clustered Jacobi tile kernel only");
+    DeviceGuard g(h->device);
+    cudaStream_t s = h->stream;
+    const ClusterPlan &P = h->plan;
+    ClusterArgs ca{};
+    ca.x4 = h->x4.p; ca.A = h->A.p; ca.B = h->B.p; ca.C = h->C.p;
+    ca.clVertStart = h->clVertStart.p; ca.clVerts = h->clVerts.p; ca.clVal = h->clVal.p;
+    ca.jds = h->jds.p; ca.colOff = h->colOff.p; ca.colStride = P.colStride;
+    ca.part = h->part.p; ca.acc = nullptr; ca.volAcc = nullptr; ca.sp = h->sp.p; ca.maxTileVerts = P.maxTileVerts;
+    DevBuf<float4> scratch;  // atomic-flush handles have no partial-sum array: give the kernel one
+    if (!ca.part) { CK(scratch.alloc(P.clVerts.size())); ca.part = scratch.p; }
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    launch_jacobi_cluster(s, P.T, 0, P.numClusters, ca);  // warm-up
+    CK(cudaEventRecord(e0, s));
+    for (int r = 0; r < reps; r++) launch_jacobi_cluster(s, P.T, 0, P.numClusters, ca);
+    CK(cudaEventRecord(e1, s));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    scratch.release();
+    CK(cudaGetLastError());
+    *msPerLaunch = (double)ms / reps;
+    // 56 B per tet + 32 B per vertex per launch
+    if (algorithmicBytes) *algorithmicBytes = 56ll * P.localTets + 32ll * h->nInt;
+    return TETSIM_OK;
+}
+
+int tetsim_nccl_unique_id(void *out128) {
+    if (!out128) return fail(TETSIM_E_INVALID, "null argument");
+    if (!g_nccl.load()) return fail(TETSIM_E_NCCL, g_nccl.why);
+    NcclUniqueId id;
+    int rc = g_nccl.GetUniqueId(&id);
+    if (rc != 0) return fail(TETSIM_E_NCCL, std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(rc));
+    memcpy(out128, &id, sizeof(id));
+    return TETSIM_OK;
+}
+
+int tetsim_get_ipc_handle(tetsim_t *h, void *out64) {
+    (void)h; (void)out64;
+    return fail(TETSIM_E_STATE, "fused peer-memory exchange is not built yet (TetSimOptions.exchange = 1)");
+}
+int tetsim_set_peers(tetsim_t *h, const void *handles) {
+    (void)h; (void)handles;
+    return fail(TETSIM_E_STATE, "fused peer-memory exchange is not built yet (TetSimOptions.exchange = 1)");
+}
+
+int tetsim_level_schedule(const int32_t *tetIds, int32_t numTets, int32_t numVerts, int32_t *level) {
+    if (!tetIds || !level) return fail(TETSIM_E_INVALID, "null argument");
+    return level_schedule(numVerts, numTets, tetIds, level);
+}
+int tetsim_greedy_colors(const int32_t *tetIds, int32_t numTets, int32_t numVerts, int32_t *color) {
+    if (!tetIds || !color) return fail(TETSIM_E_INVALID, "null argument");
+    int n = greedy_colors(numVerts, numTets, tetIds, color);
+    return n < 0 ? fail(TETSIM_E_INVALID, "more than 256 colours") : n;
+}
+
+int tetsim_plan_partition(const float *verts, int32_t numVerts, const int32_t *tetIds, int32_t numTets,
+                          int32_t clusterSize, int32_t reorder, int32_t rank, int32_t worldSize, int32_t counts[4],
+                          int32_t *localToCaller, int32_t *localTets) {
+    if (!verts || !tetIds || !counts) return fail(TETSIM_E_INVALID, "null argument");
+    if (clusterSize < 1 || worldSize < 1 || rank < 0 || rank >= worldSize) return fail(TETSIM_E_INVALID, "bad clusterSize/rank/worldSize");
+    for (int64_t c = 0; c < 4 * (int64_t)numTets; c++)
+        if (tetIds[c] < 0 || tetIds[c] >= numVerts) return fail(TETSIM_E_INVALID, "vertex id out of range");
+    std::vector<int> order;
+    if (reorder) order = morton_order(numVerts, numTets, verts, tetIds);
+    else { order.resize((size_t)numTets); std::iota(order.begin(), order.end(), 0); }
+    ClusterPlan P;
+    std::string err;
+    if (!build_cluster_plan(numVerts, numTets, tetIds, order, clusterSize, rank, worldSize, P, err)) return fail(TETSIM_E_INVALID, err);
+    counts[0] = P.localTets; counts[1] = P.numInterior; counts[2] = P.numBoundary; counts[3] = P.numClusters;
+    if (localToCaller) std::copy(P.localToCaller.begin(), P.localToCaller.end(), localToCaller);
+    if (localTets) {
+        int n = 0;
+        for (int t : P.recordTet) if (t >= 0) localTets[n++] = t;
+    }
+    return TETSIM_OK;
+}
+
+}  // extern "C"
