@@ -96,6 +96,9 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        t0 = time.time()
+        while self.proc and not self.rows and time.time() - t0 < 3.0:   # at least one sample
+            time.sleep(0.05)
         if self.proc:
             self.proc.terminate()
             try:
@@ -195,7 +198,8 @@ def main():
         dist.broadcast(buf, 0)
         nccl_id = bytes(buf.cpu().numpy().tobytes())
     pp = dict(ts.DEFAULT_PHYSICS_PARAMS, numSubsteps=args.substeps, worldBounds=list(mesh.wide_bounds(64.0)))
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=local_rank)   # a real (non-default) stream: the library enqueues on it, events time it
+    torch.cuda.set_stream(stream)
     body = ts.SoftBody(verts, tets, None, pp, solver="jacobi", arithmetic="fast", iters=args.iters,
                        cluster_size=args.cluster_size, reorder=not args.no_reorder, deterministic=not args.atomic,
                        device=local_rank, stream=stream.cuda_stream, rank=rank, world_size=world,
