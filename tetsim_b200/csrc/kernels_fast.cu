@@ -9,103 +9,258 @@ const KernelTable *fast_kernels() { return Launchers<false>::table(); }
 // =================================================================================================
 // Clustered Jacobi Neo-Hookean -- the throughput kernel (BASELINE config 4).
 //
-// One CTA = one tile of T consecutive tets of the (Morton-sorted) tet stream, one tet per thread.
-//   1. the tile's vertex list (unique vertices touched by its T tets, ~0.35 T of them) is gathered
-//      from HBM/L2 into shared memory as float4 (x,y,z,invMass): one LDG.128 per tile vertex;
-//   2. each thread streams its tet record with three coalesced LDG.128 (A,B,C planes = 48 B/tet:
-//      Q 36 B, invRestVolume 4 B, four 16-bit TILE-LOCAL vertex slots 8 B), gathers its 4 corners
-//      from shared memory (LDS.128), runs both Neo-Hookean projections in registers and parks the
-//      12 floats of corner dx in shared memory (3 x STS.128, 48-byte records -> conflict-free);
-//   3. the tile's vertices then sum their corners' dx straight out of shared memory.  Corner lists
-//      are stored as jagged diagonals (tile vertices sorted by descending tile valence, i-th corner
-//      of all vertices contiguous) so the 16-bit index loads are coalesced and a warp's lanes run
-//      the same trip count.  No shared-memory float atomics (sm_100a has no native one: ATOMS.CAST
-//      spin loops), no global atomics in the default flush: each tile writes its partial sums to
-//      its own slice of `part` with plain coalesced STG.128 and the vertex kernel adds the few
-//      (~1.6) slices of a vertex in a fixed order -> bit-reproducible run to run.
-//      (deterministic = 0 flushes with one REDG.E.ADD.F32x4 per tile vertex instead.)
-// Algorithmic traffic per launch: 56 B/tet + 32 B/vertex; actual DRAM traffic is
-// lower on the tet stream (48 B) and higher on the vertex side (tile overlap).
+// Persistent CTAs (grid = SMs x resident CTAs), each walking tiles c = blockIdx.x, + gridDim.x, ...
+// One tile = T consecutive tets of the (Morton-sorted) tet stream, one tet per thread.  Everything a
+// tile needs is staged in shared memory by ASYNCHRONOUS copies issued one tile ahead, so the math of
+// tile k overlaps the HBM/L2 latency of tile k+1 (round-1 ncu: the non-pipelined version sat at 35 %
+// issue utilisation with long-scoreboard and barrier stalls on top):
+//   * tet block (T*56 B contiguous: Q 36 B, invRestVolume 4 B, 4 vertex slots 8 B, 4 scatter
+//     destinations 8 B per tet, as planes) -> ONE cp.async.bulk (TMA, UBLKCP) on an mbarrier;
+//   * meta block (tile vertex ids, valences, diagonal offsets) -> ONE cp.async.bulk, two tiles ahead;
+//   * the tile's vertex records float4(x,y,z,invMass): indexed gather with cp.async 16 B (LDGSTS),
+//     straight from L2/HBM into shared memory, no register staging.
+// Per tile:  gather 4 corners (LDS.128) -> both Neo-Hookean projections in registers (device_math.cuh)
+//   -> each corner's dx is stored (STS.128) at its precomputed slot of a jagged-diagonal buffer
+//   (entry (i, j) = i-th corner of tile vertex j; vertices sorted by descending tile valence)
+//   -> barrier -> thread j sums entries (0..val_j, j): consecutive lanes read consecutive 16-B
+//   entries (conflict-free LDS.128, no index loads), in ascending (tet, corner) order
+//   -> one coalesced STG.128 of the tile's partial sum per tile vertex.
+// No shared-memory float atomics (sm_100a has none natively: ATOMS.CAST spin loops) and, in the
+// default flush, no global atomics either: the vertex kernel adds the ~3 tile partials of a vertex in a
+// fixed order -> results are bit-reproducible run to run.  (deterministic = 0 flushes with one
+// REDG.E.ADD.F32x4 per tile vertex instead.)
+// Algorithmic traffic per launch: 56 B/tet + 32 B/vertex.
 // =================================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(b))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done)
+            : "r"(smem_u32(b)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 template <int T>
-__global__ void __launch_bounds__(T) k_jacobi_cluster(int firstCluster, ClusterArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *sdx = reinterpret_cast<float *>(smem_raw);                          // [T * 12]
-    float4 *sx = reinterpret_cast<float4 *>(smem_raw + (size_t)T * 48);        // [maxTileVerts]
-    uint16_t *scol = reinterpret_cast<uint16_t *>(sx + a.maxTileVerts);        // [colStride]
+struct TileSmem {
+    static constexpr int TET_BYTES = T * 56;
+    // byte offsets inside dynamic shared memory (computed, never indexed: keeps them in registers)
+    int sxBytes, metaStride, sdx, sx0, meta0, bars, total;
+    __host__ __device__ TileSmem(int metaStride_, int maxTileVertsPad) {
+        sxBytes = maxTileVertsPad * 16;
+        metaStride = metaStride_;
+        sdx = 2 * TET_BYTES;
+        sx0 = sdx + 4 * T * 16;
+        meta0 = sx0 + 2 * sxBytes;
+        bars = meta0 + 3 * metaStride;
+        total = bars + 5 * 8 + 8;
+    }
+    __host__ __device__ int tet(int buf) const { return buf * TET_BYTES; }
+    __host__ __device__ int sx(int buf) const { return sx0 + buf * sxBytes; }
+    __host__ __device__ int meta(int slot) const { return meta0 + slot * metaStride; }
+};
 
-    const int c = firstCluster + blockIdx.x;
-    const int t = threadIdx.x;
-    const int v0 = a.clVertStart[c];
-    const int nl = a.clVertStart[c + 1] - v0;
-    const size_t rec = (size_t)c * T + t;
+template <int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) k_jacobi_tiles(TileArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const TileSmem<T> L(a.metaStride, a.maxTileVertsPad);
+    uint64_t *tetFull = reinterpret_cast<uint64_t *>(smem + L.bars);  // [2]
+    uint64_t *metaFull = tetFull + 2;                                 // [3]
+    unsigned char *const sdx = smem + L.sdx;
+    const int tid = threadIdx.x;
+    const int stride = gridDim.x;
+    const int first = blockIdx.x;
+    if (first >= a.numTiles) return;
 
-    // tet record: issue the streaming loads first so they overlap the tile gather
-    const float4 A = ldg4(a.A + rec), B = ldg4(a.B + rec), C = ldg4(a.C + rec);
-
-    for (int j = t; j < nl; j += T) sx[j] = a.x4[a.clVerts[v0 + j]];
-    if (t < a.colStride) scol[t] = a.colOff[(size_t)c * a.colStride + t];
+    if (tid == 0) {
+        mbar_init(tetFull + 0, 1); mbar_init(tetFull + 1, 1);
+        mbar_init(metaFull + 0, 1); mbar_init(metaFull + 1, 1); mbar_init(metaFull + 2, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
 
-    const unsigned s01 = __float_as_uint(C.z), s23 = __float_as_uint(C.w);
-    const float4 q0 = sx[s01 & 0xffffu], q1 = sx[s01 >> 16], q2 = sx[s23 & 0xffffu], q3 = sx[s23 >> 16];
-    V3 p[4] = {{q0.x, q0.y, q0.z}, {q1.x, q1.y, q1.z}, {q2.x, q2.y, q2.z}, {q3.x, q3.y, q3.z}};
-    const float w[4] = {q0.w, q1.w, q2.w, q3.w};
-    const float Q[9] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w, C.x};
     const SubstepParams *sp = a.sp;
-    float vm1 = nh_solve_fast(p, w, Q, C.y, sp->alphaDev, sp->alphaVol, sp->gammaVol);
+    const float alphaDev = sp->alphaDev, alphaVol = sp->alphaVol, gammaVol = sp->gammaVol;
 
-    float4 *d4 = reinterpret_cast<float4 *>(sdx + t * 12);
-    d4[0] = make_float4(p[0].x - q0.x, p[0].y - q0.y, p[0].z - q0.z, p[1].x - q1.x);
-    d4[1] = make_float4(p[1].y - q1.y, p[1].z - q1.z, p[2].x - q2.x, p[2].y - q2.y);
-    d4[2] = make_float4(p[2].z - q2.z, p[3].x - q3.x, p[3].y - q3.y, p[3].z - q3.z);
+    auto issue_meta = [&](int tile, int slot) {  // one thread
+        mbar_expect_tx(metaFull + slot, (uint32_t)a.metaStride);
+        bulk_g2s(smem + L.meta(slot), a.meta + (size_t)tile * a.metaStride, (uint32_t)a.metaStride, metaFull + slot);
+    };
+    auto issue_tets = [&](int tile, int buf) {  // one thread
+        mbar_expect_tx(tetFull + buf, (uint32_t)TileSmem<T>::TET_BYTES);
+        bulk_g2s(smem + L.tet(buf), a.tets + (size_t)tile * TileSmem<T>::TET_BYTES, (uint32_t)TileSmem<T>::TET_BYTES,
+                 tetFull + buf);
+    };
+    auto issue_gather = [&](int slot, int buf) {  // all threads
+        const unsigned char *m = smem + L.meta(slot);
+        const int nl = reinterpret_cast<const int *>(m)[1];
+        const int *ids = reinterpret_cast<const int *>(m + a.metaIdsOff);
+        float4 *sx = reinterpret_cast<float4 *>(smem + L.sx(buf));
+        for (int j = tid; j < nl; j += T) cp_async16(sx + j, a.x4 + ids[j]);
+        cp_async_commit();
+    };
 
-    if (a.volAcc) {  // volError (src/Softbody.js:163): warp-reduce, one double atomic per warp
-        float s = (C.y != 0.0f) ? vm1 : 0.0f;  // padding records carry invRestVolume = 0
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if ((t & 31) == 0) atomicAdd(a.volAcc, (double)s);
+    // prologue: meta of the first two tiles, then the first tile's vertex gather and tet block
+    if (tid == 0) {
+        issue_meta(first, 0);
+        if (first + stride < a.numTiles) issue_meta(first + stride, 1);
+        issue_tets(first, 0);
     }
-    __syncthreads();
+    mbar_wait(metaFull + 0, 0);
+    issue_gather(0, 0);
 
-    const uint16_t *jd = a.jds + (size_t)c * 4 * T;
-    for (int j = t; j < nl; j += T) {
-        const int val = a.clVal[v0 + j];
-        float ax = 0.0f, ay = 0.0f, az = 0.0f;
-#pragma unroll 4
-        for (int i = 0; i < val; i++) {
-            const unsigned e = jd[scol[i] + j];
-            const float *d = sdx + 3 * e;
-            ax += d[0]; ay += d[1]; az += d[2];
+    int k = 0;
+    for (int c = first; c < a.numTiles; c += stride, k++) {
+        const int cur = k & 1, mcur = k % 3;
+        cp_async_wait_all();
+        mbar_wait(tetFull + cur, (k >> 1) & 1);
+        __syncthreads();  // gathers of all threads landed; previous tile's vertex phase finished
+
+        // ---- prefetch tile k+1 (data) and tile k+2 (meta) ----
+        if (c + stride < a.numTiles) {
+            const int mnext = (k + 1) % 3;
+            mbar_wait(metaFull + mnext, ((k + 1) / 3) & 1);
+            issue_gather(mnext, cur ^ 1);
+            if (tid == 0) issue_tets(c + stride, cur ^ 1);
         }
-        if (a.acc) atomicAdd(a.acc + a.clVerts[v0 + j], make_float4(ax, ay, az, 0.0f));
-        else a.part[v0 + j] = make_float4(ax, ay, az, 0.0f);
+        if (tid == 0 && c + 2 * stride < a.numTiles) issue_meta(c + 2 * stride, (k + 2) % 3);
+
+        // ---- per-tet solve ----
+        const unsigned char *tb = smem + L.tet(cur);
+        const float4 A = reinterpret_cast<const float4 *>(tb)[tid];
+        const float4 B = reinterpret_cast<const float4 *>(tb + T * 16)[tid];
+        const float4 C = reinterpret_cast<const float4 *>(tb + T * 32)[tid];
+        const uint2 D = reinterpret_cast<const uint2 *>(tb + T * 48)[tid];
+        const unsigned char *sxb = smem + L.sx(cur);
+        const unsigned s01 = __float_as_uint(C.z), s23 = __float_as_uint(C.w);
+        const float4 q0 = *reinterpret_cast<const float4 *>(sxb + (s01 & 0xffffu));
+        const float4 q1 = *reinterpret_cast<const float4 *>(sxb + (s01 >> 16));
+        const float4 q2 = *reinterpret_cast<const float4 *>(sxb + (s23 & 0xffffu));
+        const float4 q3 = *reinterpret_cast<const float4 *>(sxb + (s23 >> 16));
+        V3 p[4] = {{q0.x, q0.y, q0.z}, {q1.x, q1.y, q1.z}, {q2.x, q2.y, q2.z}, {q3.x, q3.y, q3.z}};
+        const float w[4] = {q0.w, q1.w, q2.w, q3.w};
+        const float Q[9] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w, C.x};
+        const float vm1 = nh_solve_fast(p, w, Q, C.y, alphaDev, alphaVol, gammaVol);
+        *reinterpret_cast<float4 *>(sdx + (D.x & 0xffffu)) = make_float4(p[0].x - q0.x, p[0].y - q0.y, p[0].z - q0.z, 0.f);
+        *reinterpret_cast<float4 *>(sdx + (D.x >> 16)) = make_float4(p[1].x - q1.x, p[1].y - q1.y, p[1].z - q1.z, 0.f);
+        *reinterpret_cast<float4 *>(sdx + (D.y & 0xffffu)) = make_float4(p[2].x - q2.x, p[2].y - q2.y, p[2].z - q2.z, 0.f);
+        *reinterpret_cast<float4 *>(sdx + (D.y >> 16)) = make_float4(p[3].x - q3.x, p[3].y - q3.y, p[3].z - q3.z, 0.f);
+        if (a.volAcc) {  // volError (src/Softbody.js:163): warp-reduce, one double atomic per warp
+            float s = (C.y != 0.0f) ? vm1 : 0.0f;  // padding records carry invRestVolume = 0
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if ((tid & 31) == 0) atomicAdd(a.volAcc, (double)s);
+        }
+        __syncthreads();
+
+        // ---- per-tile-vertex sum of corner dx, fixed order ----
+        const unsigned char *m = smem + L.meta(mcur);
+        const int v0 = reinterpret_cast<const int *>(m)[0];
+        const int nl = reinterpret_cast<const int *>(m)[1];
+        const uint16_t *scol = reinterpret_cast<const uint16_t *>(m + 16);
+        for (int j = tid; j < nl; j += T) {
+            const int val = m[a.metaValOff + j];
+            const unsigned char *base = sdx + j * 16;
+            float ax = 0.0f, ay = 0.0f, az = 0.0f;
+#pragma unroll 4
+            for (int i = 0; i < val; i++) {
+                const float4 d = *reinterpret_cast<const float4 *>(base + scol[i]);
+                ax += d.x; ay += d.y; az += d.z;
+            }
+            if (a.acc) atomicAdd(a.acc + reinterpret_cast<const int *>(m + a.metaIdsOff)[j], make_float4(ax, ay, az, 0.0f));
+            else a.part[v0 + j] = make_float4(ax, ay, az, 0.0f);
+        }
     }
 }
 
-size_t jacobi_cluster_smem(int clusterSize, int maxTileVerts, int colStride) {
-    return (size_t)clusterSize * 48 + (size_t)maxTileVerts * 16 + (size_t)((colStride * 2 + 15) / 16) * 16;
+size_t jacobi_tiles_smem(int clusterSize, const TileArgs &a) {
+    switch (clusterSize) {
+        case 128: return (size_t)TileSmem<128>(a.metaStride, a.maxTileVertsPad).total;
+        case 256: return (size_t)TileSmem<256>(a.metaStride, a.maxTileVertsPad).total;
+        default: return (size_t)TileSmem<512>(a.metaStride, a.maxTileVertsPad).total;
+    }
 }
 
-template <int T>
-static void launch_cluster_T(cudaStream_t s, int first, int n, const ClusterArgs &a) {
-    size_t smem = jacobi_cluster_smem(T, a.maxTileVerts, a.colStride);
+template <int T, int MINB>
+static void launch_tiles_T(cudaStream_t s, const TileArgs &a) {
+    const size_t smem = (size_t)TileSmem<T>(a.metaStride, a.maxTileVertsPad).total;
     static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(k_jacobi_cluster<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static int ctasPerSm = 0, numSms = 0;
+    if (smem != configured) {
+        cudaFuncSetAttribute(k_jacobi_tiles<T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, k_jacobi_tiles<T, MINB>, T, smem);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&numSms, cudaDevAttrMultiProcessorCount, dev);
         configured = smem;
     }
-    k_jacobi_cluster<T><<<n, T, smem, s>>>(first, a);
+    if (ctasPerSm < 1) ctasPerSm = 1;
+    int grid = numSms * ctasPerSm;  // persistent: every CTA resident, tiles strided over the grid
+    if (grid > a.numTiles) grid = a.numTiles;
+    k_jacobi_tiles<T, MINB><<<grid, T, smem, s>>>(a);
 }
 
-void launch_jacobi_cluster(cudaStream_t s, int clusterSize, int firstCluster, int numClusters, const ClusterArgs &a) {
-    if (numClusters <= 0) return;
+void launch_jacobi_tiles(cudaStream_t s, int clusterSize, const TileArgs &a) {
+    if (a.numTiles <= 0) return;
     switch (clusterSize) {
-        case 128: launch_cluster_T<128>(s, firstCluster, numClusters, a); break;
-        case 256: launch_cluster_T<256>(s, firstCluster, numClusters, a); break;
-        case 512: launch_cluster_T<512>(s, firstCluster, numClusters, a); break;
+        case 128: launch_tiles_T<128, 6>(s, a); break;
+        case 256: launch_tiles_T<256, 4>(s, a); break;
+        case 512: launch_tiles_T<512, 2>(s, a); break;
         default: break;
     }
+}
+
+// Tile-major tet blocks from the tet-order rest data (device) and the host-built slot/destination words.
+template <int T>
+__global__ void k_build_tiles(int numRecords, const int *__restrict__ order, const float *__restrict__ Q9,
+                              const float *__restrict__ irv, const uint4 *__restrict__ aux,
+                              unsigned char *__restrict__ tets) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= numRecords) return;
+    const int tile = r / T, t = r % T;
+    unsigned char *tb = tets + (size_t)tile * T * 56;
+    const int e = order[r];
+    const uint4 x = aux[r];
+    float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A;
+    float q8 = 0.f, rv = 0.f;
+    if (e >= 0) {
+        const float *q = Q9 + 9 * (size_t)e;
+        A = make_float4(q[0], q[1], q[2], q[3]);
+        B = make_float4(q[4], q[5], q[6], q[7]);
+        q8 = q[8];
+        rv = irv[e];
+    }
+    reinterpret_cast<float4 *>(tb)[t] = A;
+    reinterpret_cast<float4 *>(tb + T * 16)[t] = B;
+    reinterpret_cast<float4 *>(tb + T * 32)[t] = make_float4(q8, rv, __uint_as_float(x.x), __uint_as_float(x.y));
+    reinterpret_cast<uint2 *>(tb + T * 48)[t] = make_uint2(x.z, x.w);
+}
+void launch_build_tiles(cudaStream_t s, int clusterSize, int numRecords, const int *order, const float *Q9,
+                        const float *irv, const uint4 *aux, unsigned char *tets) {
+    if (numRecords <= 0) return;
+    const int g = cdiv(numRecords, 256);
+    if (clusterSize == 128) k_build_tiles<128><<<g, 256, 0, s>>>(numRecords, order, Q9, irv, aux, tets);
+    else if (clusterSize == 256) k_build_tiles<256><<<g, 256, 0, s>>>(numRecords, order, Q9, irv, aux, tets);
+    else k_build_tiles<512><<<g, 256, 0, s>>>(numRecords, order, Q9, irv, aux, tets);
 }
 
 // Vertex side of the clustered Jacobi: x += (sum of the vertex's tile partials) / valence, optionally

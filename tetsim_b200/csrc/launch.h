@@ -46,23 +46,26 @@ const KernelTable *exact_kernels();
 const KernelTable *fast_kernels();
 
 // ---- FAST-only throughput path: clustered Jacobi (kernels_fast.cu) ----
-struct ClusterArgs {
-    const float4 *x4;
-    const float4 *A, *B, *C;        // tet stream, cluster-major, clusterSize records per cluster
-    const int *clVertStart;         // [numClusters + 1] offsets into clVerts / clVal / part
-    const int *clVerts;             // tile vertex list (handle-local vertex ids), descending tile valence
-    const uint8_t *clVal;           // tile valence of each tile vertex
-    const uint16_t *jds;            // [numClusters * 4 * clusterSize] corner lists, jagged-diagonal order
-    const uint16_t *colOff;         // [numClusters * colStride] column offsets of the jagged diagonals
-    int colStride;
-    float4 *part;                   // per-tile partial dx sums (deterministic flush), parallel to clVerts
+// Tile-major HBM layout consumed by the persistent tile kernel.  Per tile of T tets:
+//   tet block  (T * 56 B, one bulk async copy): planes A[T] float4 (Q0..Q3), B[T] float4 (Q4..Q7),
+//              C[T] float4 (Q8, invRestVolume, slot01, slot23), D[T] uint2 (dest01, dest23)
+//   meta block (metaStride B, one bulk async copy): see ClusterPlan::tileMeta in mesh_prep.h
+struct TileArgs {
+    const float4 *x4;               // handle-local vertex records (x, y, z, invMass)
+    const unsigned char *tets;      // [numTiles * T * 56]
+    const unsigned char *meta;      // [numTiles * metaStride]
+    int numTiles;
+    int metaStride, metaValOff, metaIdsOff, colStride, maxTileVertsPad;
+    float4 *part;                   // per-tile partial dx sums (deterministic flush)
     float4 *acc;                    // global accumulator (atomic flush), or NULL
     double *volAcc;                 // sum over tets of det F - 1, or NULL
     const SubstepParams *sp;
-    int maxTileVerts;
 };
-void launch_jacobi_cluster(cudaStream_t, int clusterSize, int firstCluster, int numClusters, const ClusterArgs &a);
-size_t jacobi_cluster_smem(int clusterSize, int maxTileVerts, int colStride);
+void launch_jacobi_tiles(cudaStream_t, int clusterSize, const TileArgs &a);
+size_t jacobi_tiles_smem(int clusterSize, const TileArgs &a);
+// record r of the tile stream: Q/irv of tet order[r] (or zeros when order[r] < 0) + aux[r] -> tet blocks
+void launch_build_tiles(cudaStream_t, int clusterSize, int numRecords, const int *order, const float *Q9,
+                        const float *irv, const uint4 *aux, unsigned char *tets);
 
 struct ApplyArgs {
     float4 *x4, *prev4, *vel4;

@@ -209,25 +209,25 @@ bool build_cluster_plan(int numVerts, int numTets, const int *tetIds, const std:
     // tiles
     const size_t nRec = (size_t)P.numClusters * T;
     P.recordTet.assign(nRec, -1);
-    P.recordSlots.assign(2 * nRec, 0u);
+    P.recordAux.assign(4 * nRec, 0u);
     P.clVertStart.assign((size_t)P.numClusters + 1, 0);
-    P.jds.assign(4 * nRec, 0);
     std::vector<int> stamp((size_t)P.numLocalVerts, -1), tileIdx((size_t)P.numLocalVerts, 0);
     std::vector<int> tileVerts, tileVal, perm, rank_of;
     std::vector<std::vector<uint16_t>> colOffs((size_t)P.numClusters);
-    std::vector<int> cornerStart, cornerFill;
-    std::vector<uint16_t> corners;
+    std::vector<uint8_t> allVal;
+    std::vector<int> cornerRank;  // per corner of the tile: its index i in its vertex's list
     int maxTileVal = 0;
     for (int c = 0; c < P.numClusters; c++) {
         const int pb = (c0 + c) * T, pe = std::min(numTets, pb + T);
         tileVerts.clear(); tileVal.clear();
+        cornerRank.assign(4 * (size_t)T, 0);
         for (int pos = pb; pos < pe; pos++) {
             const int *t = tetIds + 4 * (size_t)order[pos];
             P.recordTet[(size_t)c * T + (pos - pb)] = order[pos];
             for (int k = 0; k < 4; k++) {
                 int lv = local[t[k]];
                 if (stamp[lv] != c) { stamp[lv] = c; tileIdx[lv] = (int)tileVerts.size(); tileVerts.push_back(lv); tileVal.push_back(0); }
-                tileVal[tileIdx[lv]]++;
+                cornerRank[4 * (size_t)(pos - pb) + k] = tileVal[tileIdx[lv]]++;  // ascending (tet, corner) order
             }
         }
         const int nl = (int)tileVerts.size();
@@ -241,45 +241,52 @@ bool build_cluster_plan(int numVerts, int numTets, const int *tetIds, const std:
         if (tv > 255) { err = "a vertex has more than 255 tet corners inside one tile"; return false; }
         maxTileVal = std::max(maxTileVal, tv);
         P.clVertStart[c + 1] = P.clVertStart[c] + nl;
-        for (int j = 0; j < nl; j++) { P.clVerts.push_back(tileVerts[perm[j]]); P.clVal.push_back((uint8_t)tileVal[perm[j]]); }
+        for (int j = 0; j < nl; j++) { P.clVerts.push_back(tileVerts[perm[j]]); allVal.push_back((uint8_t)tileVal[perm[j]]); }
         P.maxTileVerts = std::max(P.maxTileVerts, nl);
-        // per-vertex corner lists (ascending 4*tetLocal + corner), then jagged-diagonal layout
-        cornerStart.assign((size_t)nl + 1, 0);
-        for (int j = 0; j < nl; j++) cornerStart[j + 1] = cornerStart[j] + tileVal[perm[j]];
-        cornerFill.assign(cornerStart.begin(), cornerStart.end() - 1);
-        corners.resize((size_t)cornerStart[nl]);
-        for (int pos = pb; pos < pe; pos++) {
-            const int *t = tetIds + 4 * (size_t)order[pos];
-            uint32_t s[4];
-            for (int k = 0; k < 4; k++) {
-                int j = rank_of[tileIdx[local[t[k]]]];
-                s[k] = (uint32_t)j;
-                corners[cornerFill[j]++] = (uint16_t)(4 * (pos - pb) + k);
-            }
-            size_t r = (size_t)c * T + (pos - pb);
-            P.recordSlots[2 * r] = s[0] | s[1] << 16;
-            P.recordSlots[2 * r + 1] = s[2] | s[3] << 16;
-        }
+        // jagged diagonals: diagonal i holds the i-th corner of every vertex with valence > i; vertices
+        // are valence-sorted, so those are a prefix and entry (i, j) sits at colOff[i] + j
         std::vector<uint16_t> &co = colOffs[c];
         co.assign((size_t)tv + 1, 0);
-        uint16_t *jd = P.jds.data() + (size_t)c * 4 * T;
-        int off = 0;
+        int off = 0, cnt = nl;
         for (int i = 0; i < tv; i++) {
             co[i] = (uint16_t)off;
-            int cnt = 0;
-            while (cnt < nl && tileVal[perm[cnt]] > i) {  // vertices are valence-sorted: a prefix qualifies
-                jd[off + cnt] = corners[cornerStart[cnt] + i];
-                cnt++;
-            }
+            while (cnt > 0 && tileVal[perm[cnt - 1]] <= i) cnt--;
             off += cnt;
         }
         co[tv] = (uint16_t)off;
+        for (int pos = pb; pos < pe; pos++) {
+            const int *t = tetIds + 4 * (size_t)order[pos];
+            uint32_t sl[4], ds[4];
+            for (int k = 0; k < 4; k++) {
+                int j = rank_of[tileIdx[local[t[k]]]];
+                sl[k] = 16u * (uint32_t)j;
+                ds[k] = 16u * ((uint32_t)co[cornerRank[4 * (size_t)(pos - pb) + k]] + (uint32_t)j);
+            }
+            size_t r = (size_t)c * T + (pos - pb);
+            P.recordAux[4 * r + 0] = sl[0] | sl[1] << 16;
+            P.recordAux[4 * r + 1] = sl[2] | sl[3] << 16;
+            P.recordAux[4 * r + 2] = ds[0] | ds[1] << 16;
+            P.recordAux[4 * r + 3] = ds[2] | ds[3] << 16;
+        }
     }
-    P.colStride = ((maxTileVal + 1 + 7) / 8) * 8;
-    P.colOff.assign((size_t)P.numClusters * P.colStride, 0);
-    for (int c = 0; c < P.numClusters; c++)
-        std::copy(colOffs[c].begin(), colOffs[c].end(), P.colOff.begin() + (size_t)c * P.colStride);
     if (P.maxTileVerts < 1) P.maxTileVerts = 1;
+    if (16 * P.maxTileVerts > 65535 || 16 * 4 * T > 65535) { err = "tile too large for 16-bit byte offsets"; return false; }
+    P.colStride = ((maxTileVal + 1 + 7) / 8) * 8;
+    P.maxTileVertsPad = ((P.maxTileVerts + 15) / 16) * 16;
+    P.metaValOff = 16 + 2 * P.colStride;
+    P.metaIdsOff = P.metaValOff + P.maxTileVertsPad;
+    P.metaStride = P.metaIdsOff + 4 * P.maxTileVertsPad;
+    P.tileMeta.assign((size_t)P.numClusters * P.metaStride, 0);
+    for (int c = 0; c < P.numClusters; c++) {
+        unsigned char *m = P.tileMeta.data() + (size_t)c * P.metaStride;
+        const int v0 = P.clVertStart[c], nl = P.clVertStart[c + 1] - v0;
+        int hdr[4] = {v0, nl, (int)colOffs[c].size() - 1, 0};
+        memcpy(m, hdr, 16);
+        uint16_t *co = reinterpret_cast<uint16_t *>(m + 16);
+        for (size_t i = 0; i < colOffs[c].size(); i++) co[i] = (uint16_t)(16u * colOffs[c][i]);
+        memcpy(m + P.metaValOff, allVal.data() + v0, (size_t)nl);
+        memcpy(m + P.metaIdsOff, P.clVerts.data() + v0, 4 * (size_t)nl);
+    }
 
     // vertex -> partial-sum slots, ascending tile order
     P.vpStart.assign((size_t)P.numLocalVerts + 1, 0);

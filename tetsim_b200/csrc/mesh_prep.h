@@ -45,14 +45,21 @@ struct ClusterPlan {
     int numBoundary = 0;                // global count of rank-shared vertices (same on every rank)
     std::vector<int> localToCaller;     // [numLocalVerts]
     std::vector<int> recordTet;         // [numClusters * T] caller tet index, -1 = padding
-    std::vector<uint32_t> recordSlots;  // [numClusters * T * 2] packed 16-bit tile slots
+    // per record: {slot0|slot1<<16, slot2|slot3<<16, dest0|dest1<<16, dest2|dest3<<16}.  slot = byte offset
+    // (16 * tile vertex index) of a corner's position in the staged vertex tile; dest = byte offset
+    // (16 * entry) of the corner's dx in the staged jagged-diagonal sum buffer.
+    std::vector<uint32_t> recordAux;    // [numClusters * T * 4]
     std::vector<int> clVertStart;       // [numClusters + 1]
     std::vector<int> clVerts;           // local vertex ids per tile, descending tile valence
-    std::vector<uint8_t> clVal;         // tile valence per tile vertex
-    std::vector<uint16_t> jds;          // [numClusters * 4T]
-    std::vector<uint16_t> colOff;       // [numClusters * colStride]
+    // One fixed-stride metadata block per tile, fetched with a single bulk async copy:
+    //   [0,16)   int32 {first partial-sum slot, tile vertex count, max tile valence, 0}
+    //   [16, ..) uint16 colOff[colStride]   byte offset (16 * entry) of jagged diagonal i
+    //   then     uint8  val[maxTileVertsPad] tile valence of tile vertex j (descending)
+    //   then     int32  ids[maxTileVertsPad] handle-local vertex id of tile vertex j
+    std::vector<unsigned char> tileMeta;
+    int metaStride = 0, metaValOff = 0, metaIdsOff = 0;
     int colStride = 0;
-    int maxTileVerts = 0;
+    int maxTileVerts = 0, maxTileVertsPad = 0;
     std::vector<int> vpStart, vpSlot;   // local vertex -> indices into the partial-sum array
     std::vector<float> invValence;      // [numLocalVerts] 1 / GLOBAL valence
     int localTets = 0;

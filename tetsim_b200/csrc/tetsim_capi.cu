@@ -132,9 +132,8 @@ struct tetsim {
     DevBuf<float4> dx;
     // Jacobi cluster path
     ClusterPlan plan;
-    DevBuf<int> clVertStart, clVerts, vpStart, vpSlot;
-    DevBuf<uint8_t> clVal;
-    DevBuf<uint16_t> jds, colOff;
+    DevBuf<int> vpStart, vpSlot;
+    DevBuf<unsigned char> tileTets, tileMeta;
     DevBuf<float4> part, acc, bsum;
     DevBuf<float> invVal;
     bool clustered = false;
@@ -169,8 +168,8 @@ struct tetsim {
         return (int64_t)(x4.bytes() + prev4.bytes() + vel4.bytes() + vertId.bytes() + Q9.bytes() + irv.bytes() +
                          invMass.bytes() + ids.bytes() + cStart.bytes() + cEnt.bytes() + A.bytes() + B.bytes() +
                          C.bytes() + I.bytes() + order.bytes() + levelStart.bytes() + bodies.bytes() +
-                         volTerm.bytes() + dx.bytes() + clVertStart.bytes() + clVerts.bytes() + vpStart.bytes() +
-                         vpSlot.bytes() + clVal.bytes() + jds.bytes() + colOff.bytes() + part.bytes() + acc.bytes() +
+                         volTerm.bytes() + dx.bytes() + vpStart.bytes() + vpSlot.bytes() + tileTets.bytes() +
+                         tileMeta.bytes() + part.bytes() + acc.bytes() +
                          bsum.bytes() + invVal.bytes() + rest.bytes() + quat.bytes() + tStart.bytes() + tEnt.bytes() +
                          stage3.bytes() + visV.bytes() + visTri.bytes() + vtStart.bytes() + vtEnt.bytes() +
                          visPos.bytes() + visNrm.bytes());
@@ -343,24 +342,17 @@ int build_jacobi_cluster(tetsim *h, const std::vector<float> &verts, const std::
     cudaStream_t s = h->stream;
     const size_t nRec = (size_t)P.numClusters * P.T;
     CK(h->order.upload(P.recordTet, s));
-    CK(h->A.alloc(nRec)); CK(h->B.alloc(nRec)); CK(h->C.alloc(nRec));
     {
-        std::vector<float4> Ch(nRec);
-        for (size_t r = 0; r < nRec; r++) {
-            float z, w;
-            memcpy(&z, &P.recordSlots[2 * r], 4);
-            memcpy(&w, &P.recordSlots[2 * r + 1], 4);
-            Ch[r] = make_float4(0.f, 0.f, z, w);
-        }
-        if (nRec) CK(cudaMemcpyAsync(h->C.p, Ch.data(), nRec * sizeof(float4), cudaMemcpyHostToDevice, s));
+        DevBuf<uint4> aux;
+        CK(aux.alloc(nRec));
+        if (nRec) CK(cudaMemcpyAsync(aux.p, P.recordAux.data(), nRec * sizeof(uint4), cudaMemcpyHostToDevice, s));
+        CK(h->tileTets.alloc(nRec * 56));
+        launch_build_tiles(s, P.T, (int)nRec, h->order.p, h->Q9.p, h->irv.p, aux.p, h->tileTets.p);
+        CK(cudaGetLastError());
         CK(cudaStreamSynchronize(s));
+        aux.release();
     }
-    launch_build_stream(s, (int)nRec, h->order.p, h->Q9.p, h->irv.p, h->A.p, h->B.p, h->C.p);
-    CK(h->clVertStart.upload(P.clVertStart, s));
-    CK(h->clVerts.upload(P.clVerts, s));
-    CK(h->clVal.upload(P.clVal, s));
-    CK(h->jds.upload(P.jds, s));
-    CK(h->colOff.upload(P.colOff, s));
+    CK(h->tileMeta.upload(P.tileMeta, s));
     CK(h->vpStart.upload(P.vpStart, s));
     CK(h->vpSlot.upload(P.vpSlot, s));
     CK(h->invVal.upload(P.invValence, s));
@@ -392,6 +384,16 @@ int build_polar(tetsim *h, const std::vector<int> &tetIds) {
 }
 
 // ---- substep scheduling --------------------------------------------------------------------------
+
+TileArgs tile_args(const tetsim *h) {
+    const ClusterPlan &P = h->plan;
+    TileArgs a{};
+    a.x4 = h->x4.p; a.tets = h->tileTets.p; a.meta = h->tileMeta.p; a.numTiles = P.numClusters;
+    a.metaStride = P.metaStride; a.metaValOff = P.metaValOff; a.metaIdsOff = P.metaIdsOff;
+    a.colStride = P.colStride; a.maxTileVertsPad = P.maxTileVertsPad;
+    a.part = h->part.p; a.acc = nullptr; a.volAcc = nullptr; a.sp = h->sp.p;
+    return a;
+}
 
 // Enqueue `count` substeps.  Inside one call dt and the parameters are constant, which is what lets
 // the clustered Jacobi path fuse a substep's post with the next substep's predict.
@@ -430,12 +432,8 @@ int enqueue_substeps(tetsim *h, int count) {
                 } else {
                     const ClusterPlan &P = h->plan;
                     if (step == 0) { K->predict(s, h->nInt, h->x4.p, h->prev4.p, h->vel4.p, sp); h->enq++; }
-                    ClusterArgs ca{};
-                    ca.x4 = h->x4.p; ca.A = h->A.p; ca.B = h->B.p; ca.C = h->C.p;
-                    ca.clVertStart = h->clVertStart.p; ca.clVerts = h->clVerts.p; ca.clVal = h->clVal.p;
-                    ca.jds = h->jds.p; ca.colOff = h->colOff.p; ca.colStride = P.colStride;
-                    ca.part = h->part.p; ca.acc = h->acc.p; ca.volAcc = h->volTerm.p; ca.sp = sp;
-                    ca.maxTileVerts = P.maxTileVerts;
+                    TileArgs ca = tile_args(h);
+                    ca.acc = h->acc.p; ca.volAcc = h->volTerm.p;
                     ApplyArgs aa{};
                     aa.x4 = h->x4.p; aa.prev4 = h->prev4.p; aa.vel4 = h->vel4.p;
                     aa.vpStart = h->vpStart.p; aa.vpSlot = h->vpSlot.p; aa.part = h->part.p; aa.acc = h->acc.p;
@@ -444,7 +442,7 @@ int enqueue_substeps(tetsim *h, int count) {
                     const bool multi = h->opt.worldSize > 1 && P.numBoundary > 0;
                     for (int it = 0; it < h->opt.iters; it++) {
                         if (h->trackVol) CK(cudaMemsetAsync(h->volTerm.p, 0, sizeof(double), s));
-                        launch_jacobi_cluster(s, P.T, 0, P.numClusters, ca);
+                        launch_jacobi_tiles(s, P.T, ca);
                         h->enq += 2;  // tile kernel + vertex kernel
                         const bool last = it == h->opt.iters - 1;
                         const int mode = !last ? 0 : (step + 1 < count ? 2 : 1);
@@ -733,12 +731,12 @@ void tetsim_destroy(tetsim_t *h) {
     if (h->comm) g_nccl.CommDestroy(h->comm);
     DevBuf<float4> *f4[] = {&h->x4, &h->prev4, &h->vel4, &h->A, &h->B, &h->C, &h->dx, &h->part, &h->acc, &h->bsum, &h->rest, &h->quat, &h->visV};
     for (auto *b : f4) b->release();
-    DevBuf<int> *i1[] = {&h->vertId, &h->cStart, &h->cEnt, &h->order, &h->levelStart, &h->clVertStart, &h->clVerts, &h->vpStart, &h->vpSlot, &h->tStart, &h->tEnt, &h->grabOut, &h->visTri, &h->vtStart, &h->vtEnt};
+    DevBuf<int> *i1[] = {&h->vertId, &h->cStart, &h->cEnt, &h->order, &h->levelStart, &h->vpStart, &h->vpSlot, &h->tStart, &h->tEnt, &h->grabOut, &h->visTri, &h->vtStart, &h->vtEnt};
     for (auto *b : i1) b->release();
     DevBuf<float> *f1[] = {&h->Q9, &h->irv, &h->invMass, &h->invVal, &h->stage3, &h->visPos, &h->visNrm};
     for (auto *b : f1) b->release();
     h->ids.release(); h->I.release(); h->bodies.release(); h->volTerm.release(); h->volOut.release();
-    h->clVal.release(); h->jds.release(); h->colOff.release(); h->sp.release(); h->grabP.release(); h->grabScratch.release();
+    h->tileTets.release(); h->tileMeta.release(); h->sp.release(); h->grabP.release(); h->grabScratch.release();
     if (h->ownStream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -935,18 +933,14 @@ int tetsim_time_kernel(tetsim_t *h, int32_t reps, double *msPerLaunch, int64_t *
     DeviceGuard g(h->device);
     cudaStream_t s = h->stream;
     const ClusterPlan &P = h->plan;
-    ClusterArgs ca{};
-    ca.x4 = h->x4.p; ca.A = h->A.p; ca.B = h->B.p; ca.C = h->C.p;
-    ca.clVertStart = h->clVertStart.p; ca.clVerts = h->clVerts.p; ca.clVal = h->clVal.p;
-    ca.jds = h->jds.p; ca.colOff = h->colOff.p; ca.colStride = P.colStride;
-    ca.part = h->part.p; ca.acc = nullptr; ca.volAcc = nullptr; ca.sp = h->sp.p; ca.maxTileVerts = P.maxTileVerts;
+    TileArgs ca = tile_args(h);
     DevBuf<float4> scratch;  // atomic-flush handles have no partial-sum array: give the kernel one
     if (!ca.part) { CK(scratch.alloc(P.clVerts.size())); ca.part = scratch.p; }
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    launch_jacobi_cluster(s, P.T, 0, P.numClusters, ca);  // warm-up
+    launch_jacobi_tiles(s, P.T, ca);  // warm-up
     CK(cudaEventRecord(e0, s));
-    for (int r = 0; r < reps; r++) launch_jacobi_cluster(s, P.T, 0, P.numClusters, ca);
+    for (int r = 0; r < reps; r++) launch_jacobi_tiles(s, P.T, ca);
     CK(cudaEventRecord(e1, s));
     CK(cudaEventSynchronize(e1));
     float ms = 0.f;
