@@ -69,7 +69,7 @@ struct TileSmem {
         sxBytes = maxTileVertsPad * 16;
         metaStride = metaStride_;
         sdx = 2 * TET_BYTES;
-        sx0 = sdx + 4 * T * 16;
+        sx0 = sdx + (4 * T + 1) * 16;  // + one spare entry for padding records
         meta0 = sx0 + 2 * sxBytes;
         bars = meta0 + 3 * metaStride;
         total = bars + 5 * 8 + 8;

@@ -269,6 +269,13 @@ bool build_cluster_plan(int numVerts, int numTets, const int *tetIds, const std:
             P.recordAux[4 * r + 3] = ds[2] | ds[3] << 16;
         }
     }
+    // padding records of the last tile: read tile vertex 0, park their (zero) dx in the spare entry 4T
+    for (size_t r = 0; r < nRec; r++)
+        if (P.recordTet[r] < 0) {
+            const uint32_t spare = 16u * 4u * (uint32_t)T;
+            P.recordAux[4 * r + 2] = spare | spare << 16;
+            P.recordAux[4 * r + 3] = spare | spare << 16;
+        }
     if (P.maxTileVerts < 1) P.maxTileVerts = 1;
     if (16 * P.maxTileVerts > 65535 || 16 * 4 * T > 65535) { err = "tile too large for 16-bit byte offsets"; return false; }
     P.colStride = ((maxTileVal + 1 + 7) / 8) * 8;
