@@ -117,6 +117,9 @@ typedef struct TetSimInfo {
     int64_t deviceBytes;      /* device memory held by the handle                                     */
     int64_t sumLocalVerts;    /* Jacobi: sum over clusters of tile vertex counts                      */
     int64_t kernelLaunches;   /* kernels launched by simulate/step since create (graph replays count) */
+    int64_t tileMetaBytes;    /* Jacobi: bytes of per-tile metadata streamed per launch               */
+    int32_t maxTileVerts;     /* Jacobi: largest tile vertex count                                    */
+    int32_t reserved_;
 } TetSimInfo;
 
 typedef struct tetsim tetsim_t;

@@ -35,7 +35,7 @@ def test_header_python_and_library_agree():
 def test_struct_layouts_match_header():
     assert C.sizeof(_capi.TetSimParams) == 11 * 8
     assert C.sizeof(_capi.TetSimOptions) == 12 * 4 + 2 * 8
-    assert C.sizeof(_capi.TetSimInfo) == 16 * 4 + 3 * 8
+    assert C.sizeof(_capi.TetSimInfo) == 16 * 4 + 4 * 8 + 2 * 4
     p = _capi.default_params()
     assert (p.gravity, p.friction, p.density, p.devCompliance, p.volCompliance) == (-9.81, 1000.0, 1000.0, 1e-5, 0.0)
     assert list(p.worldBounds) == [-2.5, -1.0, -2.5, 2.5, 10.0, 2.5]      # src/main.js:32

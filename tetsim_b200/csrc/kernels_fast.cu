@@ -101,9 +101,10 @@ __global__ void __launch_bounds__(T, MINB) k_jacobi_tiles(TileArgs a) {
     const SubstepParams *sp = a.sp;
     const float alphaDev = sp->alphaDev, alphaVol = sp->alphaVol, gammaVol = sp->gammaVol;
 
-    auto issue_meta = [&](int tile, int slot) {  // one thread
-        mbar_expect_tx(metaFull + slot, (uint32_t)a.metaStride);
-        bulk_g2s(smem + L.meta(slot), a.meta + (size_t)tile * a.metaStride, (uint32_t)a.metaStride, metaFull + slot);
+    auto issue_meta = [&](uint32_t o, uint32_t end, int slot) {  // one thread; block = [16*o, 16*end)
+        const uint32_t bytes = (end - o) * 16u;
+        mbar_expect_tx(metaFull + slot, bytes);
+        bulk_g2s(smem + L.meta(slot), a.meta + (size_t)o * 16, bytes, metaFull + slot);
     };
     auto issue_tets = [&](int tile, int buf) {  // one thread
         mbar_expect_tx(tetFull + buf, (uint32_t)TileSmem<T>::TET_BYTES);
@@ -113,17 +114,21 @@ __global__ void __launch_bounds__(T, MINB) k_jacobi_tiles(TileArgs a) {
     auto issue_gather = [&](int slot, int buf) {  // all threads
         const unsigned char *m = smem + L.meta(slot);
         const int nl = reinterpret_cast<const int *>(m)[1];
-        const int *ids = reinterpret_cast<const int *>(m + a.metaIdsOff);
+        const int *ids = reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3]);
         float4 *sx = reinterpret_cast<float4 *>(smem + L.sx(buf));
         for (int j = tid; j < nl; j += T) cp_async16(sx + j, a.x4 + ids[j]);
         cp_async_commit();
     };
 
-    // prologue: meta of the first two tiles, then the first tile's vertex gather and tet block
+    // prologue: meta of the first two tiles, then the first tile's vertex gather and tet block.
+    // Thread 0 keeps the block range of the tile whose meta it issues NEXT iteration in registers
+    // (loaded one iteration early, so the dependent global load never stalls the issue).
+    uint32_t nOff = 0, nEnd = 0;
     if (tid == 0) {
-        issue_meta(first, 0);
-        if (first + stride < a.numTiles) issue_meta(first + stride, 1);
+        issue_meta(a.metaOff[first], a.metaOff[first + 1], 0);
+        if (first + stride < a.numTiles) issue_meta(a.metaOff[first + stride], a.metaOff[first + stride + 1], 1);
         issue_tets(first, 0);
+        if (first + 2 * stride < a.numTiles) { nOff = a.metaOff[first + 2 * stride]; nEnd = a.metaOff[first + 2 * stride + 1]; }
     }
     mbar_wait(metaFull + 0, 0);
     issue_gather(0, 0);
@@ -142,7 +147,10 @@ __global__ void __launch_bounds__(T, MINB) k_jacobi_tiles(TileArgs a) {
             issue_gather(mnext, cur ^ 1);
             if (tid == 0) issue_tets(c + stride, cur ^ 1);
         }
-        if (tid == 0 && c + 2 * stride < a.numTiles) issue_meta(c + 2 * stride, (k + 2) % 3);
+        if (tid == 0 && c + 2 * stride < a.numTiles) {
+            issue_meta(nOff, nEnd, (k + 2) % 3);
+            if (c + 3 * stride < a.numTiles) { nOff = a.metaOff[c + 3 * stride]; nEnd = a.metaOff[c + 3 * stride + 1]; }
+        }
 
         // ---- per-tet solve ----
         const unsigned char *tb = smem + L.tet(cur);
@@ -173,21 +181,32 @@ __global__ void __launch_bounds__(T, MINB) k_jacobi_tiles(TileArgs a) {
         __syncthreads();
 
         // ---- per-tile-vertex sum of corner dx, fixed order ----
+        // Two lanes per tile vertex: lane h of the pair sums diagonals h, h+2, ... and the halves are
+        // combined with one shuffle (even half + odd half: a fixed order, so still reproducible).
+        // Halving the trip count and doubling the active lanes is what keeps this phase from
+        // holding the CTA's other warps at the next barrier.
         const unsigned char *m = smem + L.meta(mcur);
         const int v0 = reinterpret_cast<const int *>(m)[0];
         const int nl = reinterpret_cast<const int *>(m)[1];
         const uint16_t *scol = reinterpret_cast<const uint16_t *>(m + 16);
-        for (int j = tid; j < nl; j += T) {
-            const int val = m[a.metaValOff + j];
+        for (int jj = tid; jj < 2 * ((nl + 15) & ~15); jj += T) {  // whole warps stay together for the shuffle
+            const int j = jj >> 1, h = jj & 1;
+            const int val = j < nl ? m[a.metaValOff + j] : 0;
             const unsigned char *base = sdx + j * 16;
             float ax = 0.0f, ay = 0.0f, az = 0.0f;
 #pragma unroll 4
-            for (int i = 0; i < val; i++) {
+            for (int i = h; i < val; i += 2) {
                 const float4 d = *reinterpret_cast<const float4 *>(base + scol[i]);
                 ax += d.x; ay += d.y; az += d.z;
             }
-            if (a.acc) atomicAdd(a.acc + reinterpret_cast<const int *>(m + a.metaIdsOff)[j], make_float4(ax, ay, az, 0.0f));
-            else a.part[v0 + j] = make_float4(ax, ay, az, 0.0f);
+            ax += __shfl_xor_sync(0xffffffffu, ax, 1);
+            ay += __shfl_xor_sync(0xffffffffu, ay, 1);
+            az += __shfl_xor_sync(0xffffffffu, az, 1);
+            if (h == 0 && j < nl) {
+                if (a.acc) atomicAdd(a.acc + reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3])[j],
+                                     make_float4(ax, ay, az, 0.0f));
+                else a.part[v0 + j] = make_float4(ax, ay, az, 0.0f);
+            }
         }
     }
 }

@@ -49,13 +49,14 @@ const KernelTable *fast_kernels();
 // Tile-major HBM layout consumed by the persistent tile kernel.  Per tile of T tets:
 //   tet block  (T * 56 B, one bulk async copy): planes A[T] float4 (Q0..Q3), B[T] float4 (Q4..Q7),
 //              C[T] float4 (Q8, invRestVolume, slot01, slot23), D[T] uint2 (dest01, dest23)
-//   meta block (metaStride B, one bulk async copy): see ClusterPlan::tileMeta in mesh_prep.h
+//   meta block (variable size, one bulk async copy): see ClusterPlan::tileMeta in mesh_prep.h
 struct TileArgs {
     const float4 *x4;               // handle-local vertex records (x, y, z, invMass)
     const unsigned char *tets;      // [numTiles * T * 56]
-    const unsigned char *meta;      // [numTiles * metaStride]
+    const unsigned char *meta;      // variable-size blocks, block c at 16 * metaOff[c]
+    const uint32_t *metaOff;        // [numTiles + 1]
     int numTiles;
-    int metaStride, metaValOff, metaIdsOff, colStride, maxTileVertsPad;
+    int metaStride, metaValOff, colStride, maxTileVertsPad;  // metaStride = largest block
     float4 *part;                   // per-tile partial dx sums (deterministic flush)
     float4 *acc;                    // global accumulator (atomic flush), or NULL
     double *volAcc;                 // sum over tets of det F - 1, or NULL

@@ -108,14 +108,28 @@ int greedy_colors(int numVerts, int numTets, const int *tetIds, int *color) {
     return numColors;
 }
 
-static inline uint64_t spread21(uint64_t x) {  // 21 bits -> every third bit
-    x &= 0x1fffffull;
-    x = (x | x << 32) & 0x1f00000000ffffull;
-    x = (x | x << 16) & 0x1f0000ff0000ffull;
-    x = (x | x << 8) & 0x100f00f00f00f00full;
-    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
-    x = (x | x << 2) & 0x1249249249249249ull;
-    return x;
+// 3-D Hilbert index of a point on a 2^bits grid (Skilling, "Programming the Hilbert curve", 2004):
+// unlike a Morton curve it never jumps, so a run of consecutive tets is always a connected blob
+// and the vertex footprint of a tile stays close to its average.
+static inline uint64_t hilbert3(uint32_t x, uint32_t y, uint32_t z, int bits) {
+    uint32_t X[3] = {x, y, z};
+    const uint32_t M = 1u << (bits - 1);
+    for (uint32_t Q = M; Q > 1; Q >>= 1) {  // inverse undo
+        const uint32_t P = Q - 1;
+        for (int i = 0; i < 3; i++) {
+            if (X[i] & Q) X[0] ^= P;
+            else { uint32_t t = (X[0] ^ X[i]) & P; X[0] ^= t; X[i] ^= t; }
+        }
+    }
+    for (int i = 1; i < 3; i++) X[i] ^= X[i - 1];  // Gray encode
+    uint32_t t = 0;
+    for (uint32_t Q = M; Q > 1; Q >>= 1)
+        if (X[2] & Q) t ^= Q - 1;
+    for (int i = 0; i < 3; i++) X[i] ^= t;
+    uint64_t h = 0;  // interleave, X[0] most significant within each bit triple
+    for (int b = bits - 1; b >= 0; b--)
+        for (int i = 0; i < 3; i++) h = (h << 1) | ((X[i] >> b) & 1u);
+    return h;
 }
 
 std::vector<int> morton_order(int numVerts, int numTets, const float *verts, const int *tetIds) {
@@ -128,18 +142,19 @@ std::vector<int> morton_order(int numVerts, int numTets, const float *verts, con
     // one cubic cell size for all axes so the curve follows the shape of the domain
     double ext = 0.0;
     for (int c = 0; c < 3; c++) ext = std::max(ext, (double)hi[c] - (double)lo[c]);
-    const double scale = ext > 0.0 ? (double)((1 << 21) - 1) / ext : 0.0;
+    const int bits = 20;
+    const double scale = ext > 0.0 ? (double)((1 << bits) - 1) / ext : 0.0;
     std::vector<std::pair<uint64_t, int>> keys((size_t)numTets);
     for (int e = 0; e < numTets; e++) {
         const int *t = tetIds + 4 * (size_t)e;
-        uint64_t q[3];
+        uint32_t q[3];
         for (int c = 0; c < 3; c++) {
             double m = 0.25 * ((double)verts[3 * (size_t)t[0] + c] + (double)verts[3 * (size_t)t[1] + c] +
                                (double)verts[3 * (size_t)t[2] + c] + (double)verts[3 * (size_t)t[3] + c]);
             double g = (m - (double)lo[c]) * scale;
-            q[c] = (g == g && g > 0.0) ? (uint64_t)std::min(g, (double)((1 << 21) - 1)) : 0;
+            q[c] = (g == g && g > 0.0) ? (uint32_t)std::min(g, (double)((1 << bits) - 1)) : 0u;
         }
-        keys[e] = {spread21(q[0]) | spread21(q[1]) << 1 | spread21(q[2]) << 2, e};
+        keys[e] = {hilbert3(q[0], q[1], q[2], bits), e};
     }
     std::sort(keys.begin(), keys.end());  // ties broken by tet index
     std::vector<int> order((size_t)numTets);
@@ -281,18 +296,24 @@ bool build_cluster_plan(int numVerts, int numTets, const int *tetIds, const std:
     P.colStride = ((maxTileVal + 1 + 7) / 8) * 8;
     P.maxTileVertsPad = ((P.maxTileVerts + 15) / 16) * 16;
     P.metaValOff = 16 + 2 * P.colStride;
-    P.metaIdsOff = P.metaValOff + P.maxTileVertsPad;
-    P.metaStride = P.metaIdsOff + 4 * P.maxTileVertsPad;
-    P.tileMeta.assign((size_t)P.numClusters * P.metaStride, 0);
+    P.metaStride = P.metaValOff + 5 * P.maxTileVertsPad;  // largest block (shared-memory slot size)
+    P.metaOff.assign((size_t)P.numClusters + 1, 0);       // in units of 16 bytes
     for (int c = 0; c < P.numClusters; c++) {
-        unsigned char *m = P.tileMeta.data() + (size_t)c * P.metaStride;
+        const int nl = P.clVertStart[c + 1] - P.clVertStart[c];
+        const int nlPad = ((nl + 15) / 16) * 16;
+        P.metaOff[c + 1] = P.metaOff[c] + (uint32_t)((P.metaValOff + 5 * nlPad) / 16);
+    }
+    P.tileMeta.assign((size_t)P.metaOff[P.numClusters] * 16, 0);
+    for (int c = 0; c < P.numClusters; c++) {
+        unsigned char *m = P.tileMeta.data() + (size_t)P.metaOff[c] * 16;
         const int v0 = P.clVertStart[c], nl = P.clVertStart[c + 1] - v0;
-        int hdr[4] = {v0, nl, (int)colOffs[c].size() - 1, 0};
+        const int nlPad = ((nl + 15) / 16) * 16;
+        int hdr[4] = {v0, nl, (int)colOffs[c].size() - 1, P.metaValOff + nlPad /* byte offset of ids */};
         memcpy(m, hdr, 16);
         uint16_t *co = reinterpret_cast<uint16_t *>(m + 16);
         for (size_t i = 0; i < colOffs[c].size(); i++) co[i] = (uint16_t)(16u * colOffs[c][i]);
         memcpy(m + P.metaValOff, allVal.data() + v0, (size_t)nl);
-        memcpy(m + P.metaIdsOff, P.clVerts.data() + v0, 4 * (size_t)nl);
+        memcpy(m + P.metaValOff + nlPad, P.clVerts.data() + v0, 4 * (size_t)nl);
     }
 
     // vertex -> partial-sum slots, ascending tile order

@@ -33,7 +33,7 @@ int level_schedule(int numVerts, int numTets, const int *tetIds, int *level);
 // Returns the number of colours, or -1 if more than 256 would be needed.
 int greedy_colors(int numVerts, int numTets, const int *tetIds, int *color);
 
-// Tets sorted along a Morton curve of their centroids (stable for equal keys).
+// Tets sorted along a 3-D Hilbert curve of their centroids (ties by tet index).
 std::vector<int> morton_order(int numVerts, int numTets, const float *verts, const int *tetIds);
 
 // Tiling of a tet sequence into CTA tiles for the clustered Jacobi kernel.
@@ -51,13 +51,15 @@ struct ClusterPlan {
     std::vector<uint32_t> recordAux;    // [numClusters * T * 4]
     std::vector<int> clVertStart;       // [numClusters + 1]
     std::vector<int> clVerts;           // local vertex ids per tile, descending tile valence
-    // One fixed-stride metadata block per tile, fetched with a single bulk async copy:
-    //   [0,16)   int32 {first partial-sum slot, tile vertex count, max tile valence, 0}
+    // One metadata block per tile (variable size, 16-byte granular), fetched with a single bulk async copy:
+    //   [0,16)   int32 {first partial-sum slot, tile vertex count nl, max tile valence, byte offset of ids}
     //   [16, ..) uint16 colOff[colStride]   byte offset (16 * entry) of jagged diagonal i
-    //   then     uint8  val[maxTileVertsPad] tile valence of tile vertex j (descending)
-    //   then     int32  ids[maxTileVertsPad] handle-local vertex id of tile vertex j
+    //   then     uint8  val[nlPad]          tile valence of tile vertex j (descending), nlPad = roundup16(nl)
+    //   then     int32  ids[nlPad]          handle-local vertex id of tile vertex j
     std::vector<unsigned char> tileMeta;
-    int metaStride = 0, metaValOff = 0, metaIdsOff = 0;
+    std::vector<uint32_t> metaOff;      // [numClusters + 1] block offsets in units of 16 bytes
+    int metaStride = 0;                 // largest block, bytes
+    int metaValOff = 0;
     int colStride = 0;
     int maxTileVerts = 0, maxTileVertsPad = 0;
     std::vector<int> vpStart, vpSlot;   // local vertex -> indices into the partial-sum array

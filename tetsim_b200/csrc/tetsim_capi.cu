@@ -134,6 +134,7 @@ struct tetsim {
     ClusterPlan plan;
     DevBuf<int> vpStart, vpSlot;
     DevBuf<unsigned char> tileTets, tileMeta;
+    DevBuf<uint32_t> metaOff;
     DevBuf<float4> part, acc, bsum;
     DevBuf<float> invVal;
     bool clustered = false;
@@ -169,7 +170,7 @@ struct tetsim {
                          invMass.bytes() + ids.bytes() + cStart.bytes() + cEnt.bytes() + A.bytes() + B.bytes() +
                          C.bytes() + I.bytes() + order.bytes() + levelStart.bytes() + bodies.bytes() +
                          volTerm.bytes() + dx.bytes() + vpStart.bytes() + vpSlot.bytes() + tileTets.bytes() +
-                         tileMeta.bytes() + part.bytes() + acc.bytes() +
+                         tileMeta.bytes() + metaOff.bytes() + part.bytes() + acc.bytes() +
                          bsum.bytes() + invVal.bytes() + rest.bytes() + quat.bytes() + tStart.bytes() + tEnt.bytes() +
                          stage3.bytes() + visV.bytes() + visTri.bytes() + vtStart.bytes() + vtEnt.bytes() +
                          visPos.bytes() + visNrm.bytes());
@@ -353,6 +354,7 @@ int build_jacobi_cluster(tetsim *h, const std::vector<float> &verts, const std::
         aux.release();
     }
     CK(h->tileMeta.upload(P.tileMeta, s));
+    CK(h->metaOff.upload(P.metaOff, s));
     CK(h->vpStart.upload(P.vpStart, s));
     CK(h->vpSlot.upload(P.vpSlot, s));
     CK(h->invVal.upload(P.invValence, s));
@@ -389,7 +391,7 @@ TileArgs tile_args(const tetsim *h) {
     const ClusterPlan &P = h->plan;
     TileArgs a{};
     a.x4 = h->x4.p; a.tets = h->tileTets.p; a.meta = h->tileMeta.p; a.numTiles = P.numClusters;
-    a.metaStride = P.metaStride; a.metaValOff = P.metaValOff; a.metaIdsOff = P.metaIdsOff;
+    a.metaOff = h->metaOff.p; a.metaStride = P.metaStride; a.metaValOff = P.metaValOff;
     a.colStride = P.colStride; a.maxTileVertsPad = P.maxTileVertsPad;
     a.part = h->part.p; a.acc = nullptr; a.volAcc = nullptr; a.sp = h->sp.p;
     return a;
@@ -736,7 +738,7 @@ void tetsim_destroy(tetsim_t *h) {
     DevBuf<float> *f1[] = {&h->Q9, &h->irv, &h->invMass, &h->invVal, &h->stage3, &h->visPos, &h->visNrm};
     for (auto *b : f1) b->release();
     h->ids.release(); h->I.release(); h->bodies.release(); h->volTerm.release(); h->volOut.release();
-    h->tileTets.release(); h->tileMeta.release(); h->sp.release(); h->grabP.release(); h->grabScratch.release();
+    h->tileTets.release(); h->tileMeta.release(); h->metaOff.release(); h->sp.release(); h->grabP.release(); h->grabScratch.release();
     if (h->ownStream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -924,6 +926,8 @@ int tetsim_get_info(tetsim_t *h, TetSimInfo *info) {
     info->deviceBytes = h->deviceBytes();
     info->sumLocalVerts = (int64_t)h->plan.clVerts.size();
     info->kernelLaunches = h->totalLaunches;
+    info->tileMetaBytes = (int64_t)h->plan.tileMeta.size();
+    info->maxTileVerts = h->clustered ? h->plan.maxTileVerts : 0;
     return TETSIM_OK;
 }
 

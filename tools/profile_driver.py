@@ -31,6 +31,7 @@ for _ in range(a.steps):
 b.synchronize()
 ms, nbytes = b.time_kernel(a.reps)
 info = b.info()
-print("tile kernel %.4f ms/launch, %.1f GB/s algorithmic, %.3e tets/s; tiles %d, sum tile verts %d (%.2f per tet), maxValence %d"
-      % (ms, nbytes / ms / 1e6, info["localTets"] / ms * 1e3, info["numClusters"], info["sumLocalVerts"],
-         info["sumLocalVerts"] / max(info["localTets"], 1), info["maxValence"]))
+print("tile kernel %.4f ms/launch, %.1f GB/s algorithmic, %.3e tets/s; T=%d tiles %d, tile verts %.2f per tet (max %d per tile), "
+      "meta %.1f B/tet" % (ms, nbytes / ms / 1e6, info["localTets"] / ms * 1e3, info["clusterSize"], info["numClusters"],
+                          info["sumLocalVerts"] / max(info["localTets"], 1), info["maxTileVerts"],
+                          info["tileMetaBytes"] / max(info["localTets"], 1)))
