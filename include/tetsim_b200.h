@@ -89,7 +89,8 @@ typedef struct TetSimOptions {
                                   tet 0 dropped from its vertex's average); 0 averages every corner  */
     int32_t reorder;           /* Jacobi: 1 (default) = sort tets along a Morton curve of their
                                   centroids before clustering; 0 = keep the caller's order           */
-    int32_t clusterSize;       /* Jacobi: tets per CTA tile: 128, 256 (default) or 512                */
+    int32_t clusterSize;       /* Jacobi: tets per tile: 32, 64 (one warp per tile) or 128, 256
+                                  (default), 512 (one CTA per tile)                                    */
     int32_t trackVolError;     /* -1 auto (on for GS, off for Jacobi), 0 off, 1 on                    */
     int32_t device;            /* CUDA device ordinal, -1 = the calling thread's current device       */
     int32_t rank;              /* multi-GPU Jacobi: this process's rank, 0 when worldSize == 1        */

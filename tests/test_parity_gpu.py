@@ -283,7 +283,8 @@ def test_jacobi_gather_bitexact(dragon, iters):
 
 
 @pytest.mark.parametrize("cluster_size,reorder,deterministic", [(256, True, True), (128, False, True), (512, True, True),
-                                                               (256, True, False)])
+                                                               (256, True, False), (32, True, True), (64, True, True),
+                                                               (64, False, False)])
 def test_jacobi_clustered_within_tolerance(dragon, cluster_size, reorder, deterministic):
     ref = oracle.SoftBodyOracle(dragon["tet_verts"], dragon["tet_ids"])
     sb = new_body(dragon, solver="jacobi", arithmetic="fast", cluster_size=cluster_size, reorder=reorder,

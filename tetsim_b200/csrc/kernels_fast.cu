@@ -116,7 +116,8 @@ __global__ void __launch_bounds__(T, MINB) k_jacobi_tiles(TileArgs a) {
         const int nl = reinterpret_cast<const int *>(m)[1];
         const int *ids = reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3]);
         float4 *sx = reinterpret_cast<float4 *>(smem + L.sx(buf));
-        for (int j = tid; j < nl; j += T) cp_async16(sx + j, a.x4 + ids[j]);
+        if (!(a.debugSkip & 4))
+            for (int j = tid; j < nl; j += T) cp_async16(sx + j, a.x4 + ids[j]);
         cp_async_commit();
     };
 
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(T, MINB) k_jacobi_tiles(TileArgs a) {
         V3 p[4] = {{q0.x, q0.y, q0.z}, {q1.x, q1.y, q1.z}, {q2.x, q2.y, q2.z}, {q3.x, q3.y, q3.z}};
         const float w[4] = {q0.w, q1.w, q2.w, q3.w};
         const float Q[9] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w, C.x};
-        const float vm1 = nh_solve_fast(p, w, Q, C.y, alphaDev, alphaVol, gammaVol);
+        const float vm1 = (a.debugSkip & 2) ? 0.0f : nh_solve_fast(p, w, Q, C.y, alphaDev, alphaVol, gammaVol);
         *reinterpret_cast<float4 *>(sdx + (D.x & 0xffffu)) = make_float4(p[0].x - q0.x, p[0].y - q0.y, p[0].z - q0.z, 0.f);
         *reinterpret_cast<float4 *>(sdx + (D.x >> 16)) = make_float4(p[1].x - q1.x, p[1].y - q1.y, p[1].z - q1.z, 0.f);
         *reinterpret_cast<float4 *>(sdx + (D.y & 0xffffu)) = make_float4(p[2].x - q2.x, p[2].y - q2.y, p[2].z - q2.z, 0.f);
@@ -189,6 +190,7 @@ __global__ void __launch_bounds__(T, MINB) k_jacobi_tiles(TileArgs a) {
         const int v0 = reinterpret_cast<const int *>(m)[0];
         const int nl = reinterpret_cast<const int *>(m)[1];
         const uint16_t *scol = reinterpret_cast<const uint16_t *>(m + 16);
+        if (!(a.debugSkip & 1))
         for (int jj = tid; jj < 2 * ((nl + 15) & ~15); jj += T) {  // whole warps stay together for the shuffle
             const int j = jj >> 1, h = jj & 1;
             const int val = j < nl ? m[a.metaValOff + j] : 0;
@@ -211,8 +213,141 @@ __global__ void __launch_bounds__(T, MINB) k_jacobi_tiles(TileArgs a) {
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// Warp-tile variant: the same pipeline, but a tile is owned by ONE WARP (T = 32 * TPL tets, TPL tets
+// per lane) and every warp is its own persistent worker with private staging buffers and
+// mbarriers.  There is no block-level barrier at all -- only __syncwarp -- so warps drift apart and
+// the SM always has warps in the math phase while others wait on loads or sum corners (the CTA-tile
+// kernel above loses ~35 % of its stall samples to __syncthreads).  TPL = 2 gives each lane two
+// independent dependency chains.
+// -------------------------------------------------------------------------------------------------
+template <int TPL>
+__global__ void __launch_bounds__(TPL == 1 ? 832 : 448, 1) k_jacobi_warptiles(TileArgs a) {
+    constexpr int T = 32 * TPL;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const TileSmem<T> L(a.metaStride, a.maxTileVertsPad);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    unsigned char *const ws = smem + (size_t)wid * ((L.total + 127) & ~127);
+    uint64_t *tetFull = reinterpret_cast<uint64_t *>(ws + L.bars);  // [2]
+    uint64_t *metaFull = tetFull + 2;                               // [3]
+    unsigned char *const sdx = ws + L.sdx;
+    const int stride = gridDim.x * wpb;
+    const int first = blockIdx.x * wpb + wid;
+    if (first >= a.numTiles) return;  // whole warp leaves; nothing below synchronises across warps
+
+    if (lane == 0) {
+        mbar_init(tetFull + 0, 1); mbar_init(tetFull + 1, 1);
+        mbar_init(metaFull + 0, 1); mbar_init(metaFull + 1, 1); mbar_init(metaFull + 2, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    const SubstepParams *sp = a.sp;
+    const float alphaDev = sp->alphaDev, alphaVol = sp->alphaVol, gammaVol = sp->gammaVol;
+
+    auto issue_meta = [&](uint32_t o, uint32_t end, int slot) {
+        const uint32_t bytes = (end - o) * 16u;
+        mbar_expect_tx(metaFull + slot, bytes);
+        bulk_g2s(ws + L.meta(slot), a.meta + (size_t)o * 16, bytes, metaFull + slot);
+    };
+    auto issue_tets = [&](int tile, int buf) {
+        mbar_expect_tx(tetFull + buf, (uint32_t)TileSmem<T>::TET_BYTES);
+        bulk_g2s(ws + L.tet(buf), a.tets + (size_t)tile * TileSmem<T>::TET_BYTES, (uint32_t)TileSmem<T>::TET_BYTES,
+                 tetFull + buf);
+    };
+    auto issue_gather = [&](int slot, int buf) {
+        const unsigned char *m = ws + L.meta(slot);
+        const int nl = reinterpret_cast<const int *>(m)[1];
+        const int *ids = reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3]);
+        float4 *sx = reinterpret_cast<float4 *>(ws + L.sx(buf));
+        for (int j = lane; j < nl; j += 32) cp_async16(sx + j, a.x4 + ids[j]);
+        cp_async_commit();
+    };
+
+    uint32_t nOff = 0, nEnd = 0;
+    if (lane == 0) {
+        issue_meta(a.metaOff[first], a.metaOff[first + 1], 0);
+        if (first + stride < a.numTiles) issue_meta(a.metaOff[first + stride], a.metaOff[first + stride + 1], 1);
+        issue_tets(first, 0);
+        if (first + 2 * stride < a.numTiles) { nOff = a.metaOff[first + 2 * stride]; nEnd = a.metaOff[first + 2 * stride + 1]; }
+    }
+    mbar_wait(metaFull + 0, 0);
+    issue_gather(0, 0);
+
+    int k = 0;
+    for (int c = first; c < a.numTiles; c += stride, k++) {
+        const int cur = k & 1, mcur = k % 3;
+        cp_async_wait_all();
+        mbar_wait(tetFull + cur, (k >> 1) & 1);
+        __syncwarp();  // every lane's gathers landed; previous tile's corner sums are done
+
+        if (c + stride < a.numTiles) {
+            const int mnext = (k + 1) % 3;
+            mbar_wait(metaFull + mnext, ((k + 1) / 3) & 1);
+            issue_gather(mnext, cur ^ 1);
+            if (lane == 0) issue_tets(c + stride, cur ^ 1);
+        }
+        if (lane == 0 && c + 2 * stride < a.numTiles) {
+            issue_meta(nOff, nEnd, (k + 2) % 3);
+            if (c + 3 * stride < a.numTiles) { nOff = a.metaOff[c + 3 * stride]; nEnd = a.metaOff[c + 3 * stride + 1]; }
+        }
+
+        const unsigned char *tb = ws + L.tet(cur);
+        const unsigned char *sxb = ws + L.sx(cur);
+        float vsum = 0.0f;
+#pragma unroll
+        for (int u = 0; u < TPL; u++) {
+            const int t = lane + 32 * u;
+            const float4 A = reinterpret_cast<const float4 *>(tb)[t];
+            const float4 B = reinterpret_cast<const float4 *>(tb + T * 16)[t];
+            const float4 C = reinterpret_cast<const float4 *>(tb + T * 32)[t];
+            const uint2 D = reinterpret_cast<const uint2 *>(tb + T * 48)[t];
+            const unsigned s01 = __float_as_uint(C.z), s23 = __float_as_uint(C.w);
+            const float4 q0 = *reinterpret_cast<const float4 *>(sxb + (s01 & 0xffffu));
+            const float4 q1 = *reinterpret_cast<const float4 *>(sxb + (s01 >> 16));
+            const float4 q2 = *reinterpret_cast<const float4 *>(sxb + (s23 & 0xffffu));
+            const float4 q3 = *reinterpret_cast<const float4 *>(sxb + (s23 >> 16));
+            V3 p[4] = {{q0.x, q0.y, q0.z}, {q1.x, q1.y, q1.z}, {q2.x, q2.y, q2.z}, {q3.x, q3.y, q3.z}};
+            const float w[4] = {q0.w, q1.w, q2.w, q3.w};
+            const float Q[9] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w, C.x};
+            const float vm1 = nh_solve_fast(p, w, Q, C.y, alphaDev, alphaVol, gammaVol);
+            *reinterpret_cast<float4 *>(sdx + (D.x & 0xffffu)) = make_float4(p[0].x - q0.x, p[0].y - q0.y, p[0].z - q0.z, 0.f);
+            *reinterpret_cast<float4 *>(sdx + (D.x >> 16)) = make_float4(p[1].x - q1.x, p[1].y - q1.y, p[1].z - q1.z, 0.f);
+            *reinterpret_cast<float4 *>(sdx + (D.y & 0xffffu)) = make_float4(p[2].x - q2.x, p[2].y - q2.y, p[2].z - q2.z, 0.f);
+            *reinterpret_cast<float4 *>(sdx + (D.y >> 16)) = make_float4(p[3].x - q3.x, p[3].y - q3.y, p[3].z - q3.z, 0.f);
+            vsum += (C.y != 0.0f) ? vm1 : 0.0f;
+        }
+        if (a.volAcc) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
+            if (lane == 0) atomicAdd(a.volAcc, (double)vsum);
+        }
+        __syncwarp();
+
+        const unsigned char *m = ws + L.meta(mcur);
+        const int v0 = reinterpret_cast<const int *>(m)[0];
+        const int nl = reinterpret_cast<const int *>(m)[1];
+        const uint16_t *scol = reinterpret_cast<const uint16_t *>(m + 16);
+        for (int j = lane; j < nl; j += 32) {
+            const int val = m[a.metaValOff + j];
+            const unsigned char *base = sdx + j * 16;
+            float ax = 0.0f, ay = 0.0f, az = 0.0f;
+#pragma unroll 4
+            for (int i = 0; i < val; i++) {
+                const float4 d = *reinterpret_cast<const float4 *>(base + scol[i]);
+                ax += d.x; ay += d.y; az += d.z;
+            }
+            if (a.acc) atomicAdd(a.acc + reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3])[j],
+                                 make_float4(ax, ay, az, 0.0f));
+            else a.part[v0 + j] = make_float4(ax, ay, az, 0.0f);
+        }
+    }
+}
+
 size_t jacobi_tiles_smem(int clusterSize, const TileArgs &a) {
     switch (clusterSize) {
+        case 32: return (size_t)((TileSmem<32>(a.metaStride, a.maxTileVertsPad).total + 127) & ~127);   // per warp
+        case 64: return (size_t)((TileSmem<64>(a.metaStride, a.maxTileVertsPad).total + 127) & ~127);   // per warp
         case 128: return (size_t)TileSmem<128>(a.metaStride, a.maxTileVertsPad).total;
         case 256: return (size_t)TileSmem<256>(a.metaStride, a.maxTileVertsPad).total;
         default: return (size_t)TileSmem<512>(a.metaStride, a.maxTileVertsPad).total;
@@ -238,9 +373,38 @@ static void launch_tiles_T(cudaStream_t s, const TileArgs &a) {
     k_jacobi_tiles<T, MINB><<<grid, T, smem, s>>>(a);
 }
 
+// Warp tiles: one CTA per SM holding as many warps as shared memory and registers allow.
+template <int TPL>
+static void launch_warptiles(cudaStream_t s, const TileArgs &a) {
+    const size_t perWarp = (size_t)((TileSmem<32 * TPL>(a.metaStride, a.maxTileVertsPad).total + 127) & ~127);
+    static size_t configured = 0;
+    static int warps = 0, numSms = 0;
+    if (perWarp != configured) {
+        int dev = 0, maxSmem = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&numSms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, k_jacobi_warptiles<TPL>);
+        int byRegs = 65536 / (32 * (fa.numRegs > 0 ? fa.numRegs : 64));
+        warps = (int)((size_t)maxSmem / perWarp);
+        if (warps > byRegs) warps = byRegs;
+        if (warps > (TPL == 1 ? 832 : 448) / 32) warps = (TPL == 1 ? 832 : 448) / 32;
+        if (const char *w = getenv("TETSIM_WARPS_PER_SM")) { int v = atoi(w); if (v >= 1 && v < warps) warps = v; }
+        if (warps < 1) warps = 1;
+        cudaFuncSetAttribute(k_jacobi_warptiles<TPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(perWarp * warps));
+        configured = perWarp;
+    }
+    int grid = numSms;
+    if ((long long)grid * warps > a.numTiles) grid = (a.numTiles + warps - 1) / warps;
+    k_jacobi_warptiles<TPL><<<grid, 32 * warps, perWarp * warps, s>>>(a);
+}
+
 void launch_jacobi_tiles(cudaStream_t s, int clusterSize, const TileArgs &a) {
     if (a.numTiles <= 0) return;
     switch (clusterSize) {
+        case 32: launch_warptiles<1>(s, a); break;
+        case 64: launch_warptiles<2>(s, a); break;
         case 128: launch_tiles_T<128, 6>(s, a); break;
         case 256: launch_tiles_T<256, 4>(s, a); break;
         case 512: launch_tiles_T<512, 2>(s, a); break;
@@ -277,7 +441,9 @@ void launch_build_tiles(cudaStream_t s, int clusterSize, int numRecords, const i
                         const float *irv, const uint4 *aux, unsigned char *tets) {
     if (numRecords <= 0) return;
     const int g = cdiv(numRecords, 256);
-    if (clusterSize == 128) k_build_tiles<128><<<g, 256, 0, s>>>(numRecords, order, Q9, irv, aux, tets);
+    if (clusterSize == 32) k_build_tiles<32><<<g, 256, 0, s>>>(numRecords, order, Q9, irv, aux, tets);
+    else if (clusterSize == 64) k_build_tiles<64><<<g, 256, 0, s>>>(numRecords, order, Q9, irv, aux, tets);
+    else if (clusterSize == 128) k_build_tiles<128><<<g, 256, 0, s>>>(numRecords, order, Q9, irv, aux, tets);
     else if (clusterSize == 256) k_build_tiles<256><<<g, 256, 0, s>>>(numRecords, order, Q9, irv, aux, tets);
     else k_build_tiles<512><<<g, 256, 0, s>>>(numRecords, order, Q9, irv, aux, tets);
 }

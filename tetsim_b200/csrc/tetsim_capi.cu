@@ -593,8 +593,8 @@ int tetsim_create(const float *verts, int32_t numVerts, const int32_t *tetIds, i
     if (opt.arithmetic != TETSIM_ARITH_FAST_F32 && opt.arithmetic != TETSIM_ARITH_BITEXACT)
         return fail(TETSIM_E_INVALID, "unknown arithmetic");
     if (opt.iters < 1) return fail(TETSIM_E_INVALID, "iters must be >= 1");
-    if (opt.clusterSize != 128 && opt.clusterSize != 256 && opt.clusterSize != 512)
-        return fail(TETSIM_E_INVALID, "clusterSize must be 128, 256 or 512");
+    if (opt.clusterSize != 32 && opt.clusterSize != 64 && opt.clusterSize != 128 && opt.clusterSize != 256 && opt.clusterSize != 512)
+        return fail(TETSIM_E_INVALID, "clusterSize must be 32, 64 (warp tiles) or 128, 256, 512 (CTA tiles)");
     if (opt.worldSize < 1 || opt.rank < 0 || opt.rank >= opt.worldSize) return fail(TETSIM_E_INVALID, "bad rank/worldSize");
     const bool clustered = opt.solver == TETSIM_NH_JACOBI && opt.arithmetic == TETSIM_ARITH_FAST_F32;
     if (opt.worldSize > 1 && !clustered)
@@ -938,6 +938,7 @@ int tetsim_time_kernel(tetsim_t *h, int32_t reps, double *msPerLaunch, int64_t *
     cudaStream_t s = h->stream;
     const ClusterPlan &P = h->plan;
     TileArgs ca = tile_args(h);
+    if (const char *dbg = getenv("TETSIM_TILE_DEBUG")) ca.debugSkip = atoi(dbg);
     DevBuf<float4> scratch;  // atomic-flush handles have no partial-sum array: give the kernel one
     if (!ca.part) { CK(scratch.alloc(P.clVerts.size())); ca.part = scratch.p; }
     cudaEvent_t e0, e1;
