@@ -49,7 +49,7 @@ def test_sass_is_sm100a_without_tensor_or_cas_loops():
     contraction on this path) and no shared-memory CAS spin loops in the clustered Jacobi kernel."""
     out = subprocess.run(["cuobjdump", "-lelf", _capi.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
-    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN4tsim14k_jacobi_tilesILi256ELi4EEEvNS_8TileArgsE",
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN4tsim14k_jacobi_tilesILi256ELi2ELi4EEEvNS_8TileArgsE",
                            _capi.LIB_PATH], capture_output=True, text=True).stdout
     # TMA bulk copies on mbarriers, cp.async gathers, 128-bit shared-memory traffic
     assert "UBLKCP" in sass and "SYNCS" in sass and "LDGSTS.E.BYPASS.128" in sass

@@ -60,43 +60,47 @@ __device__ __forceinline__ void cp_async16(void *dst, const void *src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-template <int T>
+template <int T, int S>
 struct TileSmem {
     static constexpr int TET_BYTES = T * 56;
-    // byte offsets inside dynamic shared memory (computed, never indexed: keeps them in registers)
+    // byte offsets inside the worker's shared-memory region (computed, never indexed: stays in registers)
     int sxBytes, metaStride, sdx, sx0, meta0, bars, total;
     __host__ __device__ TileSmem(int metaStride_, int maxTileVertsPad) {
         sxBytes = maxTileVertsPad * 16;
         metaStride = metaStride_;
-        sdx = 2 * TET_BYTES;
+        sdx = S * TET_BYTES;
         sx0 = sdx + (4 * T + 1) * 16;  // + one spare entry for padding records
-        meta0 = sx0 + 2 * sxBytes;
-        bars = meta0 + 3 * metaStride;
-        total = bars + 5 * 8 + 8;
+        meta0 = sx0 + S * sxBytes;
+        bars = meta0 + (S + 1) * metaStride;
+        total = (bars + (2 * S + 1) * 8 + 127) & ~127;
     }
     __host__ __device__ int tet(int buf) const { return buf * TET_BYTES; }
     __host__ __device__ int sx(int buf) const { return sx0 + buf * sxBytes; }
     __host__ __device__ int meta(int slot) const { return meta0 + slot * metaStride; }
 };
 
-template <int T, int MINB>
-__global__ void __launch_bounds__(T, MINB) k_jacobi_tiles(TileArgs a) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    const TileSmem<T> L(a.metaStride, a.maxTileVertsPad);
-    uint64_t *tetFull = reinterpret_cast<uint64_t *>(smem + L.bars);  // [2]
-    uint64_t *metaFull = tetFull + 2;                                 // [3]
-    unsigned char *const sdx = smem + L.sdx;
-    const int tid = threadIdx.x;
-    const int stride = gridDim.x;
-    const int first = blockIdx.x;
-    if (first >= a.numTiles) return;
+template <int N>
+__device__ __forceinline__ void cp_async_wait_pending() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// One persistent worker (a CTA when WARP_SCOPE = false, a single warp when true) walking tiles
+// first, first + stride, ...  NT = threads of the worker, TPT = tets per thread, T = NT * TPT.
+// S-stage ring: at tile k the tet block and vertex gather of tile k+S-1 and the meta block of tile
+// k+S are put in flight, so S-1 tiles of HBM/L2 latency are covered by math.
+template <int NT, int TPT, int S, bool WARP_SCOPE>
+__device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws, const int tid, const int first,
+                                            const int stride) {
+    constexpr int T = NT * TPT;
+    const TileSmem<T, S> L(a.metaStride, a.maxTileVertsPad);
+    uint64_t *tetFull = reinterpret_cast<uint64_t *>(ws + L.bars);  // [S]
+    uint64_t *metaFull = tetFull + S;                               // [S + 1]
+    unsigned char *const sdx = ws + L.sdx;
+    auto sync = [&]() { if (WARP_SCOPE) __syncwarp(); else __syncthreads(); };
 
     if (tid == 0) {
-        mbar_init(tetFull + 0, 1); mbar_init(tetFull + 1, 1);
-        mbar_init(metaFull + 0, 1); mbar_init(metaFull + 1, 1); mbar_init(metaFull + 2, 1);
+        for (int i = 0; i < 2 * S + 1; i++) mbar_init(tetFull + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
+    sync();
 
     const SubstepParams *sp = a.sp;
     const float alphaDev = sp->alphaDev, alphaVol = sp->alphaVol, gammaVol = sp->gammaVol;
@@ -104,200 +108,72 @@ __global__ void __launch_bounds__(T, MINB) k_jacobi_tiles(TileArgs a) {
     auto issue_meta = [&](uint32_t o, uint32_t end, int slot) {  // one thread; block = [16*o, 16*end)
         const uint32_t bytes = (end - o) * 16u;
         mbar_expect_tx(metaFull + slot, bytes);
-        bulk_g2s(smem + L.meta(slot), a.meta + (size_t)o * 16, bytes, metaFull + slot);
-    };
-    auto issue_tets = [&](int tile, int buf) {  // one thread
-        mbar_expect_tx(tetFull + buf, (uint32_t)TileSmem<T>::TET_BYTES);
-        bulk_g2s(smem + L.tet(buf), a.tets + (size_t)tile * TileSmem<T>::TET_BYTES, (uint32_t)TileSmem<T>::TET_BYTES,
-                 tetFull + buf);
-    };
-    auto issue_gather = [&](int slot, int buf) {  // all threads
-        const unsigned char *m = smem + L.meta(slot);
-        const int nl = reinterpret_cast<const int *>(m)[1];
-        const int *ids = reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3]);
-        float4 *sx = reinterpret_cast<float4 *>(smem + L.sx(buf));
-        if (!(a.debugSkip & 4))
-            for (int j = tid; j < nl; j += T) cp_async16(sx + j, a.x4 + ids[j]);
-        cp_async_commit();
-    };
-
-    // prologue: meta of the first two tiles, then the first tile's vertex gather and tet block.
-    // Thread 0 keeps the block range of the tile whose meta it issues NEXT iteration in registers
-    // (loaded one iteration early, so the dependent global load never stalls the issue).
-    uint32_t nOff = 0, nEnd = 0;
-    if (tid == 0) {
-        issue_meta(a.metaOff[first], a.metaOff[first + 1], 0);
-        if (first + stride < a.numTiles) issue_meta(a.metaOff[first + stride], a.metaOff[first + stride + 1], 1);
-        issue_tets(first, 0);
-        if (first + 2 * stride < a.numTiles) { nOff = a.metaOff[first + 2 * stride]; nEnd = a.metaOff[first + 2 * stride + 1]; }
-    }
-    mbar_wait(metaFull + 0, 0);
-    issue_gather(0, 0);
-
-    int k = 0;
-    for (int c = first; c < a.numTiles; c += stride, k++) {
-        const int cur = k & 1, mcur = k % 3;
-        cp_async_wait_all();
-        mbar_wait(tetFull + cur, (k >> 1) & 1);
-        __syncthreads();  // gathers of all threads landed; previous tile's vertex phase finished
-
-        // ---- prefetch tile k+1 (data) and tile k+2 (meta) ----
-        if (c + stride < a.numTiles) {
-            const int mnext = (k + 1) % 3;
-            mbar_wait(metaFull + mnext, ((k + 1) / 3) & 1);
-            issue_gather(mnext, cur ^ 1);
-            if (tid == 0) issue_tets(c + stride, cur ^ 1);
-        }
-        if (tid == 0 && c + 2 * stride < a.numTiles) {
-            issue_meta(nOff, nEnd, (k + 2) % 3);
-            if (c + 3 * stride < a.numTiles) { nOff = a.metaOff[c + 3 * stride]; nEnd = a.metaOff[c + 3 * stride + 1]; }
-        }
-
-        // ---- per-tet solve ----
-        const unsigned char *tb = smem + L.tet(cur);
-        const float4 A = reinterpret_cast<const float4 *>(tb)[tid];
-        const float4 B = reinterpret_cast<const float4 *>(tb + T * 16)[tid];
-        const float4 C = reinterpret_cast<const float4 *>(tb + T * 32)[tid];
-        const uint2 D = reinterpret_cast<const uint2 *>(tb + T * 48)[tid];
-        const unsigned char *sxb = smem + L.sx(cur);
-        const unsigned s01 = __float_as_uint(C.z), s23 = __float_as_uint(C.w);
-        const float4 q0 = *reinterpret_cast<const float4 *>(sxb + (s01 & 0xffffu));
-        const float4 q1 = *reinterpret_cast<const float4 *>(sxb + (s01 >> 16));
-        const float4 q2 = *reinterpret_cast<const float4 *>(sxb + (s23 & 0xffffu));
-        const float4 q3 = *reinterpret_cast<const float4 *>(sxb + (s23 >> 16));
-        V3 p[4] = {{q0.x, q0.y, q0.z}, {q1.x, q1.y, q1.z}, {q2.x, q2.y, q2.z}, {q3.x, q3.y, q3.z}};
-        const float w[4] = {q0.w, q1.w, q2.w, q3.w};
-        const float Q[9] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w, C.x};
-        const float vm1 = (a.debugSkip & 2) ? 0.0f : nh_solve_fast(p, w, Q, C.y, alphaDev, alphaVol, gammaVol);
-        *reinterpret_cast<float4 *>(sdx + (D.x & 0xffffu)) = make_float4(p[0].x - q0.x, p[0].y - q0.y, p[0].z - q0.z, 0.f);
-        *reinterpret_cast<float4 *>(sdx + (D.x >> 16)) = make_float4(p[1].x - q1.x, p[1].y - q1.y, p[1].z - q1.z, 0.f);
-        *reinterpret_cast<float4 *>(sdx + (D.y & 0xffffu)) = make_float4(p[2].x - q2.x, p[2].y - q2.y, p[2].z - q2.z, 0.f);
-        *reinterpret_cast<float4 *>(sdx + (D.y >> 16)) = make_float4(p[3].x - q3.x, p[3].y - q3.y, p[3].z - q3.z, 0.f);
-        if (a.volAcc) {  // volError (src/Softbody.js:163): warp-reduce, one double atomic per warp
-            float s = (C.y != 0.0f) ? vm1 : 0.0f;  // padding records carry invRestVolume = 0
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if ((tid & 31) == 0) atomicAdd(a.volAcc, (double)s);
-        }
-        __syncthreads();
-
-        // ---- per-tile-vertex sum of corner dx, fixed order ----
-        // Two lanes per tile vertex: lane h of the pair sums diagonals h, h+2, ... and the halves are
-        // combined with one shuffle (even half + odd half: a fixed order, so still reproducible).
-        // Halving the trip count and doubling the active lanes is what keeps this phase from
-        // holding the CTA's other warps at the next barrier.
-        const unsigned char *m = smem + L.meta(mcur);
-        const int v0 = reinterpret_cast<const int *>(m)[0];
-        const int nl = reinterpret_cast<const int *>(m)[1];
-        const uint16_t *scol = reinterpret_cast<const uint16_t *>(m + 16);
-        if (!(a.debugSkip & 1))
-        for (int jj = tid; jj < 2 * ((nl + 15) & ~15); jj += T) {  // whole warps stay together for the shuffle
-            const int j = jj >> 1, h = jj & 1;
-            const int val = j < nl ? m[a.metaValOff + j] : 0;
-            const unsigned char *base = sdx + j * 16;
-            float ax = 0.0f, ay = 0.0f, az = 0.0f;
-#pragma unroll 4
-            for (int i = h; i < val; i += 2) {
-                const float4 d = *reinterpret_cast<const float4 *>(base + scol[i]);
-                ax += d.x; ay += d.y; az += d.z;
-            }
-            ax += __shfl_xor_sync(0xffffffffu, ax, 1);
-            ay += __shfl_xor_sync(0xffffffffu, ay, 1);
-            az += __shfl_xor_sync(0xffffffffu, az, 1);
-            if (h == 0 && j < nl) {
-                if (a.acc) atomicAdd(a.acc + reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3])[j],
-                                     make_float4(ax, ay, az, 0.0f));
-                else a.part[v0 + j] = make_float4(ax, ay, az, 0.0f);
-            }
-        }
-    }
-}
-
-// -------------------------------------------------------------------------------------------------
-// Warp-tile variant: the same pipeline, but a tile is owned by ONE WARP (T = 32 * TPL tets, TPL tets
-// per lane) and every warp is its own persistent worker with private staging buffers and
-// mbarriers.  There is no block-level barrier at all -- only __syncwarp -- so warps drift apart and
-// the SM always has warps in the math phase while others wait on loads or sum corners (the CTA-tile
-// kernel above loses ~35 % of its stall samples to __syncthreads).  TPL = 2 gives each lane two
-// independent dependency chains.
-// -------------------------------------------------------------------------------------------------
-template <int TPL>
-__global__ void __launch_bounds__(TPL == 1 ? 832 : 448, 1) k_jacobi_warptiles(TileArgs a) {
-    constexpr int T = 32 * TPL;
-    extern __shared__ __align__(128) unsigned char smem[];
-    const TileSmem<T> L(a.metaStride, a.maxTileVertsPad);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    unsigned char *const ws = smem + (size_t)wid * ((L.total + 127) & ~127);
-    uint64_t *tetFull = reinterpret_cast<uint64_t *>(ws + L.bars);  // [2]
-    uint64_t *metaFull = tetFull + 2;                               // [3]
-    unsigned char *const sdx = ws + L.sdx;
-    const int stride = gridDim.x * wpb;
-    const int first = blockIdx.x * wpb + wid;
-    if (first >= a.numTiles) return;  // whole warp leaves; nothing below synchronises across warps
-
-    if (lane == 0) {
-        mbar_init(tetFull + 0, 1); mbar_init(tetFull + 1, 1);
-        mbar_init(metaFull + 0, 1); mbar_init(metaFull + 1, 1); mbar_init(metaFull + 2, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-
-    const SubstepParams *sp = a.sp;
-    const float alphaDev = sp->alphaDev, alphaVol = sp->alphaVol, gammaVol = sp->gammaVol;
-
-    auto issue_meta = [&](uint32_t o, uint32_t end, int slot) {
-        const uint32_t bytes = (end - o) * 16u;
-        mbar_expect_tx(metaFull + slot, bytes);
         bulk_g2s(ws + L.meta(slot), a.meta + (size_t)o * 16, bytes, metaFull + slot);
     };
-    auto issue_tets = [&](int tile, int buf) {
-        mbar_expect_tx(tetFull + buf, (uint32_t)TileSmem<T>::TET_BYTES);
-        bulk_g2s(ws + L.tet(buf), a.tets + (size_t)tile * TileSmem<T>::TET_BYTES, (uint32_t)TileSmem<T>::TET_BYTES,
-                 tetFull + buf);
+    auto issue_tets = [&](int tile, int buf) {  // one thread
+        mbar_expect_tx(tetFull + buf, (uint32_t)TileSmem<T, S>::TET_BYTES);
+        bulk_g2s(ws + L.tet(buf), a.tets + (size_t)tile * TileSmem<T, S>::TET_BYTES,
+                 (uint32_t)TileSmem<T, S>::TET_BYTES, tetFull + buf);
     };
-    auto issue_gather = [&](int slot, int buf) {
+    auto issue_gather = [&](int slot, int buf) {  // all threads; always commits exactly one group
         const unsigned char *m = ws + L.meta(slot);
         const int nl = reinterpret_cast<const int *>(m)[1];
         const int *ids = reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3]);
         float4 *sx = reinterpret_cast<float4 *>(ws + L.sx(buf));
-        for (int j = lane; j < nl; j += 32) cp_async16(sx + j, a.x4 + ids[j]);
+        if (!(a.debugSkip & 4))
+            for (int j = tid; j < nl; j += NT) cp_async16(sx + j, a.x4 + ids[j]);
         cp_async_commit();
     };
 
+    // prologue: meta of tiles 0..S-1, tet blocks + gathers of tiles 0..S-2.  Thread 0 keeps the block
+    // range of the NEXT meta it will issue in registers (loaded an iteration early, never stalls).
     uint32_t nOff = 0, nEnd = 0;
-    if (lane == 0) {
-        issue_meta(a.metaOff[first], a.metaOff[first + 1], 0);
-        if (first + stride < a.numTiles) issue_meta(a.metaOff[first + stride], a.metaOff[first + stride + 1], 1);
-        issue_tets(first, 0);
-        if (first + 2 * stride < a.numTiles) { nOff = a.metaOff[first + 2 * stride]; nEnd = a.metaOff[first + 2 * stride + 1]; }
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < S; i++)
+            if (first + i * stride < a.numTiles) issue_meta(a.metaOff[first + i * stride], a.metaOff[first + i * stride + 1], i);
+#pragma unroll
+        for (int i = 0; i < S - 1; i++)
+            if (first + i * stride < a.numTiles) issue_tets(first + i * stride, i);
+        if (first + S * stride < a.numTiles) { nOff = a.metaOff[first + S * stride]; nEnd = a.metaOff[first + S * stride + 1]; }
     }
-    mbar_wait(metaFull + 0, 0);
-    issue_gather(0, 0);
+#pragma unroll
+    for (int i = 0; i < S - 1; i++) {
+        if (first + i * stride < a.numTiles) { mbar_wait(metaFull + i, 0); issue_gather(i, i); }
+        else cp_async_commit();
+    }
 
     int k = 0;
     for (int c = first; c < a.numTiles; c += stride, k++) {
-        const int cur = k & 1, mcur = k % 3;
-        cp_async_wait_all();
-        mbar_wait(tetFull + cur, (k >> 1) & 1);
-        __syncwarp();  // every lane's gathers landed; previous tile's corner sums are done
+        const int cur = k % S, mcur = k % (S + 1);
+        cp_async_wait_pending<S - 2>();
+        mbar_wait(tetFull + cur, (k / S) & 1);
+        sync();  // this tile's gathers (all threads') landed; previous tile's corner sums are finished
 
-        if (c + stride < a.numTiles) {
-            const int mnext = (k + 1) % 3;
-            mbar_wait(metaFull + mnext, ((k + 1) / 3) & 1);
-            issue_gather(mnext, cur ^ 1);
-            if (lane == 0) issue_tets(c + stride, cur ^ 1);
-        }
-        if (lane == 0 && c + 2 * stride < a.numTiles) {
-            issue_meta(nOff, nEnd, (k + 2) % 3);
-            if (c + 3 * stride < a.numTiles) { nOff = a.metaOff[c + 3 * stride]; nEnd = a.metaOff[c + 3 * stride + 1]; }
+        // ---- put tile k+S-1 (data) and tile k+S (meta) in flight ----
+        {
+            const int kn = k + S - 1, cn = c + (S - 1) * stride;
+            if (cn < a.numTiles) {
+                const int mslot = kn % (S + 1), buf = kn % S;
+                mbar_wait(metaFull + mslot, (kn / (S + 1)) & 1);
+                issue_gather(mslot, buf);
+                if (tid == 0) issue_tets(cn, buf);
+            } else {
+                cp_async_commit();
+            }
+            if (tid == 0 && c + S * stride < a.numTiles) {
+                issue_meta(nOff, nEnd, (k + S) % (S + 1));
+                if (c + (S + 1) * stride < a.numTiles) { nOff = a.metaOff[c + (S + 1) * stride]; nEnd = a.metaOff[c + (S + 1) * stride + 1]; }
+            }
         }
 
+        // ---- per-tet solve ----
         const unsigned char *tb = ws + L.tet(cur);
         const unsigned char *sxb = ws + L.sx(cur);
         float vsum = 0.0f;
 #pragma unroll
-        for (int u = 0; u < TPL; u++) {
-            const int t = lane + 32 * u;
+        for (int u = 0; u < TPT; u++) {
+            const int t = tid + NT * u;
             const float4 A = reinterpret_cast<const float4 *>(tb)[t];
             const float4 B = reinterpret_cast<const float4 *>(tb + T * 16)[t];
             const float4 C = reinterpret_cast<const float4 *>(tb + T * 32)[t];
@@ -310,104 +186,134 @@ __global__ void __launch_bounds__(TPL == 1 ? 832 : 448, 1) k_jacobi_warptiles(Ti
             V3 p[4] = {{q0.x, q0.y, q0.z}, {q1.x, q1.y, q1.z}, {q2.x, q2.y, q2.z}, {q3.x, q3.y, q3.z}};
             const float w[4] = {q0.w, q1.w, q2.w, q3.w};
             const float Q[9] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w, C.x};
-            const float vm1 = nh_solve_fast(p, w, Q, C.y, alphaDev, alphaVol, gammaVol);
+            const float vm1 = (a.debugSkip & 2) ? 0.0f : nh_solve_fast(p, w, Q, C.y, alphaDev, alphaVol, gammaVol);
             *reinterpret_cast<float4 *>(sdx + (D.x & 0xffffu)) = make_float4(p[0].x - q0.x, p[0].y - q0.y, p[0].z - q0.z, 0.f);
             *reinterpret_cast<float4 *>(sdx + (D.x >> 16)) = make_float4(p[1].x - q1.x, p[1].y - q1.y, p[1].z - q1.z, 0.f);
             *reinterpret_cast<float4 *>(sdx + (D.y & 0xffffu)) = make_float4(p[2].x - q2.x, p[2].y - q2.y, p[2].z - q2.z, 0.f);
             *reinterpret_cast<float4 *>(sdx + (D.y >> 16)) = make_float4(p[3].x - q3.x, p[3].y - q3.y, p[3].z - q3.z, 0.f);
-            vsum += (C.y != 0.0f) ? vm1 : 0.0f;
+            vsum += (C.y != 0.0f) ? vm1 : 0.0f;  // padding records carry invRestVolume = 0
         }
-        if (a.volAcc) {
+        if (a.volAcc) {  // volError (src/Softbody.js:163): warp-reduce, one double atomic per warp
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
-            if (lane == 0) atomicAdd(a.volAcc, (double)vsum);
+            if ((tid & 31) == 0) atomicAdd(a.volAcc, (double)vsum);
         }
-        __syncwarp();
+        sync();
 
+        // ---- per-tile-vertex sum of corner dx, ascending (tet, corner) order ----
         const unsigned char *m = ws + L.meta(mcur);
         const int v0 = reinterpret_cast<const int *>(m)[0];
         const int nl = reinterpret_cast<const int *>(m)[1];
         const uint16_t *scol = reinterpret_cast<const uint16_t *>(m + 16);
-        for (int j = lane; j < nl; j += 32) {
-            const int val = m[a.metaValOff + j];
-            const unsigned char *base = sdx + j * 16;
-            float ax = 0.0f, ay = 0.0f, az = 0.0f;
+        if (!(a.debugSkip & 1))
+            for (int j = tid; j < nl; j += NT) {
+                const int val = m[a.metaValOff + j];
+                const unsigned char *base = sdx + j * 16;
+                float ax = 0.0f, ay = 0.0f, az = 0.0f;
 #pragma unroll 4
-            for (int i = 0; i < val; i++) {
-                const float4 d = *reinterpret_cast<const float4 *>(base + scol[i]);
-                ax += d.x; ay += d.y; az += d.z;
+                for (int i = 0; i < val; i++) {
+                    const float4 d = *reinterpret_cast<const float4 *>(base + scol[i]);
+                    ax += d.x; ay += d.y; az += d.z;
+                }
+                if (a.acc) atomicAdd(a.acc + reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3])[j],
+                                     make_float4(ax, ay, az, 0.0f));
+                else a.part[v0 + j] = make_float4(ax, ay, az, 0.0f);
             }
-            if (a.acc) atomicAdd(a.acc + reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3])[j],
-                                 make_float4(ax, ay, az, 0.0f));
-            else a.part[v0 + j] = make_float4(ax, ay, az, 0.0f);
-        }
     }
+}
+
+// CTA tiles: T tets per tile, one tet per thread, __syncthreads between the phases.
+template <int T, int S, int MINB>
+__global__ void __launch_bounds__(T, MINB) k_jacobi_tiles(TileArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    if ((int)blockIdx.x >= a.numTiles) return;
+    tile_worker<T, 1, S, false>(a, smem, threadIdx.x, blockIdx.x, gridDim.x);
+}
+
+// Warp tiles: every warp is its own worker with private staging and mbarriers (tile = 32 * TPL tets);
+// no block-level barrier anywhere, so warps drift apart and cover each other's load and sum phases.
+template <int TPL, int S>
+__global__ void __launch_bounds__(TPL == 1 ? 832 : 448, 1) k_jacobi_warptiles(TileArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int first = blockIdx.x * wpb + wid;
+    if (first >= a.numTiles) return;
+    const TileSmem<32 * TPL, S> L(a.metaStride, a.maxTileVertsPad);
+    tile_worker<32, TPL, S, true>(a, smem + (size_t)wid * L.total, lane, first, gridDim.x * wpb);
+}
+
+template <int T, int S>
+static size_t tile_smem_bytes(const TileArgs &a) { return (size_t)TileSmem<T, S>(a.metaStride, a.maxTileVertsPad).total; }
+
+static int tile_stages(int clusterSize) {
+    int s = clusterSize >= 256 ? 2 : 3;
+    if (const char *e = getenv("TETSIM_TILE_STAGES")) { int v = atoi(e); if (v >= 2 && v <= 4) s = v; }
+    return s;
 }
 
 size_t jacobi_tiles_smem(int clusterSize, const TileArgs &a) {
-    switch (clusterSize) {
-        case 32: return (size_t)((TileSmem<32>(a.metaStride, a.maxTileVertsPad).total + 127) & ~127);   // per warp
-        case 64: return (size_t)((TileSmem<64>(a.metaStride, a.maxTileVertsPad).total + 127) & ~127);   // per warp
-        case 128: return (size_t)TileSmem<128>(a.metaStride, a.maxTileVertsPad).total;
-        case 256: return (size_t)TileSmem<256>(a.metaStride, a.maxTileVertsPad).total;
-        default: return (size_t)TileSmem<512>(a.metaStride, a.maxTileVertsPad).total;
-    }
+    const int S = tile_stages(clusterSize);
+#define TS_CASE(T_) case T_: return S == 2 ? tile_smem_bytes<T_, 2>(a) : (S == 3 ? tile_smem_bytes<T_, 3>(a) : tile_smem_bytes<T_, 4>(a));
+    switch (clusterSize) { TS_CASE(32) TS_CASE(64) TS_CASE(128) TS_CASE(256) default: return tile_smem_bytes<512, 2>(a); }
+#undef TS_CASE
 }
 
-template <int T, int MINB>
+struct LaunchCache { size_t smem = 0; int n = 0, sms = 0; };
+
+template <int T, int S, int MINB>
 static void launch_tiles_T(cudaStream_t s, const TileArgs &a) {
-    const size_t smem = (size_t)TileSmem<T>(a.metaStride, a.maxTileVertsPad).total;
-    static size_t configured = 0;
-    static int ctasPerSm = 0, numSms = 0;
-    if (smem != configured) {
-        cudaFuncSetAttribute(k_jacobi_tiles<T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, k_jacobi_tiles<T, MINB>, T, smem);
+    const size_t smem = tile_smem_bytes<T, S>(a);
+    static LaunchCache lc;
+    if (smem != lc.smem) {
+        cudaFuncSetAttribute(k_jacobi_tiles<T, S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lc.n, k_jacobi_tiles<T, S, MINB>, T, smem);
         int dev = 0;
         cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&numSms, cudaDevAttrMultiProcessorCount, dev);
-        configured = smem;
+        cudaDeviceGetAttribute(&lc.sms, cudaDevAttrMultiProcessorCount, dev);
+        if (lc.n < 1) lc.n = 1;
+        lc.smem = smem;
     }
-    if (ctasPerSm < 1) ctasPerSm = 1;
-    int grid = numSms * ctasPerSm;  // persistent: every CTA resident, tiles strided over the grid
+    int grid = lc.sms * lc.n;  // persistent: every CTA resident, tiles strided over the grid
     if (grid > a.numTiles) grid = a.numTiles;
-    k_jacobi_tiles<T, MINB><<<grid, T, smem, s>>>(a);
+    k_jacobi_tiles<T, S, MINB><<<grid, T, smem, s>>>(a);
 }
 
 // Warp tiles: one CTA per SM holding as many warps as shared memory and registers allow.
-template <int TPL>
+template <int TPL, int S>
 static void launch_warptiles(cudaStream_t s, const TileArgs &a) {
-    const size_t perWarp = (size_t)((TileSmem<32 * TPL>(a.metaStride, a.maxTileVertsPad).total + 127) & ~127);
-    static size_t configured = 0;
-    static int warps = 0, numSms = 0;
-    if (perWarp != configured) {
+    const size_t perWarp = tile_smem_bytes<32 * TPL, S>(a);
+    static LaunchCache lc;
+    if (perWarp != lc.smem) {
         int dev = 0, maxSmem = 0;
         cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&numSms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&lc.sms, cudaDevAttrMultiProcessorCount, dev);
         cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
         cudaFuncAttributes fa;
-        cudaFuncGetAttributes(&fa, k_jacobi_warptiles<TPL>);
-        int byRegs = 65536 / (32 * (fa.numRegs > 0 ? fa.numRegs : 64));
-        warps = (int)((size_t)maxSmem / perWarp);
+        cudaFuncGetAttributes(&fa, k_jacobi_warptiles<TPL, S>);
+        const int byRegs = 65536 / (32 * (fa.numRegs > 0 ? fa.numRegs : 64));
+        int warps = (int)((size_t)maxSmem / perWarp);
         if (warps > byRegs) warps = byRegs;
         if (warps > (TPL == 1 ? 832 : 448) / 32) warps = (TPL == 1 ? 832 : 448) / 32;
         if (const char *w = getenv("TETSIM_WARPS_PER_SM")) { int v = atoi(w); if (v >= 1 && v < warps) warps = v; }
         if (warps < 1) warps = 1;
-        cudaFuncSetAttribute(k_jacobi_warptiles<TPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(perWarp * warps));
-        configured = perWarp;
+        cudaFuncSetAttribute(k_jacobi_warptiles<TPL, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(perWarp * warps));
+        lc.n = warps;
+        lc.smem = perWarp;
     }
-    int grid = numSms;
-    if ((long long)grid * warps > a.numTiles) grid = (a.numTiles + warps - 1) / warps;
-    k_jacobi_warptiles<TPL><<<grid, 32 * warps, perWarp * warps, s>>>(a);
+    int grid = lc.sms;
+    if ((long long)grid * lc.n > a.numTiles) grid = (a.numTiles + lc.n - 1) / lc.n;
+    k_jacobi_warptiles<TPL, S><<<grid, 32 * lc.n, perWarp * lc.n, s>>>(a);
 }
 
 void launch_jacobi_tiles(cudaStream_t s, int clusterSize, const TileArgs &a) {
     if (a.numTiles <= 0) return;
+    const int S = tile_stages(clusterSize);
     switch (clusterSize) {
-        case 32: launch_warptiles<1>(s, a); break;
-        case 64: launch_warptiles<2>(s, a); break;
-        case 128: launch_tiles_T<128, 6>(s, a); break;
-        case 256: launch_tiles_T<256, 4>(s, a); break;
-        case 512: launch_tiles_T<512, 2>(s, a); break;
+        case 32: S == 2 ? launch_warptiles<1, 2>(s, a) : (S == 3 ? launch_warptiles<1, 3>(s, a) : launch_warptiles<1, 4>(s, a)); break;
+        case 64: S == 2 ? launch_warptiles<2, 2>(s, a) : (S == 3 ? launch_warptiles<2, 3>(s, a) : launch_warptiles<2, 4>(s, a)); break;
+        case 128: S == 2 ? launch_tiles_T<128, 2, 6>(s, a) : (S == 3 ? launch_tiles_T<128, 3, 5>(s, a) : launch_tiles_T<128, 4, 4>(s, a)); break;
+        case 256: S == 2 ? launch_tiles_T<256, 2, 4>(s, a) : (S == 3 ? launch_tiles_T<256, 3, 2>(s, a) : launch_tiles_T<256, 4, 2>(s, a)); break;
+        case 512: launch_tiles_T<512, 2, 2>(s, a); break;
         default: break;
     }
 }
