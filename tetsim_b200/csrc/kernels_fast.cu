@@ -68,16 +68,30 @@ struct TileSmem {
     __host__ __device__ TileSmem(int metaStride_, int maxTileVertsPad) {
         sxBytes = maxTileVertsPad * 16;
         metaStride = metaStride_;
-        sdx = S * TET_BYTES;
+        sdx = 0;
         sx0 = sdx + (4 * T + 1) * 16;  // + one spare entry for padding records
         meta0 = sx0 + S * sxBytes;
         bars = meta0 + (S + 1) * metaStride;
-        total = (bars + (2 * S + 1) * 8 + 127) & ~127;
+        total = (bars + (S + 1) * 8 + 127) & ~127;
     }
-    __host__ __device__ int tet(int buf) const { return buf * TET_BYTES; }
     __host__ __device__ int sx(int buf) const { return sx0 + buf * sxBytes; }
     __host__ __device__ int meta(int slot) const { return meta0 + slot * metaStride; }
 };
+
+__device__ __forceinline__ float4 ldg_stream4(const void *p) {  // read-once stream: do not pollute L1
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 ldg_stream2(const void *p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void *p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 
 template <int N>
 __device__ __forceinline__ void cp_async_wait_pending() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -91,13 +105,12 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
                                             const int stride) {
     constexpr int T = NT * TPT;
     const TileSmem<T, S> L(a.metaStride, a.maxTileVertsPad);
-    uint64_t *tetFull = reinterpret_cast<uint64_t *>(ws + L.bars);  // [S]
-    uint64_t *metaFull = tetFull + S;                               // [S + 1]
+    uint64_t *metaFull = reinterpret_cast<uint64_t *>(ws + L.bars);  // [S + 1]
     unsigned char *const sdx = ws + L.sdx;
     auto sync = [&]() { if (WARP_SCOPE) __syncwarp(); else __syncthreads(); };
 
     if (tid == 0) {
-        for (int i = 0; i < 2 * S + 1; i++) mbar_init(tetFull + i, 1);
+        for (int i = 0; i < S + 1; i++) mbar_init(metaFull + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     sync();
@@ -110,10 +123,13 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
         mbar_expect_tx(metaFull + slot, bytes);
         bulk_g2s(ws + L.meta(slot), a.meta + (size_t)o * 16, bytes, metaFull + slot);
     };
-    auto issue_tets = [&](int tile, int buf) {  // one thread
-        mbar_expect_tx(tetFull + buf, (uint32_t)TileSmem<T, S>::TET_BYTES);
-        bulk_g2s(ws + L.tet(buf), a.tets + (size_t)tile * TileSmem<T, S>::TET_BYTES,
-                 (uint32_t)TileSmem<T, S>::TET_BYTES, tetFull + buf);
+    // The tet stream is read once, straight into registers (3.5 coalesced LDG.128 per tet: staging it in
+    // shared memory would cost a write and a read of the SM's 128 B/clk shared-memory pipe, which the
+    // gather/scatter traffic of this kernel already loads heavily).  Its HBM latency is hidden by a
+    // bulk L2 prefetch of the whole 56*T-byte block issued PF tiles ahead.
+    constexpr int PF = 2;
+    auto prefetch_tets = [&](int tile) {  // one thread
+        bulk_prefetch_l2(a.tets + (size_t)tile * TileSmem<T, S>::TET_BYTES, (uint32_t)TileSmem<T, S>::TET_BYTES);
     };
     auto issue_gather = [&](int slot, int buf) {  // all threads; always commits exactly one group
         const unsigned char *m = ws + L.meta(slot);
@@ -133,8 +149,8 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
         for (int i = 0; i < S; i++)
             if (first + i * stride < a.numTiles) issue_meta(a.metaOff[first + i * stride], a.metaOff[first + i * stride + 1], i);
 #pragma unroll
-        for (int i = 0; i < S - 1; i++)
-            if (first + i * stride < a.numTiles) issue_tets(first + i * stride, i);
+        for (int i = 1; i <= PF; i++)
+            if (first + i * stride < a.numTiles) prefetch_tets(first + i * stride);
         if (first + S * stride < a.numTiles) { nOff = a.metaOff[first + S * stride]; nEnd = a.metaOff[first + S * stride + 1]; }
     }
 #pragma unroll
@@ -146,8 +162,19 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
     int k = 0;
     for (int c = first; c < a.numTiles; c += stride, k++) {
         const int cur = k % S, mcur = k % (S + 1);
+        // this tile's records: issue the loads first, they land while we wait and prefetch below
+        const unsigned char *tb = a.tets + (size_t)c * TileSmem<T, S>::TET_BYTES;
+        float4 rA[TPT], rB[TPT], rC[TPT];
+        uint2 rD[TPT];
+#pragma unroll
+        for (int u = 0; u < TPT; u++) {
+            const int t = tid + NT * u;
+            rA[u] = ldg_stream4(tb + t * 16);
+            rB[u] = ldg_stream4(tb + T * 16 + t * 16);
+            rC[u] = ldg_stream4(tb + T * 32 + t * 16);
+            rD[u] = ldg_stream2(tb + T * 48 + t * 8);
+        }
         cp_async_wait_pending<S - 2>();
-        mbar_wait(tetFull + cur, (k / S) & 1);
         sync();  // this tile's gathers (all threads') landed; previous tile's corner sums are finished
 
         // ---- put tile k+S-1 (data) and tile k+S (meta) in flight ----
@@ -157,10 +184,10 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
                 const int mslot = kn % (S + 1), buf = kn % S;
                 mbar_wait(metaFull + mslot, (kn / (S + 1)) & 1);
                 issue_gather(mslot, buf);
-                if (tid == 0) issue_tets(cn, buf);
             } else {
                 cp_async_commit();
             }
+            if (tid == 0 && c + (PF + 1) * stride < a.numTiles) prefetch_tets(c + (PF + 1) * stride);
             if (tid == 0 && c + S * stride < a.numTiles) {
                 issue_meta(nOff, nEnd, (k + S) % (S + 1));
                 if (c + (S + 1) * stride < a.numTiles) { nOff = a.metaOff[c + (S + 1) * stride]; nEnd = a.metaOff[c + (S + 1) * stride + 1]; }
@@ -168,16 +195,12 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
         }
 
         // ---- per-tet solve ----
-        const unsigned char *tb = ws + L.tet(cur);
         const unsigned char *sxb = ws + L.sx(cur);
         float vsum = 0.0f;
 #pragma unroll
         for (int u = 0; u < TPT; u++) {
-            const int t = tid + NT * u;
-            const float4 A = reinterpret_cast<const float4 *>(tb)[t];
-            const float4 B = reinterpret_cast<const float4 *>(tb + T * 16)[t];
-            const float4 C = reinterpret_cast<const float4 *>(tb + T * 32)[t];
-            const uint2 D = reinterpret_cast<const uint2 *>(tb + T * 48)[t];
+            const float4 A = rA[u], B = rB[u], C = rC[u];
+            const uint2 D = rD[u];
             const unsigned s01 = __float_as_uint(C.z), s23 = __float_as_uint(C.w);
             const float4 q0 = *reinterpret_cast<const float4 *>(sxb + (s01 & 0xffffu));
             const float4 q1 = *reinterpret_cast<const float4 *>(sxb + (s01 >> 16));
@@ -246,7 +269,7 @@ template <int T, int S>
 static size_t tile_smem_bytes(const TileArgs &a) { return (size_t)TileSmem<T, S>(a.metaStride, a.maxTileVertsPad).total; }
 
 static int tile_stages(int clusterSize) {
-    int s = clusterSize >= 256 ? 2 : 3;
+    int s = 2;
     if (const char *e = getenv("TETSIM_TILE_STAGES")) { int v = atoi(e); if (v >= 2 && v <= 4) s = v; }
     return s;
 }
