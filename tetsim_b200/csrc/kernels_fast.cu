@@ -169,19 +169,30 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
         const int v0 = reinterpret_cast<const int *>(m)[0];
         const int nl = reinterpret_cast<const int *>(m)[1];
         const uint16_t *scol = reinterpret_cast<const uint16_t *>(m + 16);
+        // Two lanes per tile vertex (lane h sums diagonals h, h+2, ...; halves combined with one shuffle:
+        // a fixed order, so still reproducible), and the vertex -> warp assignment rotates with the tile
+        // index: vertices are valence-sorted, so without the rotation warp 0 would always own the
+        // long lists and every hand-over would wait for it.
+        const int lt = WARP_SCOPE ? tid : ((tid + 32 * (kk % NWARPS)) & (NT - 1));
         if (!(a.debugSkip & 1))
-            for (int j = tid; j < nl; j += NT) {
-                const int val = m[a.metaValOff + j];
+            for (int jj = lt; jj < 2 * ((nl + 15) & ~15); jj += NT) {  // whole warps stay together for the shuffle
+                const int j = jj >> 1, h = jj & 1;
+                const int val = j < nl ? m[a.metaValOff + j] : 0;
                 const unsigned char *base = sdx + j * 16;
                 float ax = 0.0f, ay = 0.0f, az = 0.0f;
 #pragma unroll 4
-                for (int i = 0; i < val; i++) {
+                for (int i = h; i < val; i += 2) {
                     const float4 d = *reinterpret_cast<const float4 *>(base + scol[i]);
                     ax += d.x; ay += d.y; az += d.z;
                 }
-                if (a.acc) atomicAdd(a.acc + reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3])[j],
-                                     make_float4(ax, ay, az, 0.0f));
-                else a.part[v0 + j] = make_float4(ax, ay, az, 0.0f);
+                ax += __shfl_xor_sync(0xffffffffu, ax, 1);
+                ay += __shfl_xor_sync(0xffffffffu, ay, 1);
+                az += __shfl_xor_sync(0xffffffffu, az, 1);
+                if (h == 0 && j < nl) {
+                    if (a.acc) atomicAdd(a.acc + reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3])[j],
+                                         make_float4(ax, ay, az, 0.0f));
+                    else a.part[v0 + j] = make_float4(ax, ay, az, 0.0f);
+                }
             }
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(sumDone + (kk & 1));
@@ -203,6 +214,9 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
     for (int i = 0; i < S - 1; i++)
         if (first + i * stride < a.numTiles) { mbar_wait(metaFull + i, 0); issue_gather(i, i); }
 
+    long long tph[6] = {0, 0, 0, 0, 0, 0};
+    long long tlast = a.trace ? clock64() : 0;
+    auto mark = [&](int ph) { if (a.trace) { long long now = clock64(); tph[ph] += now - tlast; tlast = now; } };
     int k = 0;
     for (int c = first; c < a.numTiles; c += stride, k++) {
         // ---- this tile's records: issue the loads first, they land while we wait below ----
@@ -218,6 +232,7 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
             rD[u] = ldg_stream2(tb + T * 48 + t * 8);
         }
         mbar_wait(gatherDone + k % S, (k / S) & 1);  // every thread's gathers of this tile have landed
+        mark(0);
 
         // ---- per-tet solve ----
         const unsigned char *sxb = ws + L.sx(k % S);
@@ -242,6 +257,8 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
             d3[u] = make_float4(p[3].x - q3.x, p[3].y - q3.y, p[3].z - q3.z, 0.f);
             vsum += (C.y != 0.0f) ? vm1 : 0.0f;  // padding records carry invRestVolume = 0
         }
+        if (a.trace) { float f = d0[0].x + d1[0].y + d2[0].z + d3[0].x; asm volatile("" ::"f"(f)); }
+        mark(1);
         // park the corners' dx: this buffer was last read by the corner sums of tile k-2
         if (k >= 2) mbar_wait(sumDone + (k & 1), ((k >> 1) + 1) & 1);
 #pragma unroll
@@ -260,8 +277,10 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
             if ((tid & 31) == 0) atomicAdd(a.volAcc, (double)vsum);
         }
 
+        mark(2);
         // ---- every warp is done with tile k-1's vertex tile and has parked its dx of tile k-1 ----
         if (k >= 1) mbar_wait(scatterDone + ((k - 1) & 1), ((k - 1) >> 1) & 1);
+        mark(3);
         {   // put tile k+S-1 (vertex gather) and tile k+S (meta) in flight; buffers of tile k-1 are free now
             const int kn = k + S - 1, cn = c + (S - 1) * stride;
             if (cn < a.numTiles) {
@@ -277,7 +296,14 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
                 }
             }
         }
+        mark(4);
         if (k >= 1) sum_corners(k - 1);
+        mark(5);
+    }
+    if (a.trace && (tid & 31) == 0) {
+        for (int i = 0; i < 6; i++) atomicAdd(a.trace + i, (unsigned long long)tph[i]);
+        atomicAdd(a.trace + 6, (unsigned long long)k);
+        atomicAdd(a.trace + 7, 1ull);
     }
     // drain: corner sums of the last tile
     mbar_wait(scatterDone + ((k - 1) & 1), ((k - 1) >> 1) & 1);
@@ -308,7 +334,7 @@ template <int T, int S>
 static size_t tile_smem_bytes(const TileArgs &a) { return (size_t)TileSmem<T, S>(a.metaStride, a.maxTileVertsPad).total; }
 
 static int tile_stages(int clusterSize) {
-    int s = 2;
+    int s = 3;
     if (const char *e = getenv("TETSIM_TILE_STAGES")) { int v = atoi(e); if (v >= 2 && v <= 4) s = v; }
     return s;
 }
@@ -374,7 +400,7 @@ void launch_jacobi_tiles(cudaStream_t s, int clusterSize, const TileArgs &a) {
         case 32: S == 2 ? launch_warptiles<1, 2>(s, a) : (S == 3 ? launch_warptiles<1, 3>(s, a) : launch_warptiles<1, 4>(s, a)); break;
         case 64: S == 2 ? launch_warptiles<2, 2>(s, a) : (S == 3 ? launch_warptiles<2, 3>(s, a) : launch_warptiles<2, 4>(s, a)); break;
         case 128: S == 2 ? launch_tiles_T<128, 2, 6>(s, a) : (S == 3 ? launch_tiles_T<128, 3, 5>(s, a) : launch_tiles_T<128, 4, 4>(s, a)); break;
-        case 256: S == 2 ? launch_tiles_T<256, 2, 4>(s, a) : (S == 3 ? launch_tiles_T<256, 3, 2>(s, a) : launch_tiles_T<256, 4, 2>(s, a)); break;
+        case 256: S == 2 ? launch_tiles_T<256, 2, 4>(s, a) : (S == 3 ? launch_tiles_T<256, 3, 4>(s, a) : launch_tiles_T<256, 4, 2>(s, a)); break;
         case 512: launch_tiles_T<512, 2, 2>(s, a); break;
         default: break;
     }

@@ -166,7 +166,43 @@ bool build_cluster_plan(int numVerts, int numTets, const int *tetIds, const std:
                         int worldSize, ClusterPlan &P, std::string &err) {
     P = ClusterPlan();
     P.T = T;
-    const int totalClusters = (numTets + T - 1) / T;
+    // ---- cut the tet sequence into tiles: at most T tets and at most `vertCap` distinct vertices ----
+    // A space-filling curve occasionally jumps, and a tile straddling a jump touches 2-3x the average
+    // number of vertices; since the kernel sizes its shared-memory vertex buffers by the LARGEST tile,
+    // such tiles are closed early (their remaining record slots become padding).
+    std::vector<int> tileStart;  // position in `order` of each tile's first tet, + sentinel
+    {
+        std::vector<int> stampG((size_t)numVerts, -1);
+        auto cut = [&](int cap, double *avgOut) {
+            tileStart.clear();
+            std::fill(stampG.begin(), stampG.end(), -1);
+            int tile = -1, nt = T, nv = 0;
+            long long sumV = 0;
+            for (int pos = 0; pos < numTets; pos++) {
+                const int *t = tetIds + 4 * (size_t)order[pos];
+                int fresh = 0;
+                if (tile >= 0) for (int k = 0; k < 4; k++) fresh += stampG[t[k]] != tile;
+                if (nt == T || (cap > 0 && nv + fresh > cap)) {
+                    sumV += nv;
+                    tile++; nt = 0; nv = 0;
+                    tileStart.push_back(pos);
+                }
+                for (int k = 0; k < 4; k++)
+                    if (stampG[t[k]] != tile) { stampG[t[k]] = tile; nv++; }
+                nt++;
+            }
+            sumV += nv;
+            tileStart.push_back(numTets);
+            if (avgOut) *avgOut = tile >= 0 ? (double)sumV / (tile + 1) : 0.0;
+        };
+        double avg = 0.0;
+        cut(0, &avg);
+        int cap = (((int)(1.4 * avg) + 15) / 16) * 16;
+        if (const char *e = getenv("TETSIM_TILE_VERT_CAP")) cap = atoi(e);
+        if (cap > 0 && cap < 16) cap = 16;
+        if (cap > 0) cut(cap, nullptr);
+    }
+    const int totalClusters = (int)tileStart.size() - 1;
     auto firstClusterOf = [&](int r) { return (int)((int64_t)totalClusters * r / worldSize); };
     const int c0 = firstClusterOf(rank), c1 = firstClusterOf(rank + 1);
     P.numClusters = c1 - c0;
@@ -176,10 +212,10 @@ bool build_cluster_plan(int numVerts, int numTets, const int *tetIds, const std:
     std::vector<int> rmin, rmax;
     if (worldSize > 1) { rmin.assign((size_t)numVerts, worldSize); rmax.assign((size_t)numVerts, -1); }
     {
-        int r = 0;
+        int r = 0, cl = 0;
         for (int pos = 0; pos < numTets; pos++) {
             if (worldSize > 1) {
-                int cl = pos / T;
+                while (pos >= tileStart[cl + 1]) cl++;
                 while (cl >= firstClusterOf(r + 1)) r++;
             }
             const int *t = tetIds + 4 * (size_t)order[pos];
@@ -198,7 +234,7 @@ bool build_cluster_plan(int numVerts, int numTets, const int *tetIds, const std:
         for (int v = 0; v < numVerts; v++)
             if (rmax[v] > rmin[v]) boundary.push_back(v);
     P.numBoundary = (int)boundary.size();
-    const int posBegin = c0 * T, posEnd = std::min(numTets, c1 * T);
+    const int posBegin = tileStart[c0], posEnd = tileStart[c1];
     P.localTets = std::max(0, posEnd - posBegin);
     for (int v : boundary) local[v] = -2;
     int nI = 0;
@@ -233,7 +269,7 @@ bool build_cluster_plan(int numVerts, int numTets, const int *tetIds, const std:
     std::vector<int> cornerRank;  // per corner of the tile: its index i in its vertex's list
     int maxTileVal = 0;
     for (int c = 0; c < P.numClusters; c++) {
-        const int pb = (c0 + c) * T, pe = std::min(numTets, pb + T);
+        const int pb = tileStart[c0 + c], pe = tileStart[c0 + c + 1];
         tileVerts.clear(); tileVal.clear();
         cornerRank.assign(4 * (size_t)T, 0);
         for (int pos = pb; pos < pe; pos++) {
