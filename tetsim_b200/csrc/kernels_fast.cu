@@ -63,19 +63,17 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 template <int T, int S>
 struct TileSmem {
     static constexpr int TET_BYTES = T * 56;
-    static constexpr int NBARS = (S + 2) + S + 2 + 2;  // metaFull, gatherDone, scatterDone, sumDone
     // byte offsets inside the worker's shared-memory region (computed, never indexed: stays in registers)
-    int sxBytes, metaStride, sdxBytes, sx0, meta0, bars, total;
+    int sxBytes, metaStride, sdx, sx0, meta0, bars, total;
     __host__ __device__ TileSmem(int metaStride_, int maxTileVertsPad) {
         sxBytes = maxTileVertsPad * 16;
         metaStride = metaStride_;
-        sdxBytes = (4 * T + 1) * 16;   // + one spare entry for padding records
-        sx0 = 2 * sdxBytes;            // two dx buffers: tile k's sums overlap tile k+1's math
+        sdx = 0;
+        sx0 = sdx + (4 * T + 1) * 16;  // + one spare entry for padding records
         meta0 = sx0 + S * sxBytes;
-        bars = meta0 + (S + 2) * metaStride;
-        total = (bars + NBARS * 8 + 127) & ~127;
+        bars = meta0 + (S + 1) * metaStride;
+        total = (bars + (S + 1) * 8 + 127) & ~127;
     }
-    __host__ __device__ int sdx(int buf) const { return buf * sdxBytes; }
     __host__ __device__ int sx(int buf) const { return sx0 + buf * sxBytes; }
     __host__ __device__ int meta(int slot) const { return meta0 + slot * metaStride; }
 };
@@ -94,47 +92,28 @@ __device__ __forceinline__ uint2 ldg_stream2(const void *p) {
 __device__ __forceinline__ void bulk_prefetch_l2(const void *p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *b) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
-}
-// all cp.async copies this thread issued so far signal the barrier when they have landed
-__device__ __forceinline__ void cp_async_arrive(uint64_t *b) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(b)) : "memory");
-}
+
+template <int N>
+__device__ __forceinline__ void cp_async_wait_pending() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // One persistent worker (a CTA when WARP_SCOPE = false, a single warp when true) walking tiles
 // first, first + stride, ...  NT = threads of the worker, TPT = tets per thread, T = NT * TPT.
-//
-// Dataflow, not phases: there is NO block-wide barrier in the loop.  Every hand-over is an mbarrier
-// that a warp waits on only when it needs the data (round-1 ncu of the __syncthreads version: 35 %
-// of all stall samples sat on the two barriers, because the corner sums keep half the warps busy
-// while the other half wait):
-//   metaFull[S+2]   TMA bulk copy of a tile's meta block has landed          (complete_tx)
-//   gatherDone[S]   every thread's cp.async vertex gathers of a tile landed  (cp.async.mbarrier.arrive)
-//   scatterDone[2]  every warp has parked its corners' dx of tile k          (one arrive per warp)
-//   sumDone[2]      every warp has finished summing the corners of tile k    (one arrive per warp)
-// Iteration k of a warp:  records(k) -> [gatherDone k] math(k) -> [sumDone k-2] park dx(k), arrive
-// -> [scatterDone k-1] issue gathers(k+S-1), meta(k+S), L2 prefetch -> sum corners(k-1), arrive.
-// The sums of tile k-1 therefore overlap the math of tile k of the other warps of the same CTA.
+// S-stage ring: at tile k the tet block and vertex gather of tile k+S-1 and the meta block of tile
+// k+S are put in flight, so S-1 tiles of HBM/L2 latency are covered by math.
 template <int NT, int TPT, int S, bool WARP_SCOPE>
 __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws, const int tid, const int first,
                                             const int stride) {
     constexpr int T = NT * TPT;
-    constexpr int NWARPS = NT / 32;
-    using SM = TileSmem<T, S>;
-    const SM L(a.metaStride, a.maxTileVertsPad);
-    uint64_t *metaFull = reinterpret_cast<uint64_t *>(ws + L.bars);  // [S + 2]
-    uint64_t *gatherDone = metaFull + (S + 2);                       // [S]
-    uint64_t *scatterDone = gatherDone + S;                          // [2]
-    uint64_t *sumDone = scatterDone + 2;                             // [2]
+    const TileSmem<T, S> L(a.metaStride, a.maxTileVertsPad);
+    uint64_t *metaFull = reinterpret_cast<uint64_t *>(ws + L.bars);  // [S + 1]
+    unsigned char *const sdx = ws + L.sdx;
+    auto sync = [&]() { if (WARP_SCOPE) __syncwarp(); else __syncthreads(); };
 
     if (tid == 0) {
-        for (int i = 0; i < S + 2; i++) mbar_init(metaFull + i, 1);
-        for (int i = 0; i < S; i++) mbar_init(gatherDone + i, NT);
-        for (int i = 0; i < 2; i++) { mbar_init(scatterDone + i, NWARPS); mbar_init(sumDone + i, NWARPS); }
+        for (int i = 0; i < S + 1; i++) mbar_init(metaFull + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (WARP_SCOPE) __syncwarp(); else __syncthreads();
+    sync();
 
     const SubstepParams *sp = a.sp;
     const float alphaDev = sp->alphaDev, alphaVol = sp->alphaVol, gammaVol = sp->gammaVol;
@@ -150,58 +129,23 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
     // bulk L2 prefetch of the whole 56*T-byte block issued PF tiles ahead.
     constexpr int PF = 2;
     auto prefetch_tets = [&](int tile) {  // one thread
-        bulk_prefetch_l2(a.tets + (size_t)tile * SM::TET_BYTES, (uint32_t)SM::TET_BYTES);
+        bulk_prefetch_l2(a.tets + (size_t)tile * TileSmem<T, S>::TET_BYTES, (uint32_t)TileSmem<T, S>::TET_BYTES);
     };
-    auto issue_gather = [&](int slot, int buf) {  // all threads; each arrives once on gatherDone[buf]
+    auto issue_gather = [&](int slot, int buf) {  // all threads; always commits exactly one group
         const unsigned char *m = ws + L.meta(slot);
         const int nl = reinterpret_cast<const int *>(m)[1];
         const int *ids = reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3]);
         float4 *sx = reinterpret_cast<float4 *>(ws + L.sx(buf));
-        if (!(a.debugSkip & 4)) {
-            if (tid < nl) cp_async16(sx + tid, a.x4 + ids[tid]);
-            for (int j = tid + NT; j < nl; j += NT) cp_async16(sx + j, a.x4 + ids[j]);
-        }
-        cp_async_arrive(gatherDone + buf);
-    };
-    auto sum_corners = [&](int kk) {  // tile kk of this worker: per-tile-vertex sums, ascending (tet, corner) order
-        const unsigned char *m = ws + L.meta(kk % (S + 2));
-        const unsigned char *sdx = ws + L.sdx(kk & 1);
-        const int v0 = reinterpret_cast<const int *>(m)[0];
-        const int nl = reinterpret_cast<const int *>(m)[1];
-        const uint16_t *scol = reinterpret_cast<const uint16_t *>(m + 16);
-        // Two lanes per tile vertex (lane h sums diagonals h, h+2, ...; halves combined with one shuffle:
-        // a fixed order, so still reproducible), and the vertex -> warp assignment rotates with the tile
-        // index: vertices are valence-sorted, so without the rotation warp 0 would always own the
-        // long lists and every hand-over would wait for it.
-        const int lt = WARP_SCOPE ? tid : ((tid + 32 * (kk % NWARPS)) & (NT - 1));
-        if (!(a.debugSkip & 1))
-            for (int jj = lt; jj < 2 * ((nl + 15) & ~15); jj += NT) {  // whole warps stay together for the shuffle
-                const int j = jj >> 1, h = jj & 1;
-                const int val = j < nl ? m[a.metaValOff + j] : 0;
-                const unsigned char *base = sdx + j * 16;
-                float ax = 0.0f, ay = 0.0f, az = 0.0f;
-#pragma unroll 4
-                for (int i = h; i < val; i += 2) {
-                    const float4 d = *reinterpret_cast<const float4 *>(base + scol[i]);
-                    ax += d.x; ay += d.y; az += d.z;
-                }
-                ax += __shfl_xor_sync(0xffffffffu, ax, 1);
-                ay += __shfl_xor_sync(0xffffffffu, ay, 1);
-                az += __shfl_xor_sync(0xffffffffu, az, 1);
-                if (h == 0 && j < nl) {
-                    if (a.acc) atomicAdd(a.acc + reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3])[j],
-                                         make_float4(ax, ay, az, 0.0f));
-                    else a.part[v0 + j] = make_float4(ax, ay, az, 0.0f);
-                }
-            }
-        __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(sumDone + (kk & 1));
+        if (!(a.debugSkip & 4))
+            for (int j = tid; j < nl; j += NT) cp_async16(sx + j, a.x4 + ids[j]);
+        cp_async_commit();
     };
 
-    // prologue: meta of tiles 0..S-1, gathers of tiles 0..S-2, L2 prefetch of tet blocks 1..PF.  Thread 0
-    // keeps the block range of the NEXT meta it will issue in registers (loaded an iteration early).
+    // prologue: meta of tiles 0..S-1, tet blocks + gathers of tiles 0..S-2.  Thread 0 keeps the block
+    // range of the NEXT meta it will issue in registers (loaded an iteration early, never stalls).
+    const bool issuer = WARP_SCOPE ? tid == 0 : tid == NT / 2;  // the thread that issues bulk copies in the loop
     uint32_t nOff = 0, nEnd = 0;
-    if (tid == 0) {
+    if (issuer) {
 #pragma unroll
         for (int i = 0; i < S; i++)
             if (first + i * stride < a.numTiles) issue_meta(a.metaOff[first + i * stride], a.metaOff[first + i * stride + 1], i);
@@ -211,16 +155,16 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
         if (first + S * stride < a.numTiles) { nOff = a.metaOff[first + S * stride]; nEnd = a.metaOff[first + S * stride + 1]; }
     }
 #pragma unroll
-    for (int i = 0; i < S - 1; i++)
+    for (int i = 0; i < S - 1; i++) {
         if (first + i * stride < a.numTiles) { mbar_wait(metaFull + i, 0); issue_gather(i, i); }
+        else cp_async_commit();
+    }
 
-    long long tph[6] = {0, 0, 0, 0, 0, 0};
-    long long tlast = a.trace ? clock64() : 0;
-    auto mark = [&](int ph) { if (a.trace) { long long now = clock64(); tph[ph] += now - tlast; tlast = now; } };
     int k = 0;
     for (int c = first; c < a.numTiles; c += stride, k++) {
-        // ---- this tile's records: issue the loads first, they land while we wait below ----
-        const unsigned char *tb = a.tets + (size_t)c * SM::TET_BYTES;
+        const int cur = k % S, mcur = k % (S + 1);
+        // this tile's records: issue the loads first, they land while we wait and prefetch below
+        const unsigned char *tb = a.tets + (size_t)c * TileSmem<T, S>::TET_BYTES;
         float4 rA[TPT], rB[TPT], rC[TPT];
         uint2 rD[TPT];
 #pragma unroll
@@ -231,17 +175,45 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
             rC[u] = ldg_stream4(tb + T * 32 + t * 16);
             rD[u] = ldg_stream2(tb + T * 48 + t * 8);
         }
-        mbar_wait(gatherDone + k % S, (k / S) & 1);  // every thread's gathers of this tile have landed
-        mark(0);
+        cp_async_wait_pending<S - 2>();
+        sync();  // this tile's gathers (all threads') landed; previous tile's corner sums are finished
+
+        // ---- put tile k+S-1 (vertex gather) and tile k+S (meta) in flight ----
+        // The corner sums further down keep only the first ceil(nl/32) warps busy; the issue work is
+        // therefore handed to the LAST warps of the CTA, which would otherwise idle at the next barrier.
+        auto prefetch_next = [&]() {
+            const int kn = k + S - 1, cn = c + (S - 1) * stride;
+            constexpr int NI = WARP_SCOPE ? NT : NT / 2;      // threads that issue
+            const int it = WARP_SCOPE ? tid : tid - (NT - NI);  // their index, < 0 for the others
+            if (cn < a.numTiles) {
+                const int mslot = kn % (S + 1), buf = kn % S;
+                if (it >= 0) {
+                    mbar_wait(metaFull + mslot, (kn / (S + 1)) & 1);
+                    const unsigned char *m = ws + L.meta(mslot);
+                    const int nl = reinterpret_cast<const int *>(m)[1];
+                    const int *ids = reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3]);
+                    float4 *sx = reinterpret_cast<float4 *>(ws + L.sx(buf));
+                    if (!(a.debugSkip & 4))
+                        for (int j = it; j < nl; j += NI) cp_async16(sx + j, a.x4 + ids[j]);
+                }
+            }
+            cp_async_commit();
+            if (it == 0) {
+                if (c + (PF + 1) * stride < a.numTiles) prefetch_tets(c + (PF + 1) * stride);
+                if (c + S * stride < a.numTiles) {
+                    issue_meta(nOff, nEnd, (k + S) % (S + 1));
+                    if (c + (S + 1) * stride < a.numTiles) { nOff = a.metaOff[c + (S + 1) * stride]; nEnd = a.metaOff[c + (S + 1) * stride + 1]; }
+                }
+            }
+        };
 
         // ---- per-tet solve ----
-        const unsigned char *sxb = ws + L.sx(k % S);
-        unsigned char *const sdx = ws + L.sdx(k & 1);
+        const unsigned char *sxb = ws + L.sx(cur);
         float vsum = 0.0f;
-        float4 d0[TPT], d1[TPT], d2[TPT], d3[TPT];
 #pragma unroll
         for (int u = 0; u < TPT; u++) {
             const float4 A = rA[u], B = rB[u], C = rC[u];
+            const uint2 D = rD[u];
             const unsigned s01 = __float_as_uint(C.z), s23 = __float_as_uint(C.w);
             const float4 q0 = *reinterpret_cast<const float4 *>(sxb + (s01 & 0xffffu));
             const float4 q1 = *reinterpret_cast<const float4 *>(sxb + (s01 >> 16));
@@ -251,66 +223,43 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
             const float w[4] = {q0.w, q1.w, q2.w, q3.w};
             const float Q[9] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w, C.x};
             const float vm1 = (a.debugSkip & 2) ? 0.0f : nh_solve_fast(p, w, Q, C.y, alphaDev, alphaVol, gammaVol);
-            d0[u] = make_float4(p[0].x - q0.x, p[0].y - q0.y, p[0].z - q0.z, 0.f);
-            d1[u] = make_float4(p[1].x - q1.x, p[1].y - q1.y, p[1].z - q1.z, 0.f);
-            d2[u] = make_float4(p[2].x - q2.x, p[2].y - q2.y, p[2].z - q2.z, 0.f);
-            d3[u] = make_float4(p[3].x - q3.x, p[3].y - q3.y, p[3].z - q3.z, 0.f);
+            *reinterpret_cast<float4 *>(sdx + (D.x & 0xffffu)) = make_float4(p[0].x - q0.x, p[0].y - q0.y, p[0].z - q0.z, 0.f);
+            *reinterpret_cast<float4 *>(sdx + (D.x >> 16)) = make_float4(p[1].x - q1.x, p[1].y - q1.y, p[1].z - q1.z, 0.f);
+            *reinterpret_cast<float4 *>(sdx + (D.y & 0xffffu)) = make_float4(p[2].x - q2.x, p[2].y - q2.y, p[2].z - q2.z, 0.f);
+            *reinterpret_cast<float4 *>(sdx + (D.y >> 16)) = make_float4(p[3].x - q3.x, p[3].y - q3.y, p[3].z - q3.z, 0.f);
             vsum += (C.y != 0.0f) ? vm1 : 0.0f;  // padding records carry invRestVolume = 0
         }
-        if (a.trace) { float f = d0[0].x + d1[0].y + d2[0].z + d3[0].x; asm volatile("" ::"f"(f)); }
-        mark(1);
-        // park the corners' dx: this buffer was last read by the corner sums of tile k-2
-        if (k >= 2) mbar_wait(sumDone + (k & 1), ((k >> 1) + 1) & 1);
-#pragma unroll
-        for (int u = 0; u < TPT; u++) {
-            const uint2 D = rD[u];
-            *reinterpret_cast<float4 *>(sdx + (D.x & 0xffffu)) = d0[u];
-            *reinterpret_cast<float4 *>(sdx + (D.x >> 16)) = d1[u];
-            *reinterpret_cast<float4 *>(sdx + (D.y & 0xffffu)) = d2[u];
-            *reinterpret_cast<float4 *>(sdx + (D.y >> 16)) = d3[u];
-        }
-        __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(scatterDone + (k & 1));
         if (a.volAcc) {  // volError (src/Softbody.js:163): warp-reduce, one double atomic per warp
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
             if ((tid & 31) == 0) atomicAdd(a.volAcc, (double)vsum);
         }
+        sync();
+        prefetch_next();
 
-        mark(2);
-        // ---- every warp is done with tile k-1's vertex tile and has parked its dx of tile k-1 ----
-        if (k >= 1) mbar_wait(scatterDone + ((k - 1) & 1), ((k - 1) >> 1) & 1);
-        mark(3);
-        {   // put tile k+S-1 (vertex gather) and tile k+S (meta) in flight; buffers of tile k-1 are free now
-            const int kn = k + S - 1, cn = c + (S - 1) * stride;
-            if (cn < a.numTiles) {
-                const int mslot = kn % (S + 2);
-                mbar_wait(metaFull + mslot, (kn / (S + 2)) & 1);
-                issue_gather(mslot, kn % S);
-            }
-            if (tid == 0) {
-                if (c + (PF + 1) * stride < a.numTiles) prefetch_tets(c + (PF + 1) * stride);
-                if (c + S * stride < a.numTiles) {
-                    issue_meta(nOff, nEnd, (k + S) % (S + 2));  // slot of tile k-2, whose sums finished last iteration
-                    if (c + (S + 1) * stride < a.numTiles) { nOff = a.metaOff[c + (S + 1) * stride]; nEnd = a.metaOff[c + (S + 1) * stride + 1]; }
+        // ---- per-tile-vertex sum of corner dx, ascending (tet, corner) order ----
+        const unsigned char *m = ws + L.meta(mcur);
+        const int v0 = reinterpret_cast<const int *>(m)[0];
+        const int nl = reinterpret_cast<const int *>(m)[1];
+        const uint16_t *scol = reinterpret_cast<const uint16_t *>(m + 16);
+        if (!(a.debugSkip & 1))
+            for (int j = tid; j < nl; j += NT) {
+                const int val = m[a.metaValOff + j];
+                const unsigned char *base = sdx + j * 16;
+                float ax = 0.0f, ay = 0.0f, az = 0.0f;
+#pragma unroll 4
+                for (int i = 0; i < val; i++) {
+                    const float4 d = *reinterpret_cast<const float4 *>(base + scol[i]);
+                    ax += d.x; ay += d.y; az += d.z;
                 }
+                if (a.acc) atomicAdd(a.acc + reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3])[j],
+                                     make_float4(ax, ay, az, 0.0f));
+                else a.part[v0 + j] = make_float4(ax, ay, az, 0.0f);
             }
-        }
-        mark(4);
-        if (k >= 1) sum_corners(k - 1);
-        mark(5);
     }
-    if (a.trace && (tid & 31) == 0) {
-        for (int i = 0; i < 6; i++) atomicAdd(a.trace + i, (unsigned long long)tph[i]);
-        atomicAdd(a.trace + 6, (unsigned long long)k);
-        atomicAdd(a.trace + 7, 1ull);
-    }
-    // drain: corner sums of the last tile
-    mbar_wait(scatterDone + ((k - 1) & 1), ((k - 1) >> 1) & 1);
-    sum_corners(k - 1);
 }
 
-// CTA tiles: T tets per tile, one tet per thread; warps of the CTA hand tiles over through mbarriers.
+// CTA tiles: T tets per tile, one tet per thread, two __syncthreads per tile.
 template <int T, int S, int MINB>
 __global__ void __launch_bounds__(T, MINB) k_jacobi_tiles(TileArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
