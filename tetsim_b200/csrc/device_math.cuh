@@ -195,6 +195,48 @@ __device__ __forceinline__ float nh_solve_fast(V3 p[4], const float w[4], const 
     return vol - 1.0f;
 }
 
+// FAST Neo-Hookean, rest-metric form -- what the throughput (tile) kernel runs.  Same two projections,
+// with the rest inverse Q eliminated algebraically (F = P Q, P = current edge matrix):
+//   deviatoric : C = ||F||,  dC/dP = F Q^T / C = P B / C  with B = Q Q^T (symmetric, 6 floats per tet)
+//                and ||F||^2 = tr(P^T P B) = sum_k P_k . (P B)_k         -> F is never formed
+//   hydrostatic: det F = det P det Q,  d(det F)/dP = det Q cof(P)         -> no Q at all
+// 170 FP instructions per tet instead of 290 (round-1 ncu + ablation: the tile kernel is bound by the
+// FP32 pipe, not by HBM, once the stream is prefetched), and the tet stream shrinks to 7 floats.
+// Algebraically identical to nh_solve_fast; roundings differ at the 1e-7 level.
+__device__ __forceinline__ float nh_solve_fast_metric(V3 p[4], const float w[4], const float Bm[6] /* B00 B01 B02 B11 B12 B22 */,
+                                                      float irv, float detQ, float alphaDev, float alphaVol,
+                                                      float gammaVol) {
+    V3 P0 = p[1] - p[0], P1 = p[2] - p[0], P2 = p[3] - p[0];
+    {
+        V3 G1 = fma3(P2, Bm[2], fma3(P1, Bm[1], P0 * Bm[0]));
+        V3 G2 = fma3(P2, Bm[4], fma3(P1, Bm[3], P0 * Bm[1]));
+        V3 G3 = fma3(P2, Bm[5], fma3(P1, Bm[4], P0 * Bm[2]));
+        float rs2 = dot(P0, G1) + dot(P1, G2) + dot(P2, G3);
+        V3 G0 = {-(G1.x + G2.x + G3.x), -(G1.y + G2.y + G3.y), -(G1.z + G2.z + G3.z)};
+        float wG = fmaf(w[3], dot(G3, G3), fmaf(w[2], dot(G2, G2), fmaf(w[1], dot(G1, G1), w[0] * dot(G0, G0))));
+        float den = fmaf(alphaDev * irv, rs2, wG);
+        float s = (rs2 > 0.0f && wG > 0.0f) ? -__fdividef(rs2, den) : 0.0f;
+        p[0] = fma3(G0, s * w[0], p[0]);
+        p[1] = fma3(G1, s * w[1], p[1]);
+        p[2] = fma3(G2, s * w[2], p[2]);
+        p[3] = fma3(G3, s * w[3], p[3]);
+    }
+    P0 = p[1] - p[0]; P1 = p[2] - p[0]; P2 = p[3] - p[0];
+    V3 c1 = cross(P1, P2), c2 = cross(P2, P0), c3 = cross(P0, P1);
+    float vol = dot(P0, c1) * detQ;
+    V3 c0 = {-(c1.x + c2.x + c3.x), -(c1.y + c2.y + c3.y), -(c1.z + c2.z + c3.z)};
+    float wC = fmaf(w[3], dot(c3, c3), fmaf(w[2], dot(c2, c2), fmaf(w[1], dot(c1, c1), w[0] * dot(c0, c0))));
+    float C = vol - gammaVol;
+    // true gradients are detQ * c_i:  dlambda = -C / (detQ^2 wC + alpha);  step_i = c_i * (detQ * dlambda * w_i)
+    float den = fmaf(detQ * detQ, wC, alphaVol * irv);
+    float s = (C != 0.0f && wC > 0.0f) ? -__fdividef(C * detQ, den) : 0.0f;
+    p[0] = fma3(c0, s * w[0], p[0]);
+    p[1] = fma3(c1, s * w[1], p[1]);
+    p[2] = fma3(c2, s * w[2], p[2]);
+    p[3] = fma3(c3, s * w[3], p[3]);
+    return vol - 1.0f;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Polar-decomposition shape matching (src/SoftbodyGPU.js:80-262), f32.
 // EXACT: every op separately rounded (TU compiled -fmad=false), IEEE div/sqrt, sin via double.

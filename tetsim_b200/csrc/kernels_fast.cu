@@ -62,7 +62,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 template <int T, int S>
 struct TileSmem {
-    static constexpr int TET_BYTES = T * 56;
+    static constexpr int TET_BYTES = T * 48;
     // byte offsets inside the worker's shared-memory region (computed, never indexed: stays in registers)
     int sxBytes, metaStride, sdx, sx0, meta0, bars, total;
     __host__ __device__ TileSmem(int metaStride_, int maxTileVertsPad) {
@@ -166,14 +166,21 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
         // this tile's records: issue the loads first, they land while we wait and prefetch below
         const unsigned char *tb = a.tets + (size_t)c * TileSmem<T, S>::TET_BYTES;
         float4 rA[TPT], rB[TPT], rC[TPT];
-        uint2 rD[TPT];
 #pragma unroll
         for (int u = 0; u < TPT; u++) {
             const int t = tid + NT * u;
+            if (a.debugSkip & 8) {  // measurement only: synthetic record, no HBM stream
+                const float f = 1.0f + 1e-3f * (float)(t & 7);
+                rA[u] = make_float4(f, 0.01f, 0.02f, f); rB[u] = make_float4(0.03f, f, 6.0f, 1.0f);
+                rC[u] = make_float4(__uint_as_float(((t * 16) & 0x3ff) | (((t * 16 + 16) & 0x3ff) << 16)),
+                                    __uint_as_float(((t * 16 + 32) & 0x3ff) | (((t * 16 + 48) & 0x3ff) << 16)),
+                                    __uint_as_float((unsigned)(t * 64) | (unsigned)(t * 64 + 16) << 16),
+                                    __uint_as_float((unsigned)(t * 64 + 32) | (unsigned)(t * 64 + 48) << 16));
+                continue;
+            }
             rA[u] = ldg_stream4(tb + t * 16);
             rB[u] = ldg_stream4(tb + T * 16 + t * 16);
             rC[u] = ldg_stream4(tb + T * 32 + t * 16);
-            rD[u] = ldg_stream2(tb + T * 48 + t * 8);
         }
         cp_async_wait_pending<S - 2>();
         sync();  // this tile's gathers (all threads') landed; previous tile's corner sums are finished
@@ -213,21 +220,22 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
 #pragma unroll
         for (int u = 0; u < TPT; u++) {
             const float4 A = rA[u], B = rB[u], C = rC[u];
-            const uint2 D = rD[u];
-            const unsigned s01 = __float_as_uint(C.z), s23 = __float_as_uint(C.w);
+            const unsigned s01 = __float_as_uint(C.x), s23 = __float_as_uint(C.y);
+            const uint2 D = make_uint2(__float_as_uint(C.z), __float_as_uint(C.w));
             const float4 q0 = *reinterpret_cast<const float4 *>(sxb + (s01 & 0xffffu));
             const float4 q1 = *reinterpret_cast<const float4 *>(sxb + (s01 >> 16));
             const float4 q2 = *reinterpret_cast<const float4 *>(sxb + (s23 & 0xffffu));
             const float4 q3 = *reinterpret_cast<const float4 *>(sxb + (s23 >> 16));
             V3 p[4] = {{q0.x, q0.y, q0.z}, {q1.x, q1.y, q1.z}, {q2.x, q2.y, q2.z}, {q3.x, q3.y, q3.z}};
             const float w[4] = {q0.w, q1.w, q2.w, q3.w};
-            const float Q[9] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w, C.x};
-            const float vm1 = (a.debugSkip & 2) ? 0.0f : nh_solve_fast(p, w, Q, C.y, alphaDev, alphaVol, gammaVol);
+            const float Bm[6] = {A.x, A.y, A.z, A.w, B.x, B.y};
+            const float vm1 = (a.debugSkip & 2) ? 0.0f : nh_solve_fast_metric(p, w, Bm, B.z, B.w, alphaDev, alphaVol, gammaVol);
+            if ((a.debugSkip & 16) && p[0].x + p[1].y + p[2].z + p[3].x != 123.456f) continue;  // measurement only: no scatter
             *reinterpret_cast<float4 *>(sdx + (D.x & 0xffffu)) = make_float4(p[0].x - q0.x, p[0].y - q0.y, p[0].z - q0.z, 0.f);
             *reinterpret_cast<float4 *>(sdx + (D.x >> 16)) = make_float4(p[1].x - q1.x, p[1].y - q1.y, p[1].z - q1.z, 0.f);
             *reinterpret_cast<float4 *>(sdx + (D.y & 0xffffu)) = make_float4(p[2].x - q2.x, p[2].y - q2.y, p[2].z - q2.z, 0.f);
             *reinterpret_cast<float4 *>(sdx + (D.y >> 16)) = make_float4(p[3].x - q3.x, p[3].y - q3.y, p[3].z - q3.z, 0.f);
-            vsum += (C.y != 0.0f) ? vm1 : 0.0f;  // padding records carry invRestVolume = 0
+            vsum += (B.z != 0.0f) ? vm1 : 0.0f;  // padding records carry invRestVolume = 0
         }
         if (a.volAcc) {  // volError (src/Softbody.js:163): warp-reduce, one double atomic per warp
 #pragma unroll
@@ -363,22 +371,24 @@ __global__ void k_build_tiles(int numRecords, const int *__restrict__ order, con
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= numRecords) return;
     const int tile = r / T, t = r % T;
-    unsigned char *tb = tets + (size_t)tile * T * 56;
+    unsigned char *tb = tets + (size_t)tile * T * 48;
     const int e = order[r];
     const uint4 x = aux[r];
-    float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A;
-    float q8 = 0.f, rv = 0.f;
+    float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A;  // padding record: B = 0, invRestVolume = 0 -> no correction
     if (e >= 0) {
+        // rest metric B = Q Q^T (Q column-major: Q(i,k) = q[3k+i]), formed in f64 and rounded once
         const float *q = Q9 + 9 * (size_t)e;
-        A = make_float4(q[0], q[1], q[2], q[3]);
-        B = make_float4(q[4], q[5], q[6], q[7]);
-        q8 = q[8];
-        rv = irv[e];
+        double b[3][3];
+        for (int i = 0; i < 3; i++)
+            for (int j = i; j < 3; j++)
+                b[i][j] = (double)q[i] * (double)q[j] + (double)q[3 + i] * (double)q[3 + j] + (double)q[6 + i] * (double)q[6 + j];
+        const float rv = irv[e];
+        A = make_float4((float)b[0][0], (float)b[0][1], (float)b[0][2], (float)b[1][1]);
+        B = make_float4((float)b[1][2], (float)b[2][2], rv, rv / 6.0f);  // det Q = 1 / det Dm = invRestVolume / 6
     }
     reinterpret_cast<float4 *>(tb)[t] = A;
     reinterpret_cast<float4 *>(tb + T * 16)[t] = B;
-    reinterpret_cast<float4 *>(tb + T * 32)[t] = make_float4(q8, rv, __uint_as_float(x.x), __uint_as_float(x.y));
-    reinterpret_cast<uint2 *>(tb + T * 48)[t] = make_uint2(x.z, x.w);
+    reinterpret_cast<uint4 *>(tb + T * 32)[t] = x;
 }
 void launch_build_tiles(cudaStream_t s, int clusterSize, int numRecords, const int *order, const float *Q9,
                         const float *irv, const uint4 *aux, unsigned char *tets) {

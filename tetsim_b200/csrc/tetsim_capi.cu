@@ -347,7 +347,7 @@ int build_jacobi_cluster(tetsim *h, const std::vector<float> &verts, const std::
         DevBuf<uint4> aux;
         CK(aux.alloc(nRec));
         if (nRec) CK(cudaMemcpyAsync(aux.p, P.recordAux.data(), nRec * sizeof(uint4), cudaMemcpyHostToDevice, s));
-        CK(h->tileTets.alloc(nRec * 56));
+        CK(h->tileTets.alloc(nRec * 48));
         launch_build_tiles(s, P.T, (int)nRec, h->order.p, h->Q9.p, h->irv.p, aux.p, h->tileTets.p);
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(s));
