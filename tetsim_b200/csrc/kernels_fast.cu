@@ -10,16 +10,21 @@ const KernelTable *fast_kernels() { return Launchers<false>::table(); }
 // Clustered Jacobi Neo-Hookean -- the throughput kernel (BASELINE config 4).
 //
 // Persistent CTAs (grid = SMs x resident CTAs), each walking tiles c = blockIdx.x, + gridDim.x, ...
-// One tile = T consecutive tets of the (Morton-sorted) tet stream, one tet per thread.  Everything a
-// tile needs is staged in shared memory by ASYNCHRONOUS copies issued one tile ahead, so the math of
-// tile k overlaps the HBM/L2 latency of tile k+1 (round-1 ncu: the non-pipelined version sat at 35 %
-// issue utilisation with long-scoreboard and barrier stalls on top):
-//   * tet block (T*56 B contiguous: Q 36 B, invRestVolume 4 B, 4 vertex slots 8 B, 4 scatter
-//     destinations 8 B per tet, as planes) -> ONE cp.async.bulk (TMA, UBLKCP) on an mbarrier;
-//   * meta block (tile vertex ids, valences, diagonal offsets) -> ONE cp.async.bulk, two tiles ahead;
+// One tile = up to T consecutive tets of the Hilbert-sorted tet stream (closed early if it would touch
+// more than a capped number of vertices), one tet per thread.  HBM layout per tile:
+//   tet block  T*48 B: planes A[T] float4 (B00,B01,B02,B11), B[T] float4 (B12,B22,invRestVolume,detQ),
+//              C[T] uint4 (4 vertex slots, 4 scatter destinations as 16-bit byte offsets); B = Q Q^T is
+//              the rest metric (see nh_solve_fast_metric) -- 28 B of physics + 16 B of indices per tet;
+//   meta block (variable size): tile vertex ids, tile valences, jagged-diagonal offsets.
+// Data movement, all asynchronous and issued ahead of use:
+//   * tet block: one cp.async.bulk.prefetch.L2 per tile two tiles ahead, then three coalesced
+//     LDG.128 per thread straight into registers (staging the stream in shared memory would spend
+//     two passes of the 128 B/clk shared-memory pipe, which gather + scatter already load to 60 %);
+//   * meta block: ONE cp.async.bulk (TMA, UBLKCP) on an mbarrier, S tiles ahead;
 //   * the tile's vertex records float4(x,y,z,invMass): indexed gather with cp.async 16 B (LDGSTS),
-//     straight from L2/HBM into shared memory, no register staging.
-// Per tile:  gather 4 corners (LDS.128) -> both Neo-Hookean projections in registers (device_math.cuh)
+//     L2 -> shared memory without register staging, S-1 tiles ahead, issued by the warps that have
+//     no corner sums to do.
+// Per tile:  gather 4 corners (LDS.128) -> both Neo-Hookean projections in registers
 //   -> each corner's dx is stored (STS.128) at its precomputed slot of a jagged-diagonal buffer
 //   (entry (i, j) = i-th corner of tile vertex j; vertices sorted by descending tile valence)
 //   -> barrier -> thread j sums entries (0..val_j, j): consecutive lanes read consecutive 16-B
@@ -29,7 +34,10 @@ const KernelTable *fast_kernels() { return Launchers<false>::table(); }
 // default flush, no global atomics either: the vertex kernel adds the ~3 tile partials of a vertex in a
 // fixed order -> results are bit-reproducible run to run.  (deterministic = 0 flushes with one
 // REDG.E.ADD.F32x4 per tile vertex instead.)
-// Algorithmic traffic per launch: 56 B/tet + 32 B/vertex.
+// Algorithmic traffic per launch: 56 B/tet + 32 B/vertex; the kernel's own
+// DRAM traffic is lower on the tet stream (48 B) and adds ~3 B/tet of metadata and the partial sums.
+// Round-1 measurements: HBM is NOT the binding limit once the stream is prefetched; FP32
+// issue + shared-memory wavefronts are (math-only ablation 0.13 ms of 0.20 ms per 10M-tet launch).
 // =================================================================================================
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *b, uint32_t count) {
@@ -272,6 +280,12 @@ template <int T, int S, int MINB>
 __global__ void __launch_bounds__(T, MINB) k_jacobi_tiles(TileArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     if ((int)blockIdx.x >= a.numTiles) return;
+    if (a.staggerNs > 0) {  // co-resident CTAs are identical and would otherwise run their phases in lockstep
+        int sms;
+        asm("mov.u32 %0, %%nsmid;" : "=r"(sms));
+        const unsigned slot = blockIdx.x / (unsigned)sms;
+        if (slot) __nanosleep(slot * (unsigned)a.staggerNs);
+    }
     tile_worker<T, 1, S, false>(a, smem, threadIdx.x, blockIdx.x, gridDim.x);
 }
 

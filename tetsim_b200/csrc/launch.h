@@ -61,7 +61,7 @@ struct TileArgs {
     float4 *acc;                    // global accumulator (atomic flush), or NULL
     double *volAcc;                 // sum over tets of det F - 1, or NULL
     const SubstepParams *sp;
-    unsigned long long *trace;      // measurement only: per-phase cycle totals (8 slots) or NULL
+    int staggerNs;                  // initial delay per resident-CTA slot (breaks phase lockstep of co-resident CTAs)
     int debugSkip;                  // measurement only (tetsim_time_kernel + TETSIM_TILE_DEBUG): 1 no vertex phase, 2 no math, 4 no gather
 };
 void launch_jacobi_tiles(cudaStream_t, int clusterSize, const TileArgs &a);

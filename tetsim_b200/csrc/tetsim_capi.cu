@@ -394,6 +394,8 @@ TileArgs tile_args(const tetsim *h) {
     a.metaOff = h->metaOff.p; a.metaStride = P.metaStride; a.metaValOff = P.metaValOff;
     a.colStride = P.colStride; a.maxTileVertsPad = P.maxTileVertsPad;
     a.part = h->part.p; a.acc = nullptr; a.volAcc = nullptr; a.sp = h->sp.p;
+    a.staggerNs = 0;
+    if (const char *e = getenv("TETSIM_TILE_STAGGER_NS")) a.staggerNs = atoi(e);
     return a;
 }
 
@@ -954,21 +956,6 @@ int tetsim_time_kernel(tetsim_t *h, int32_t reps, double *msPerLaunch, int64_t *
     scratch.release();
     CK(cudaGetLastError());
     *msPerLaunch = (double)ms / reps;
-    if (getenv("TETSIM_TILE_TRACE")) {  // per-phase cycle totals of one extra launch (debug aid)
-        DevBuf<unsigned long long> tr;
-        CK(tr.alloc(8));
-        CK(cudaMemsetAsync(tr.p, 0, 64, s));
-        ca.trace = tr.p;
-        launch_jacobi_tiles(s, P.T, ca);
-        unsigned long long hv[8];
-        CK(cudaMemcpyAsync(hv, tr.p, 64, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        const double w = (double)hv[6] > 0 ? (double)hv[6] : 1.0;  // warp-tiles
-        fprintf(stderr, "[tile trace] warps %llu, tiles/warp %.1f; cycles per tile per warp: wait-gather %.0f, math(+records) %.0f, "
-                        "park dx %.0f, wait others' math %.0f, issue prefetch %.0f, corner sums %.0f\n",
-                hv[7], w / (double)hv[7], hv[0] / w, hv[1] / w, hv[2] / w, hv[3] / w, hv[4] / w, hv[5] / w);
-        tr.release();
-    }
     // 56 B per tet + 32 B per vertex per launch
     if (algorithmicBytes) *algorithmicBytes = 56ll * P.localTets + 32ll * h->nInt;
     return TETSIM_OK;
