@@ -38,15 +38,20 @@ for r in rows[2:]:
         print("    %-40s %.3f" % (h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")], v))
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 srows = list(csv.reader(io.StringIO(src)))
-start = next(i for i, r in enumerate(srows) if r and r[0] == "Address")
-sh = srows[start]
-ix = {h: i for i, h in enumerate(sh)}
-body = [r for r in srows[start + 1:] if len(r) == len(sh)]
-tot = sum(int(r[ix["# Samples"]]) for r in body) or 1
-warps = max(int(r[ix["Instructions Executed"]]) for r in body)
-print("== source page: %d SASS lines, %d stall samples, %.1f instructions per warp" % (
-    len(body), tot, sum(int(r[ix["Instructions Executed"]]) for r in body) / warps))
-print("  hottest lines (line, samples %, executed, shared N-way conflicts, SASS):")
-for n, r in sorted(enumerate(body), key=lambda x: -int(x[1][ix["# Samples"]]))[:top]:
-    print("    %4d %5.1f%% %9s %6s  %s" % (n, 100.0 * int(r[ix["# Samples"]]) / tot, r[ix["Instructions Executed"]],
-                                         r[ix["L1 Conflicts Shared N-Way"]], r[ix["Source"]].strip()[:90]))
+starts = [i for i, r in enumerate(srows) if r and r[0] == "Address"]
+for si, start in enumerate(starts):
+    end = starts[si + 1] - 1 if si + 1 < len(starts) else len(srows)
+    name = srows[start - 1][1] if start > 0 and len(srows[start - 1]) > 1 else "?"
+    sh = srows[start]
+    ix = {h: i for i, h in enumerate(sh)}
+    body = [r for r in srows[start + 1:end] if len(r) == len(sh) and r[0] != "Address"]
+    if not body:
+        continue
+    tot = sum(int(r[ix["# Samples"]]) for r in body) or 1
+    warps = max(int(r[ix["Instructions Executed"]]) for r in body) or 1
+    print("== source page of %s: %d SASS lines, %d stall samples, %.1f instructions per warp" % (
+        name, len(body), tot, sum(int(r[ix["Instructions Executed"]]) for r in body) / warps))
+    print("  hottest lines (line, samples %, executed, shared N-way conflicts, SASS):")
+    for n, r in sorted(enumerate(body), key=lambda x: -int(x[1][ix["# Samples"]]))[:top]:
+        print("    %4d %5.1f%% %9s %6s  %s" % (n, 100.0 * int(r[ix["# Samples"]]) / tot, r[ix["Instructions Executed"]],
+                                             r[ix["L1 Conflicts Shared N-Way"]], r[ix["Source"]].strip()[:90]))
