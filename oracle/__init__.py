@@ -149,6 +149,17 @@ class SoftBodyOracle:
             _p(self.grabPos, C.c_float), C.byref(ve))
         self.volError = ve.value
 
+    def jacobi_accumulate(self, tet_list, dt: float) -> np.ndarray:
+        """dx sums (3 per vertex) contributed by the tets in ``tet_list`` from the current positions."""
+        tl = _i32(tet_list)
+        acc = np.zeros(3 * self.numParticles, np.float32)
+        p = self._cparams(None)
+        lib().oracle_jacobi_accumulate(
+            tl.size, _p(tl, C.c_int), _p(self.pos, C.c_float), _p(self.invMass, C.c_float),
+            _p(self.invRestPose, C.c_float), _p(self.invRestVolume, C.c_float), _p(self.tetIds, C.c_int),
+            _p(acc, C.c_float), C.c_double(dt), C.byref(p))
+        return acc
+
     # grab API, src/Softbody.js:279-298
     def startGrab(self, pos):
         p = np.asarray(pos, np.float64)

@@ -300,6 +300,31 @@ void oracle_simulate_jacobi(int numVerts, int numTets, float *pos, float *prev, 
     post(numVerts, pos, prev, vel, p, dt, grabId, grabPos);
 }
 
+/* The tet half of one Jacobi iteration on a SUBSET of the tets (tetList, numList entries): adds each
+ * corner's dx into acc (3 floats per vertex, caller-zeroed).  Used by the multi-process tests to
+ * restate what one rank of a tet-partitioned run contributes before the boundary all-reduce. */
+void oracle_jacobi_accumulate(int numList, const int *tetList, const float *pos, const float *invMass,
+                              const float *invRestPose, const float *invRestVolume, const int *tetIds, float *acc,
+                              double dt, const OracleParams *p) {
+    Scratch s;
+    static const int loc[4] = {0, 1, 2, 3};
+    for (int n = 0; n < numList; n++) {
+        const int e = tetList[n];
+        const int *ids = tetIds + 4 * (size_t)e;
+        float y[12], w4[4];
+        for (int k = 0; k < 4; k++) {
+            y[3 * k] = pos[3 * ids[k]]; y[3 * k + 1] = pos[3 * ids[k] + 1]; y[3 * k + 2] = pos[3 * ids[k] + 2];
+            w4[k] = invMass[ids[k]];
+        }
+        solve_elem(&s, y, loc, w4, invRestPose, e, invRestVolume[e], dt, p->devCompliance, p->volCompliance);
+        for (int k = 0; k < 4; k++)
+            for (int c = 0; c < 3; c++) {
+                float dx = st((double)y[3 * k + c] - (double)pos[3 * ids[k] + c]);
+                acc[3 * ids[k] + c] = acc[3 * ids[k] + c] + dx;
+            }
+    }
+}
+
 /* SoftBody.updateVisMesh without the normals: barycentric skinning.  src/Softbody.js:259-273.
  * visVerts = (tetNr, b0, b1, b2) per vertex, b3 = 1 - b0 - b1 - b2 evaluated in f64. */
 void oracle_skin(int numVis, const float *visVerts, const int *tetIds, const float *pos, float *out) {

@@ -1,0 +1,93 @@
+"""World-size-2 tests of the multi-GPU HOST logic on CPU (gloo): the tet partition every rank derives
+independently must be consistent across ranks, and the exchange it implies -- each rank sums the dx of
+its own tets, the shared-boundary sums are all-reduced, every rank applies the reduced value -- must
+reproduce the single-process Jacobi iteration.  The per-tet arithmetic is the oracle's (this is test
+infrastructure on CPU; the GPU version of the same check is tools/multigpu_check.py)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, cluster_size, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    from tetsim_b200 import _capi, mesh
+    v, t = mesh.make_beam((24, 6, 5), h=0.05, y0=0.5, jitter=0.2)
+    N, M = v.size // 3, t.size // 4
+    plan = _capi.plan_partition(v, t, cluster_size, True, rank, world)
+    l2c, nI, nB = plan["localToCaller"], plan["numInterior"], plan["numBoundary"]
+    # ---- consistency of independently derived plans ----
+    counts = torch.tensor([len(plan["localTets"]), nI, nB], dtype=torch.int64)
+    allc = [torch.zeros_like(counts) for _ in range(world)]
+    dist.all_gather(allc, counts)
+    assert sum(int(c[0]) for c in allc) == M, "tets are not partitioned exactly"
+    assert len({int(c[2]) for c in allc}) == 1, "ranks disagree on the boundary set size"
+    bset = torch.from_numpy(l2c[nI:].astype(np.int64))
+    allb = [torch.zeros_like(bset) for _ in range(world)]
+    dist.all_gather(allb, bset)
+    assert all(torch.equal(allb[0], b) for b in allb), "boundary sets differ or are ordered differently"
+    own = torch.zeros(M, dtype=torch.int32)
+    own[torch.from_numpy(plan["localTets"].astype(np.int64))] = 1
+    dist.all_reduce(own)
+    assert int(own.min()) == 1 and int(own.max()) == 1, "a tet is owned by zero or two ranks"
+    tets = t.reshape(-1, 4)
+    touched = np.unique(tets[plan["localTets"]])
+    assert set(touched) <= set(l2c.tolist()), "a local tet references a non-resident vertex"
+    interior = torch.zeros(N, dtype=torch.int32)
+    interior[torch.from_numpy(l2c[:nI].astype(np.int64))] = 1
+    dist.all_reduce(interior)
+    assert int(interior.max()) <= 1, "an interior vertex is resident on two ranks"
+    # ---- the exchange: local sums + all-reduce of the boundary == the single-process iteration ----
+    dt = 1.0 / 1200.0
+    body = oracle.SoftBodyOracle(v, t)
+    body.pos[1::3] -= np.float32(0.01) * np.arange(N, dtype=np.float32) / N   # some deformation
+    acc = body.jacobi_accumulate(plan["localTets"], dt).reshape(N, 3)
+    b = torch.from_numpy(acc[l2c[nI:]].copy())
+    dist.all_reduce(b)                                     # what ncclAllReduce does on the GPU path
+    merged = np.full((N, 3), np.nan, np.float32)
+    merged[l2c[:nI]] = acc[l2c[:nI]]
+    merged[l2c[nI:]] = b.numpy()
+    full = body.jacobi_accumulate(np.arange(M, dtype=np.int32), dt).reshape(N, 3)
+    res = ~np.isnan(merged[:, 0])
+    scale = np.abs(full).max()
+    assert np.max(np.abs(merged[res] - full[res])) <= 2e-6 * scale
+    # every vertex is resident somewhere
+    r = torch.from_numpy(res.astype(np.int32))
+    dist.all_reduce(r)
+    assert int(r.min()) >= 1
+    out.put((rank, nI, nB))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("cluster_size", [64, 256])
+def test_partition_and_exchange_world2(cluster_size):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, cluster_size, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    got = sorted(q.get(timeout=5) for _ in range(2))
+    assert got[0][2] == got[1][2] > 0
