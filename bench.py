@@ -246,7 +246,7 @@ def main():
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("k_jacobi_cluster_dram_bytes_per_launch")
+            traffic = json.load(open(tp)).get("k_jacobi_cluster_dram_bytes_per_launch") if world == 1 else None
         except Exception:
             traffic = None
     roofline = {"kernel": "k_jacobi_tiles<%d> (persistent tile kernel, tetsim_b200/csrc/kernels_fast.cu)" % args.cluster_size, "bound": "hbm", "achieved": achieved,
@@ -306,7 +306,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "tets": M, "verts": N, "iters": args.iters, "substeps_per_step": args.substeps,
                        "cluster_size": info["clusterSize"], "clusters_rank0": info["numClusters"],
-                       "boundary_verts": info["boundaryVerts"], "deterministic": not args.atomic,
+                       "boundary_verts": info["boundaryVerts"], "boundary_tiles_rank0": info["boundaryTiles"], "deterministic": not args.atomic,
                        "parallelism": "tet-partition x%d, ncclAllReduce of boundary dx per iteration" % world if world > 1 else "single GPU",
                        "l2": "working set per substep (%.0f MB) exceeds the 126 MB L2; no flush needed" % ((56.0 * M + 144.0 * N) / 1e6)},
             "scalar_constraints_per_s_M": 2 * value,

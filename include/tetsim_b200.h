@@ -120,7 +120,7 @@ typedef struct TetSimInfo {
     int64_t kernelLaunches;   /* kernels launched by simulate/step since create (graph replays count) */
     int64_t tileMetaBytes;    /* Jacobi: bytes of per-tile metadata streamed per launch               */
     int32_t maxTileVerts;     /* Jacobi: largest tile vertex count                                    */
-    int32_t reserved_;
+    int32_t boundaryTiles;    /* Jacobi multi-GPU: tiles touching rank-shared vertices (run first)     */
 } TetSimInfo;
 
 typedef struct tetsim tetsim_t;

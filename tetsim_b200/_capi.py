@@ -77,7 +77,7 @@ class TetSimInfo(C.Structure):
         ("localTets", C.c_int32), ("localVerts", C.c_int32), ("boundaryVerts", C.c_int32),
         ("maxValence", C.c_int32), ("launchesPerSubstep", C.c_int32),
         ("deviceBytes", C.c_int64), ("sumLocalVerts", C.c_int64), ("kernelLaunches", C.c_int64),
-        ("tileMetaBytes", C.c_int64), ("maxTileVerts", C.c_int32), ("reserved_", C.c_int32),
+        ("tileMetaBytes", C.c_int64), ("maxTileVerts", C.c_int32), ("boundaryTiles", C.c_int32),
     ]
 
     def as_dict(self):

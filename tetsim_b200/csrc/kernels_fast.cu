@@ -279,14 +279,14 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
 template <int T, int S, int MINB>
 __global__ void __launch_bounds__(T, MINB) k_jacobi_tiles(TileArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    if ((int)blockIdx.x >= a.numTiles) return;
+    if (a.tileBegin + (int)blockIdx.x >= a.numTiles) return;
     if (a.staggerNs > 0) {  // co-resident CTAs are identical and would otherwise run their phases in lockstep
         int sms;
         asm("mov.u32 %0, %%nsmid;" : "=r"(sms));
         const unsigned slot = blockIdx.x / (unsigned)sms;
         if (slot) __nanosleep(slot * (unsigned)a.staggerNs);
     }
-    tile_worker<T, 1, S, false>(a, smem, threadIdx.x, blockIdx.x, gridDim.x);
+    tile_worker<T, 1, S, false>(a, smem, threadIdx.x, a.tileBegin + blockIdx.x, gridDim.x);
 }
 
 // Warp tiles: every warp is its own worker with private staging and mbarriers (tile = 32 * TPL tets);
@@ -295,7 +295,7 @@ template <int TPL, int S>
 __global__ void __launch_bounds__(TPL == 1 ? 832 : 448, 1) k_jacobi_warptiles(TileArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const int first = blockIdx.x * wpb + wid;
+    const int first = a.tileBegin + blockIdx.x * wpb + wid;
     if (first >= a.numTiles) return;
     const TileSmem<32 * TPL, S> L(a.metaStride, a.maxTileVertsPad);
     tile_worker<32, TPL, S, true>(a, smem + (size_t)wid * L.total, lane, first, gridDim.x * wpb);
@@ -333,7 +333,7 @@ static void launch_tiles_T(cudaStream_t s, const TileArgs &a) {
         lc.smem = smem;
     }
     int grid = lc.sms * lc.n;  // persistent: every CTA resident, tiles strided over the grid
-    if (grid > a.numTiles) grid = a.numTiles;
+    if (grid > a.numTiles - a.tileBegin) grid = a.numTiles - a.tileBegin;
     k_jacobi_tiles<T, S, MINB><<<grid, T, smem, s>>>(a);
 }
 
@@ -360,12 +360,12 @@ static void launch_warptiles(cudaStream_t s, const TileArgs &a) {
         lc.smem = perWarp;
     }
     int grid = lc.sms;
-    if ((long long)grid * lc.n > a.numTiles) grid = (a.numTiles + lc.n - 1) / lc.n;
+    if ((long long)grid * lc.n > a.numTiles - a.tileBegin) grid = (a.numTiles - a.tileBegin + lc.n - 1) / lc.n;
     k_jacobi_warptiles<TPL, S><<<grid, 32 * lc.n, perWarp * lc.n, s>>>(a);
 }
 
 void launch_jacobi_tiles(cudaStream_t s, int clusterSize, const TileArgs &a) {
-    if (a.numTiles <= 0) return;
+    if (a.numTiles - a.tileBegin <= 0) return;
     const int S = tile_stages(clusterSize);
     switch (clusterSize) {
         case 32: S == 2 ? launch_warptiles<1, 2>(s, a) : (S == 3 ? launch_warptiles<1, 3>(s, a) : launch_warptiles<1, 4>(s, a)); break;

@@ -55,7 +55,7 @@ struct TileArgs {
     const unsigned char *tets;      // [numTiles * T * 56]
     const unsigned char *meta;      // variable-size blocks, block c at 16 * metaOff[c]
     const uint32_t *metaOff;        // [numTiles + 1]
-    int numTiles;
+    int tileBegin, numTiles;        // this launch walks tiles [tileBegin, numTiles)
     int metaStride, metaValOff, colStride, maxTileVertsPad;  // metaStride = largest block
     float4 *part;                   // per-tile partial dx sums (deterministic flush)
     float4 *acc;                    // global accumulator (atomic flush), or NULL

@@ -234,15 +234,31 @@ bool build_cluster_plan(int numVerts, int numTets, const int *tetIds, const std:
         for (int v = 0; v < numVerts; v++)
             if (rmax[v] > rmin[v]) boundary.push_back(v);
     P.numBoundary = (int)boundary.size();
-    const int posBegin = tileStart[c0], posEnd = tileStart[c1];
-    P.localTets = std::max(0, posEnd - posBegin);
+    P.localTets = std::max(0, tileStart[c1] - tileStart[c0]);
     for (int v : boundary) local[v] = -2;
-    int nI = 0;
-    for (int pos = posBegin; pos < posEnd; pos++) {
-        const int *t = tetIds + 4 * (size_t)order[pos];
-        for (int k = 0; k < 4; k++)
-            if (local[t[k]] == -1) { local[t[k]] = nI++; P.localToCaller.push_back(t[k]); }
+    // Tiles that touch a rank-shared vertex go FIRST: a multi-GPU handle launches them alone, starts
+    // the all-reduce of the boundary sums, and hides it behind the remaining (interior) tiles.
+    std::vector<int> tileOrder;  // local tile c -> global tile index
+    {
+        std::vector<int> inner;
+        for (int g = c0; g < c1; g++) {
+            bool touches = false;
+            for (int pos = tileStart[g]; pos < tileStart[g + 1] && !touches; pos++) {
+                const int *t = tetIds + 4 * (size_t)order[pos];
+                touches = local[t[0]] == -2 || local[t[1]] == -2 || local[t[2]] == -2 || local[t[3]] == -2;
+            }
+            (touches ? tileOrder : inner).push_back(g);
+        }
+        P.numBoundaryTiles = (int)tileOrder.size();
+        tileOrder.insert(tileOrder.end(), inner.begin(), inner.end());
     }
+    int nI = 0;
+    for (int g : tileOrder)
+        for (int pos = tileStart[g]; pos < tileStart[g + 1]; pos++) {
+            const int *t = tetIds + 4 * (size_t)order[pos];
+            for (int k = 0; k < 4; k++)
+                if (local[t[k]] == -1) { local[t[k]] = nI++; P.localToCaller.push_back(t[k]); }
+        }
     // vertices no tet references still fall and collide in the reference (src/Softbody.js:198-202 has
     // no valence test): keep them resident (rank 0 of a multi-GPU job), with no correction to apply
     if (rank == 0)
@@ -269,7 +285,7 @@ bool build_cluster_plan(int numVerts, int numTets, const int *tetIds, const std:
     std::vector<int> cornerRank;  // per corner of the tile: its index i in its vertex's list
     int maxTileVal = 0;
     for (int c = 0; c < P.numClusters; c++) {
-        const int pb = tileStart[c0 + c], pe = tileStart[c0 + c + 1];
+        const int pb = tileStart[tileOrder[c]], pe = tileStart[tileOrder[c] + 1];
         tileVerts.clear(); tileVal.clear();
         cornerRank.assign(4 * (size_t)T, 0);
         for (int pos = pb; pos < pe; pos++) {

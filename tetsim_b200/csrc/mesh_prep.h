@@ -40,6 +40,7 @@ std::vector<int> morton_order(int numVerts, int numTets, const float *verts, con
 struct ClusterPlan {
     int T = 0;                          // tets per tile
     int numClusters = 0;                // tiles on this rank
+    int numBoundaryTiles = 0;           // the first numBoundaryTiles tiles touch rank-shared vertices
     int numLocalVerts = 0;              // interior + all boundary vertices
     int numInterior = 0;
     int numBoundary = 0;                // global count of rank-shared vertices (same on every rank)

@@ -163,6 +163,8 @@ struct tetsim {
     int launchesPerSubstep = 0;
     // multi-GPU
     NcclComm comm = nullptr;
+    cudaStream_t commStream = nullptr;      // the all-reduce runs here, beside the interior tiles
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
     int maxValence = 0;
 
     int64_t deviceBytes() const {
@@ -390,7 +392,7 @@ int build_polar(tetsim *h, const std::vector<int> &tetIds) {
 TileArgs tile_args(const tetsim *h) {
     const ClusterPlan &P = h->plan;
     TileArgs a{};
-    a.x4 = h->x4.p; a.tets = h->tileTets.p; a.meta = h->tileMeta.p; a.numTiles = P.numClusters;
+    a.x4 = h->x4.p; a.tets = h->tileTets.p; a.meta = h->tileMeta.p; a.tileBegin = 0; a.numTiles = P.numClusters;
     a.metaOff = h->metaOff.p; a.metaStride = P.metaStride; a.metaValOff = P.metaValOff;
     a.colStride = P.colStride; a.maxTileVertsPad = P.maxTileVertsPad;
     a.part = h->part.p; a.acc = nullptr; a.volAcc = nullptr; a.sp = h->sp.p;
@@ -446,22 +448,36 @@ int enqueue_substeps(tetsim *h, int count) {
                     const bool multi = h->opt.worldSize > 1 && P.numBoundary > 0;
                     for (int it = 0; it < h->opt.iters; it++) {
                         if (h->trackVol) CK(cudaMemsetAsync(h->volTerm.p, 0, sizeof(double), s));
-                        launch_jacobi_tiles(s, P.T, ca);
-                        h->enq += 2;  // tile kernel + vertex kernel
                         const bool last = it == h->opt.iters - 1;
                         const int mode = !last ? 0 : (step + 1 < count ? 2 : 1);
-                        if (multi) {
-                            // boundary dx: pack this rank's sums, all-reduce over NVLink, then apply everywhere
+                        if (!multi) {
+                            launch_jacobi_tiles(s, P.T, ca);
+                            h->enq += 2;  // tile kernel + vertex kernel
+                        } else {
+                            // 1. the tiles that touch rank-shared vertices, then this rank's boundary sums
+                            TileArgs cb = ca;
+                            cb.numTiles = P.numBoundaryTiles;
+                            launch_jacobi_tiles(s, P.T, cb);
                             if (h->acc.p) {
                                 CK(cudaMemcpyAsync(h->bsum.p, h->acc.p + P.numInterior, h->bsum.bytes(), cudaMemcpyDeviceToDevice, s));
                                 CK(cudaMemsetAsync(h->acc.p + P.numInterior, 0, h->bsum.bytes(), s));
                             } else {
-                                h->enq++;
                                 launch_boundary_pack(s, P.numInterior, P.numBoundary, h->vpStart.p, h->vpSlot.p, h->part.p, h->bsum.p);
+                                h->enq++;
                             }
-                            int rc = g_nccl.AllReduce(h->bsum.p, h->bsum.p, (size_t)P.numBoundary * 4, kNcclFloat, kNcclSum, h->comm, s);
+                            // 2. all-reduce over NVLink on the side stream ...
+                            CK(cudaEventRecord(h->evFork, s));
+                            CK(cudaStreamWaitEvent(h->commStream, h->evFork, 0));
+                            int rc = g_nccl.AllReduce(h->bsum.p, h->bsum.p, (size_t)P.numBoundary * 4, kNcclFloat, kNcclSum, h->comm, h->commStream);
                             if (rc != 0) return fail(TETSIM_E_NCCL, std::string("ncclAllReduce: ") + g_nccl.GetErrorString(rc));
+                            CK(cudaEventRecord(h->evJoin, h->commStream));
+                            // 3. ... while the interior tiles run on the main stream
+                            TileArgs ci = ca;
+                            ci.tileBegin = P.numBoundaryTiles;
+                            launch_jacobi_tiles(s, P.T, ci);
+                            CK(cudaStreamWaitEvent(s, h->evJoin, 0));
                             aa.bsum = h->bsum.p;
+                            h->enq += 2 + (P.numBoundaryTiles > 0 && P.numBoundaryTiles < P.numClusters ? 1 : 0);
                         }
                         launch_jacobi_apply(s, 0, h->nInt, mode, aa);
                     }
@@ -674,6 +690,9 @@ int tetsim_create(const float *verts, int32_t numVerts, const int32_t *tetIds, i
                 memcpy(&id, opt.ncclUniqueId, sizeof(id));
                 int nrc = g_nccl.CommInitRank(&h->comm, opt.worldSize, id, opt.rank);
                 if (nrc != 0) return fail(TETSIM_E_NCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(nrc));
+                CK(cudaStreamCreateWithFlags(&h->commStream, cudaStreamNonBlocking));
+                CK(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming));
             }
             rc = build_jacobi_cluster(h, hv, ht);
         }
@@ -733,6 +752,9 @@ void tetsim_destroy(tetsim_t *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second);
     if (h->comm) g_nccl.CommDestroy(h->comm);
+    if (h->evFork) cudaEventDestroy(h->evFork);
+    if (h->evJoin) cudaEventDestroy(h->evJoin);
+    if (h->commStream) cudaStreamDestroy(h->commStream);
     DevBuf<float4> *f4[] = {&h->x4, &h->prev4, &h->vel4, &h->A, &h->B, &h->C, &h->dx, &h->part, &h->acc, &h->bsum, &h->rest, &h->quat, &h->visV};
     for (auto *b : f4) b->release();
     DevBuf<int> *i1[] = {&h->vertId, &h->cStart, &h->cEnt, &h->order, &h->levelStart, &h->vpStart, &h->vpSlot, &h->tStart, &h->tEnt, &h->grabOut, &h->visTri, &h->vtStart, &h->vtEnt};
@@ -930,6 +952,7 @@ int tetsim_get_info(tetsim_t *h, TetSimInfo *info) {
     info->kernelLaunches = h->totalLaunches;
     info->tileMetaBytes = (int64_t)h->plan.tileMeta.size();
     info->maxTileVerts = h->clustered ? h->plan.maxTileVerts : 0;
+    info->boundaryTiles = h->plan.numBoundaryTiles;
     return TETSIM_OK;
 }
 

@@ -80,8 +80,8 @@ if rank == 0:
     ref = single.pos.reshape(N, 3).astype(np.float64)
     err = float(np.max(np.linalg.norm(merged - ref, axis=1) / np.linalg.norm(ref, axis=1)))
     touched = bool(np.any(ref[:, 1] == 0.0))
-    print("world %d: tets/rank %d, boundary verts %d (%.1f KB all-reduced per iteration), shared %d, "
-          "vector-rel err vs 1 GPU %.3e, floor contact %s" % (world, info["localTets"], info["boundaryVerts"],
+    print("world %d: tets/rank %d, tiles %d (%d boundary), boundary verts %d (%.1f KB all-reduced per iteration), shared %d, "
+          "vector-rel err vs 1 GPU %.3e, floor contact %s" % (world, info["localTets"], info["numClusters"], info["boundaryTiles"], info["boundaryVerts"],
                                                               info["boundaryVerts"] * 16 / 1024, int(shared.sum()), err, touched))
     if not (err <= 1e-5):
         ok = False
