@@ -282,54 +282,132 @@ bool build_cluster_plan(int numVerts, int numTets, const int *tetIds, const std:
     std::vector<int> tileVerts, tileVal, perm, rank_of;
     std::vector<std::vector<uint16_t>> colOffs((size_t)P.numClusters);
     std::vector<uint8_t> allVal;
-    std::vector<int> cornerRank;  // per corner of the tile: its index i in its vertex's list
+    std::vector<int> cornerStart, cornerFill, cornerList, cornerDiag, loadG, loadS, sorted;
+    std::vector<char> posTaken, diagFree;
     int maxTileVal = 0;
     for (int c = 0; c < P.numClusters; c++) {
         const int pb = tileStart[tileOrder[c]], pe = tileStart[tileOrder[c] + 1];
         tileVerts.clear(); tileVal.clear();
-        cornerRank.assign(4 * (size_t)T, 0);
         for (int pos = pb; pos < pe; pos++) {
             const int *t = tetIds + 4 * (size_t)order[pos];
             P.recordTet[(size_t)c * T + (pos - pb)] = order[pos];
             for (int k = 0; k < 4; k++) {
                 int lv = local[t[k]];
                 if (stamp[lv] != c) { stamp[lv] = c; tileIdx[lv] = (int)tileVerts.size(); tileVerts.push_back(lv); tileVal.push_back(0); }
-                cornerRank[4 * (size_t)(pos - pb) + k] = tileVal[tileIdx[lv]]++;  // ascending (tet, corner) order
+                tileVal[tileIdx[lv]]++;
             }
         }
         const int nl = (int)tileVerts.size();
+        const int ntile = pe - pb;
         // sort tile vertices by descending tile valence (stable)
         perm.resize(nl);
         std::iota(perm.begin(), perm.end(), 0);
         std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return tileVal[a] > tileVal[b]; });
-        rank_of.resize(nl);
-        for (int j = 0; j < nl; j++) rank_of[perm[j]] = j;
         const int tv = nl ? tileVal[perm[0]] : 0;
         if (tv > 255) { err = "a vertex has more than 255 tet corners inside one tile"; return false; }
         maxTileVal = std::max(maxTileVal, tv);
-        P.clVertStart[c + 1] = P.clVertStart[c] + nl;
-        for (int j = 0; j < nl; j++) { P.clVerts.push_back(tileVerts[perm[j]]); allVal.push_back((uint8_t)tileVal[perm[j]]); }
-        P.maxTileVerts = std::max(P.maxTileVerts, nl);
-        // jagged diagonals: diagonal i holds the i-th corner of every vertex with valence > i; vertices
-        // are valence-sorted, so those are a prefix and entry (i, j) sits at colOff[i] + j
+        // jagged diagonals: diagonal i holds one corner of every vertex with valence > i; vertices are
+        // valence-sorted, so those are a prefix and entry (i, j) sits at colOff[i] + j
         std::vector<uint16_t> &co = colOffs[c];
         co.assign((size_t)tv + 1, 0);
-        int off = 0, cnt = nl;
-        for (int i = 0; i < tv; i++) {
-            co[i] = (uint16_t)off;
-            while (cnt > 0 && tileVal[perm[cnt - 1]] <= i) cnt--;
-            off += cnt;
+        {
+            int off = 0, cnt = nl;
+            for (int i = 0; i < tv; i++) {
+                co[i] = (uint16_t)off;
+                while (cnt > 0 && tileVal[perm[cnt - 1]] <= i) cnt--;
+                off += cnt;
+            }
+            co[tv] = (uint16_t)off;
         }
-        co[tv] = (uint16_t)off;
-        for (int pos = pb; pos < pe; pos++) {
-            const int *t = tetIds + 4 * (size_t)order[pos];
+        // ---- shared-memory bank placement (round-1 ncu: 37 % of this kernel's shared-memory wavefronts
+        // were bank-conflict replays of the 16-byte gathers and scatters) ----
+        // A 128-bit warp access is served a quarter-warp (8 lanes) at a time and is conflict-free when
+        // the 8 sixteen-byte chunks fall into 8 different bank groups (byte offset / 16 mod 8).  The
+        // lanes of one quarter-warp executing corner k form a "conflict set".  Two degrees of freedom
+        // cost nothing at run time: the order of vertices inside a run of equal tile valence, and
+        // which of a vertex's diagonals each of its corners is parked in.  Both are chosen greedily.
+        const int nSets = ((T + 31) / 32) * 16;
+        auto setOf = [&](int tl, int k) { return ((tl >> 5) * 4 + k) * 4 + ((tl & 31) >> 3); };
+        cornerStart.assign((size_t)nl + 1, 0);   // corners of each tile vertex (pre-sort index), appearance order
+        for (int v = 0; v < nl; v++) cornerStart[v + 1] = cornerStart[v] + tileVal[v];
+        cornerFill.assign(cornerStart.begin(), cornerStart.end() - 1);
+        cornerList.resize((size_t)cornerStart[nl]);
+        for (int tl = 0; tl < ntile; tl++) {
+            const int *t = tetIds + 4 * (size_t)order[pb + tl];
+            for (int k = 0; k < 4; k++) cornerList[cornerFill[tileIdx[local[t[k]]]]++] = 4 * tl + k;
+        }
+        // (a) position of each vertex inside its equal-valence run
+        loadG.assign((size_t)nSets * 8, 0);
+        rank_of.assign(nl, -1);
+        posTaken.assign(nl, 0);
+        for (int a0 = 0; a0 < nl;) {
+            int b0 = a0;
+            while (b0 < nl && tileVal[perm[b0]] == tileVal[perm[a0]]) b0++;
+            int nextFree[8];
+            for (int r = 0; r < 8; r++) { int p = a0 + ((r - a0) % 8 + 8) % 8; nextFree[r] = p < b0 ? p : -1; }
+            for (int q = a0; q < b0; q++) {
+                const int v = perm[q];
+                int best = -1;
+                long bestCost = 0;
+                for (int r = 0; r < 8; r++) {
+                    if (nextFree[r] < 0) continue;
+                    long cost = 0;
+                    int lastSet = -1;
+                    for (int e = cornerStart[v]; e < cornerStart[v + 1]; e++) {
+                        const int sid = setOf(cornerList[e] >> 2, cornerList[e] & 3);
+                        if (sid == lastSet) continue;  // same vertex twice in a set is a broadcast, not a conflict
+                        lastSet = sid;
+                        cost += loadG[(size_t)sid * 8 + r];
+                    }
+                    if (best < 0 || cost < bestCost || (cost == bestCost && nextFree[r] < nextFree[best])) { best = r; bestCost = cost; }
+                }
+                const int pos = nextFree[best];
+                rank_of[v] = pos;
+                posTaken[pos] = 1;
+                nextFree[best] = pos + 8 < b0 ? pos + 8 : -1;
+                int lastSet = -1;
+                for (int e = cornerStart[v]; e < cornerStart[v + 1]; e++) {
+                    const int sid = setOf(cornerList[e] >> 2, cornerList[e] & 3);
+                    if (sid == lastSet) continue;
+                    lastSet = sid;
+                    loadG[(size_t)sid * 8 + best]++;
+                }
+            }
+            a0 = b0;
+        }
+        sorted.assign(nl, 0);
+        for (int v = 0; v < nl; v++) sorted[rank_of[v]] = v;
+        P.clVertStart[c + 1] = P.clVertStart[c] + nl;
+        for (int j = 0; j < nl; j++) { P.clVerts.push_back(tileVerts[sorted[j]]); allVal.push_back((uint8_t)tileVal[sorted[j]]); }
+        P.maxTileVerts = std::max(P.maxTileVerts, nl);
+        // (b) diagonal of each corner
+        loadS.assign((size_t)nSets * 8, 0);
+        cornerDiag.assign(4 * (size_t)T, 0);
+        for (int j = 0; j < nl; j++) {
+            const int v = sorted[j], val = tileVal[v];
+            diagFree.assign(val, 1);
+            for (int e = cornerStart[v]; e < cornerStart[v + 1]; e++) {
+                const int cn = cornerList[e], sid = setOf(cn >> 2, cn & 3);
+                int best = -1, bestLoad = 0;
+                for (int i = 0; i < val; i++) {
+                    if (!diagFree[i]) continue;
+                    const int ld = loadS[(size_t)sid * 8 + ((co[i] + j) & 7)];
+                    if (best < 0 || ld < bestLoad) { best = i; bestLoad = ld; if (ld == 0) break; }
+                }
+                diagFree[best] = 0;
+                cornerDiag[cn] = best;
+                loadS[(size_t)sid * 8 + ((co[best] + j) & 7)]++;
+            }
+        }
+        for (int tl = 0; tl < ntile; tl++) {
+            const int *t = tetIds + 4 * (size_t)order[pb + tl];
             uint32_t sl[4], ds[4];
             for (int k = 0; k < 4; k++) {
-                int j = rank_of[tileIdx[local[t[k]]]];
+                const int j = rank_of[tileIdx[local[t[k]]]];
                 sl[k] = 16u * (uint32_t)j;
-                ds[k] = 16u * ((uint32_t)co[cornerRank[4 * (size_t)(pos - pb) + k]] + (uint32_t)j);
+                ds[k] = 16u * ((uint32_t)co[cornerDiag[4 * tl + k]] + (uint32_t)j);
             }
-            size_t r = (size_t)c * T + (pos - pb);
+            size_t r = (size_t)c * T + tl;
             P.recordAux[4 * r + 0] = sl[0] | sl[1] << 16;
             P.recordAux[4 * r + 1] = sl[2] | sl[3] << 16;
             P.recordAux[4 * r + 2] = ds[0] | ds[1] << 16;
