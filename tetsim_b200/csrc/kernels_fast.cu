@@ -79,8 +79,8 @@ struct TileSmem {
         sdx = 0;
         sx0 = sdx + (4 * T + 1) * 16;  // + one spare entry for padding records
         meta0 = sx0 + S * sxBytes;
-        bars = meta0 + (S + 2) * metaStride;
-        total = (bars + (S + 2) * 8 + 127) & ~127;
+        bars = meta0 + (S + 1) * metaStride;
+        total = (bars + (S + 1) * 8 + 127) & ~127;
     }
     __host__ __device__ int sx(int buf) const { return sx0 + buf * sxBytes; }
     __host__ __device__ int meta(int slot) const { return meta0 + slot * metaStride; }
@@ -113,12 +113,12 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
                                             const int stride) {
     constexpr int T = NT * TPT;
     const TileSmem<T, S> L(a.metaStride, a.maxTileVertsPad);
-    uint64_t *metaFull = reinterpret_cast<uint64_t *>(ws + L.bars);  // [S + 2]
+    uint64_t *metaFull = reinterpret_cast<uint64_t *>(ws + L.bars);  // [S + 1]
     unsigned char *const sdx = ws + L.sdx;
     auto sync = [&]() { if (WARP_SCOPE) __syncwarp(); else __syncthreads(); };
 
     if (tid == 0) {
-        for (int i = 0; i < S + 2; i++) mbar_init(metaFull + i, 1);
+        for (int i = 0; i < S + 1; i++) mbar_init(metaFull + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     sync();
@@ -168,32 +168,10 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
         else cp_async_commit();
     }
 
-    // per-tile-vertex sums of the parked corner dx of tile kk (fixed order -> reproducible)
-    auto sum_corners = [&](int kk) {
-        const unsigned char *m = ws + L.meta(kk % (S + 2));
-        const int v0 = reinterpret_cast<const int *>(m)[0];
-        const int nl = reinterpret_cast<const int *>(m)[1];
-        const uint16_t *scol = reinterpret_cast<const uint16_t *>(m + 16);
-        if (!(a.debugSkip & 1))
-            for (int j = tid; j < nl; j += NT) {
-                const int val = m[a.metaValOff + j];
-                const unsigned char *base = sdx + j * 16;
-                float ax = 0.0f, ay = 0.0f, az = 0.0f;
-#pragma unroll 4
-                for (int i = 0; i < val; i++) {
-                    const float4 d = *reinterpret_cast<const float4 *>(base + scol[i]);
-                    ax += d.x; ay += d.y; az += d.z;
-                }
-                if (a.acc) atomicAdd(a.acc + reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3])[j],
-                                     make_float4(ax, ay, az, 0.0f));
-                else a.part[v0 + j] = make_float4(ax, ay, az, 0.0f);
-            }
-    };
-
     int k = 0;
     for (int c = first; c < a.numTiles; c += stride, k++) {
-        // ---- this tile's records: issue the loads first; they land while the previous tile's corner
-        // sums and the prefetch issue below run (the L2 latency of the stream was the hottest stall) ----
+        const int cur = k % S, mcur = k % (S + 1);
+        // this tile's records: issue the loads first, they land while we wait and prefetch below
         const unsigned char *tb = a.tets + (size_t)c * TileSmem<T, S>::TET_BYTES;
         float4 rA[TPT], rB[TPT], rC[TPT];
 #pragma unroll
@@ -212,41 +190,40 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
             rB[u] = ldg_stream4(tb + T * 16 + t * 16);
             rC[u] = ldg_stream4(tb + T * 32 + t * 16);
         }
+        cp_async_wait_pending<S - 2>();
+        sync();  // this tile's gathers (all threads') landed; previous tile's corner sums are finished
 
         // ---- put tile k+S-1 (vertex gather) and tile k+S (meta) in flight ----
-        // The corner sums keep only the first ceil(nl/32) warps busy; the issue work is therefore done by
-        // the LAST warps of the CTA, which would otherwise idle at the next barrier.  Buffers reused:
-        // vertex tile and dx buffer of tile k-1 (its math finished before the barrier that ended the
-        // previous iteration), meta slot of tile k-2.
-        {
+        // The corner sums further down keep only the first ceil(nl/32) warps busy; the issue work is
+        // therefore handed to the LAST warps of the CTA, which would otherwise idle at the next barrier.
+        auto prefetch_next = [&]() {
             const int kn = k + S - 1, cn = c + (S - 1) * stride;
-            constexpr int NI = WARP_SCOPE ? NT : NT / 2;        // threads that issue
+            constexpr int NI = WARP_SCOPE ? NT : NT / 2;      // threads that issue
             const int it = WARP_SCOPE ? tid : tid - (NT - NI);  // their index, < 0 for the others
-            if (cn < a.numTiles && it >= 0) {
-                const int mslot = kn % (S + 2), buf = kn % S;
-                mbar_wait(metaFull + mslot, (kn / (S + 2)) & 1);
-                const unsigned char *m = ws + L.meta(mslot);
-                const int nl = reinterpret_cast<const int *>(m)[1];
-                const int *ids = reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3]);
-                float4 *sx = reinterpret_cast<float4 *>(ws + L.sx(buf));
-                if (!(a.debugSkip & 4))
-                    for (int j = it; j < nl; j += NI) cp_async16(sx + j, a.x4 + ids[j]);
+            if (cn < a.numTiles) {
+                const int mslot = kn % (S + 1), buf = kn % S;
+                if (it >= 0) {
+                    mbar_wait(metaFull + mslot, (kn / (S + 1)) & 1);
+                    const unsigned char *m = ws + L.meta(mslot);
+                    const int nl = reinterpret_cast<const int *>(m)[1];
+                    const int *ids = reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3]);
+                    float4 *sx = reinterpret_cast<float4 *>(ws + L.sx(buf));
+                    if (!(a.debugSkip & 4))
+                        for (int j = it; j < nl; j += NI) cp_async16(sx + j, a.x4 + ids[j]);
+                }
             }
             cp_async_commit();
             if (it == 0) {
                 if (c + (PF + 1) * stride < a.numTiles) prefetch_tets(c + (PF + 1) * stride);
                 if (c + S * stride < a.numTiles) {
-                    issue_meta(nOff, nEnd, (k + S) % (S + 2));  // slot of tile k-2
+                    issue_meta(nOff, nEnd, (k + S) % (S + 1));
                     if (c + (S + 1) * stride < a.numTiles) { nOff = a.metaOff[c + (S + 1) * stride]; nEnd = a.metaOff[c + (S + 1) * stride + 1]; }
                 }
             }
-        }
-        if (k > 0) sum_corners(k - 1);
-        cp_async_wait_pending<S - 1>();
-        sync();  // this tile's vertex gathers (all threads') landed; the dx buffer is free again
+        };
 
         // ---- per-tet solve ----
-        const unsigned char *sxb = ws + L.sx(k % S);
+        const unsigned char *sxb = ws + L.sx(cur);
         float vsum = 0.0f;
 #pragma unroll
         for (int u = 0; u < TPT; u++) {
@@ -273,9 +250,29 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
             for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
             if ((tid & 31) == 0) atomicAdd(a.volAcc, (double)vsum);
         }
-        sync();  // every corner of this tile is parked
+        sync();
+        prefetch_next();
+
+        // ---- per-tile-vertex sum of corner dx, ascending (tet, corner) order ----
+        const unsigned char *m = ws + L.meta(mcur);
+        const int v0 = reinterpret_cast<const int *>(m)[0];
+        const int nl = reinterpret_cast<const int *>(m)[1];
+        const uint16_t *scol = reinterpret_cast<const uint16_t *>(m + 16);
+        if (!(a.debugSkip & 1))
+            for (int j = tid; j < nl; j += NT) {
+                const int val = m[a.metaValOff + j];
+                const unsigned char *base = sdx + j * 16;
+                float ax = 0.0f, ay = 0.0f, az = 0.0f;
+#pragma unroll 4
+                for (int i = 0; i < val; i++) {
+                    const float4 d = *reinterpret_cast<const float4 *>(base + scol[i]);
+                    ax += d.x; ay += d.y; az += d.z;
+                }
+                if (a.acc) atomicAdd(a.acc + reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3])[j],
+                                     make_float4(ax, ay, az, 0.0f));
+                else a.part[v0 + j] = make_float4(ax, ay, az, 0.0f);
+            }
     }
-    sum_corners(k - 1);
 }
 
 // CTA tiles: T tets per tile, one tet per thread, two __syncthreads per tile.
