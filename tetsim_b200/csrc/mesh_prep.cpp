@@ -162,8 +162,67 @@ std::vector<int> morton_order(int numVerts, int numTets, const float *verts, con
     return order;
 }
 
-bool build_cluster_plan(int numVerts, int numTets, const int *tetIds, const std::vector<int> &order, int T, int rank,
-                        int worldSize, ClusterPlan &P, std::string &err) {
+// Recursive coordinate bisection of the tet centroids into `parts` pieces of (nearly) equal tet
+// count: split the longest axis of the piece's bounding box at the proportional quantile.  For a
+// beam this yields slabs with planar cuts, i.e. the smallest rank-shared vertex set.
+static void rcb(std::vector<int> &idx, int lo, int hi, int parts, int firstPart, const std::vector<float> &cent,
+                std::vector<int> &partOf) {
+    if (parts <= 1 || hi - lo <= 1) {
+        for (int i = lo; i < hi; i++) partOf[idx[i]] = firstPart;
+        return;
+    }
+    float bl[3] = {INFINITY, INFINITY, INFINITY}, bh[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = lo; i < hi; i++)
+        for (int c = 0; c < 3; c++) {
+            float x = cent[3 * (size_t)idx[i] + c];
+            bl[c] = std::min(bl[c], x); bh[c] = std::max(bh[c], x);
+        }
+    int ax = 0;
+    for (int c = 1; c < 3; c++) if (bh[c] - bl[c] > bh[ax] - bl[ax]) ax = c;
+    const int pl = parts / 2;
+    const int mid = lo + (int)((int64_t)(hi - lo) * pl / parts);
+    std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi, [&](int a, int b) {
+        float xa = cent[3 * (size_t)a + ax], xb = cent[3 * (size_t)b + ax];
+        return xa != xb ? xa < xb : a < b;
+    });
+    rcb(idx, lo, mid, pl, firstPart, cent, partOf);
+    rcb(idx, mid, hi, parts - pl, firstPart + pl, cent, partOf);
+}
+
+std::vector<int> solver_order(int numVerts, int numTets, const float *verts, const int *tetIds, bool reorder,
+                              int worldSize, std::vector<int> &rankStart) {
+    std::vector<int> order;
+    if (reorder) order = morton_order(numVerts, numTets, verts, tetIds);
+    else { order.resize((size_t)numTets); std::iota(order.begin(), order.end(), 0); }
+    rankStart.assign((size_t)worldSize + 1, 0);
+    if (worldSize <= 1 || !reorder) {  // caller's order: contiguous equal chunks
+        for (int r = 0; r <= worldSize; r++) rankStart[r] = (int)((int64_t)numTets * r / worldSize);
+        return order;
+    }
+    std::vector<float> cent(3 * (size_t)numTets);
+    for (int e = 0; e < numTets; e++) {
+        const int *t = tetIds + 4 * (size_t)e;
+        for (int c = 0; c < 3; c++)
+            cent[3 * (size_t)e + c] = 0.25f * (verts[3 * (size_t)t[0] + c] + verts[3 * (size_t)t[1] + c] +
+                                               verts[3 * (size_t)t[2] + c] + verts[3 * (size_t)t[3] + c]);
+    }
+    std::vector<int> idx((size_t)numTets), partOf((size_t)numTets, 0);
+    std::iota(idx.begin(), idx.end(), 0);
+    rcb(idx, 0, numTets, worldSize, 0, cent, partOf);
+    // keep the Hilbert order inside each part
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return partOf[a] < partOf[b]; });
+    int pos = 0;
+    for (int r = 0; r < worldSize; r++) {
+        rankStart[r] = pos;
+        while (pos < numTets && partOf[order[pos]] == r) pos++;
+    }
+    rankStart[worldSize] = numTets;
+    return order;
+}
+
+bool build_cluster_plan(int numVerts, int numTets, const int *tetIds, const std::vector<int> &order,
+                        const std::vector<int> &rankStart, int T, int rank, int worldSize, ClusterPlan &P,
+                        std::string &err) {
     P = ClusterPlan();
     P.T = T;
     // ---- cut the tet sequence into tiles: at most T tets and at most `vertCap` distinct vertices ----
@@ -176,13 +235,16 @@ bool build_cluster_plan(int numVerts, int numTets, const int *tetIds, const std:
         auto cut = [&](int cap, double *avgOut) {
             tileStart.clear();
             std::fill(stampG.begin(), stampG.end(), -1);
-            int tile = -1, nt = T, nv = 0;
+            int tile = -1, nt = T, nv = 0, nextRank = 0;
+            bool forced = false;
             long long sumV = 0;
             for (int pos = 0; pos < numTets; pos++) {
                 const int *t = tetIds + 4 * (size_t)order[pos];
                 int fresh = 0;
                 if (tile >= 0) for (int k = 0; k < 4; k++) fresh += stampG[t[k]] != tile;
-                if (nt == T || (cap > 0 && nv + fresh > cap)) {
+                while (nextRank <= worldSize && rankStart[nextRank] <= pos) { if (rankStart[nextRank] == pos) forced = true; nextRank++; }
+                if (nt == T || forced || (cap > 0 && nv + fresh > cap)) {
+                    forced = false;
                     sumV += nv;
                     tile++; nt = 0; nv = 0;
                     tileStart.push_back(pos);
@@ -203,7 +265,10 @@ bool build_cluster_plan(int numVerts, int numTets, const int *tetIds, const std:
         if (cap > 0) cut(cap, nullptr);
     }
     const int totalClusters = (int)tileStart.size() - 1;
-    auto firstClusterOf = [&](int r) { return (int)((int64_t)totalClusters * r / worldSize); };
+    std::vector<int> rankFirstTile((size_t)worldSize + 1, totalClusters);
+    for (int r = 0; r <= worldSize; r++)
+        rankFirstTile[r] = (int)(std::lower_bound(tileStart.begin(), tileStart.end() - 1, rankStart[r]) - tileStart.begin());
+    auto firstClusterOf = [&](int r) { return rankFirstTile[r]; };
     const int c0 = firstClusterOf(rank), c1 = firstClusterOf(rank + 1);
     P.numClusters = c1 - c0;
 

@@ -68,8 +68,13 @@ struct ClusterPlan {
     int localTets = 0;
     int maxValence = 0;
 };
-// order: the global tet sequence (caller tet indices); rank/worldSize select a contiguous run of tiles.
-bool build_cluster_plan(int numVerts, int numTets, const int *tetIds, const std::vector<int> &order, int T, int rank,
-                        int worldSize, ClusterPlan &plan, std::string &err);
+// Solver order of the tets: Hilbert-sorted (reorder) and, for worldSize > 1, grouped by a recursive
+// coordinate bisection into worldSize spatial parts.  rankStart[r] = position of rank r's first tet.
+std::vector<int> solver_order(int numVerts, int numTets, const float *verts, const int *tetIds, bool reorder,
+                              int worldSize, std::vector<int> &rankStart);
+// order: the global tet sequence (caller tet indices); rank r owns positions [rankStart[r], rankStart[r+1]).
+bool build_cluster_plan(int numVerts, int numTets, const int *tetIds, const std::vector<int> &order,
+                        const std::vector<int> &rankStart, int T, int rank, int worldSize, ClusterPlan &plan,
+                        std::string &err);
 
 }  // namespace tsim

@@ -334,11 +334,10 @@ int build_jacobi_gather(tetsim *h, const std::vector<int> &tetIds) {
 
 int build_jacobi_cluster(tetsim *h, const std::vector<float> &verts, const std::vector<int> &tetIds) {
     const int N = h->N, M = h->M;
-    std::vector<int> order;
-    if (h->opt.reorder) order = morton_order(N, M, verts.data(), tetIds.data());
-    else { order.resize((size_t)M); std::iota(order.begin(), order.end(), 0); }
+    std::vector<int> rankStart;
+    std::vector<int> order = solver_order(N, M, verts.data(), tetIds.data(), h->opt.reorder != 0, h->opt.worldSize, rankStart);
     std::string err;
-    if (!build_cluster_plan(N, M, tetIds.data(), order, h->opt.clusterSize, h->opt.rank, h->opt.worldSize, h->plan, err))
+    if (!build_cluster_plan(N, M, tetIds.data(), order, rankStart, h->opt.clusterSize, h->opt.rank, h->opt.worldSize, h->plan, err))
         return fail(TETSIM_E_INVALID, err);
     ClusterPlan &P = h->plan;
     h->clustered = true;
@@ -1020,12 +1019,11 @@ int tetsim_plan_partition(const float *verts, int32_t numVerts, const int32_t *t
     if (clusterSize < 1 || worldSize < 1 || rank < 0 || rank >= worldSize) return fail(TETSIM_E_INVALID, "bad clusterSize/rank/worldSize");
     for (int64_t c = 0; c < 4 * (int64_t)numTets; c++)
         if (tetIds[c] < 0 || tetIds[c] >= numVerts) return fail(TETSIM_E_INVALID, "vertex id out of range");
-    std::vector<int> order;
-    if (reorder) order = morton_order(numVerts, numTets, verts, tetIds);
-    else { order.resize((size_t)numTets); std::iota(order.begin(), order.end(), 0); }
+    std::vector<int> rankStart;
+    std::vector<int> order = solver_order(numVerts, numTets, verts, tetIds, reorder != 0, worldSize, rankStart);
     ClusterPlan P;
     std::string err;
-    if (!build_cluster_plan(numVerts, numTets, tetIds, order, clusterSize, rank, worldSize, P, err)) return fail(TETSIM_E_INVALID, err);
+    if (!build_cluster_plan(numVerts, numTets, tetIds, order, rankStart, clusterSize, rank, worldSize, P, err)) return fail(TETSIM_E_INVALID, err);
     counts[0] = P.localTets; counts[1] = P.numInterior; counts[2] = P.numBoundary; counts[3] = P.numClusters;
     if (localToCaller) std::copy(P.localToCaller.begin(), P.localToCaller.end(), localToCaller);
     if (localTets) {
