@@ -57,6 +57,8 @@ def parse():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong: the same 10M-tet mesh split over N GPUs (BASELINE config 4); weak: beam length x N")
     ap.add_argument("--cpu-substeps", type=int, default=2, help="substeps of the CPU baseline sample (rank 0, N=1)")
+    ap.add_argument("--exchange", default="allreduce", choices=["allreduce", "halo"],
+                    help="multi-GPU boundary exchange: ncclAllReduce over all ranks, or grouped ncclSend/ncclRecv with neighbours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -203,7 +205,7 @@ def main():
     body = ts.SoftBody(verts, tets, None, pp, solver="jacobi", arithmetic="fast", iters=args.iters,
                        cluster_size=args.cluster_size, reorder=not args.no_reorder, deterministic=not args.atomic,
                        device=local_rank, stream=stream.cuda_stream, rank=rank, world_size=world,
-                       nccl_unique_id=nccl_id)
+                       nccl_unique_id=nccl_id, exchange=args.exchange)
     info = body.info()
 
     def barrier():
@@ -307,7 +309,7 @@ def main():
             "config": {"workload": workload, "tets": M, "verts": N, "iters": args.iters, "substeps_per_step": args.substeps,
                        "cluster_size": info["clusterSize"], "clusters_rank0": info["numClusters"],
                        "boundary_verts": info["boundaryVerts"], "boundary_tiles_rank0": info["boundaryTiles"], "deterministic": not args.atomic,
-                       "parallelism": "tet-partition x%d, ncclAllReduce of boundary dx per iteration" % world if world > 1 else "single GPU",
+                       "parallelism": ("tet-partition x%d (RCB), %s of boundary dx per iteration, overlapped with interior tiles" % (world, "ncclAllReduce" if args.exchange == "allreduce" else "neighbour ncclSend/ncclRecv")) if world > 1 else "single GPU",
                        "l2": "working set per substep (%.0f MB) exceeds the 126 MB L2; no flush needed" % ((56.0 * M + 144.0 * N) / 1e6)},
             "scalar_constraints_per_s_M": 2 * value,
             "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,

@@ -95,8 +95,9 @@ typedef struct TetSimOptions {
     int32_t device;            /* CUDA device ordinal, -1 = the calling thread's current device       */
     int32_t rank;              /* multi-GPU Jacobi: this process's rank, 0 when worldSize == 1        */
     int32_t worldSize;         /* multi-GPU Jacobi: number of tet partitions / processes, default 1   */
-    int32_t exchange;          /* multi-GPU: 0 = ncclAllReduce of boundary dx (default),
-                                  1 = fused peer-memory exchange (needs tetsim_set_peers)            */
+    int32_t exchange;          /* multi-GPU: 0 = ncclAllReduce of the boundary dx over all ranks (default),
+                                  1 = neighbour exchange: grouped ncclSend/ncclRecv with the ranks that share
+                                  vertices with this one, sharers' sums added in ascending rank order      */
     void *stream;              /* cudaStream_t to enqueue on; NULL = a stream owned by the handle     */
     const void *ncclUniqueId;  /* 128-byte ncclUniqueId from tetsim_nccl_unique_id (rank 0's), or NULL */
 } TetSimOptions;
@@ -192,9 +193,9 @@ int tetsim_time_kernel(tetsim_t *h, int32_t reps, double *msPerLaunch, int64_t *
 /* Multi-GPU plumbing (one process per GPU).  Rank 0 calls tetsim_nccl_unique_id and broadcasts the
  * 128 bytes out of band (torch.distributed in this repo); every rank passes them in TetSimOptions. */
 int tetsim_nccl_unique_id(void *out128);
-/* Fused exchange: 64-byte cudaIpcMemHandle of this rank's boundary accumulator ... */
+/* Reserved for a fused peer-memory exchange (tile kernel storing boundary sums straight into the
+ * neighbour's accumulator through a cudaIpc mapping).  Not built yet: both return TETSIM_E_STATE. */
 int tetsim_get_ipc_handle(tetsim_t *h, void *out64);
-/* ... and the handles of all ranks (worldSize * 64 bytes, own slot ignored). */
 int tetsim_set_peers(tetsim_t *h, const void *handles);
 
 /* Host-side mesh tools used by tests and the benchmark (the reference has none; README.md:25). */

@@ -482,12 +482,40 @@ void launch_boundary_pack(cudaStream_t s, int boundaryBegin, int nB, const int *
     if (nB > 0) k_boundary_pack<<<cdiv(nB, 256), 256, 0, s>>>(boundaryBegin, nB, vpStart, vpSlot, part, bsum);
 }
 
+__global__ void k_halo_pack(int n, const int *__restrict__ sendIdx, const float4 *__restrict__ bsum,
+                            float4 *__restrict__ send) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) send[i] = bsum[sendIdx[i]];
+}
+void launch_halo_pack(cudaStream_t s, int n, const int *sendIdx, const float4 *bsum, float4 *send) {
+    if (n > 0) k_halo_pack<<<cdiv(n, 256), 256, 0, s>>>(n, sendIdx, bsum, send);
+}
+// every sharer adds the sharers' partial sums in ascending rank order -> bit-identical replicas
+__global__ void k_halo_reduce(int nB, const int *__restrict__ srcStart, const int *__restrict__ src,
+                              const float4 *__restrict__ recv, float4 *__restrict__ bsum) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nB) return;
+    const int s0 = srcStart[b], s1 = srcStart[b + 1];
+    if (s0 == s1) return;
+    float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+    for (int j = s0; j < s1; j++) {
+        const int k = src[j];
+        const float4 v = k < nB ? bsum[k] : recv[k - nB];  // k == b for the own term: read before the write below
+        sx += v.x; sy += v.y; sz += v.z;
+    }
+    bsum[b] = make_float4(sx, sy, sz, 0.0f);
+}
+void launch_halo_reduce(cudaStream_t s, int nB, const int *srcStart, const int *src, const float4 *recv, float4 *bsum) {
+    if (nB > 0) k_halo_reduce<<<cdiv(nB, 256), 256, 0, s>>>(nB, srcStart, src, recv, bsum);
+}
+
 // =================================================================================================
 // Utility kernels
 // =================================================================================================
 __global__ void k_pack3(int N, const float4 *__restrict__ src, const int *__restrict__ perm, float *__restrict__ dst) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
+    if (perm && perm[i] < 0) return;  // replica this rank does not maintain
     float4 v = src[i];
     size_t o = 3 * (size_t)(perm ? perm[i] : i);
     dst[o] = v.x; dst[o + 1] = v.y; dst[o + 2] = v.z;
@@ -499,6 +527,7 @@ __global__ void k_unpack3(int N, const float *__restrict__ src, const int *__res
                           int keepW) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
+    if (perm && perm[i] < 0) return;
     size_t o = 3 * (size_t)(perm ? perm[i] : i);
     float w = keepW ? dst[i].w : 0.0f;
     dst[i] = make_float4(src[o], src[o + 1], src[o + 2], w);

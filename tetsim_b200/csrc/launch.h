@@ -87,6 +87,11 @@ void launch_jacobi_apply(cudaStream_t, int begin, int end, int mode, const Apply
 void launch_boundary_pack(cudaStream_t, int boundaryBegin, int numBoundary, const int *vpStart, const int *vpSlot,
                           const float4 *part, float4 *bsum);
 
+// neighbour exchange: send[i] = bsum[sendIdx[i]];  bsum[b] = sum over srcs (own bsum / recv entries) in rank order
+void launch_halo_pack(cudaStream_t, int n, const int *sendIdx, const float4 *bsum, float4 *send);
+void launch_halo_reduce(cudaStream_t, int numBoundary, const int *srcStart, const int *src, const float4 *recv,
+                        float4 *bsum);
+
 // ---- utility kernels (kernels_fast.cu) ----
 void launch_pack3(cudaStream_t, int N, const float4 *src, const int *perm, float *dst3);       // dst[perm[i]] = src[i].xyz
 void launch_unpack3(cudaStream_t, int N, const float *src3, const int *perm, float4 *dst, int keepW);

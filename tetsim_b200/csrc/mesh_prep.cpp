@@ -162,10 +162,12 @@ std::vector<int> morton_order(int numVerts, int numTets, const float *verts, con
     return order;
 }
 
-// Recursive coordinate bisection of the tet centroids into `parts` pieces of (nearly) equal tet
-// count: split the longest axis of the piece's bounding box at the proportional quantile.  For a
-// beam this yields slabs with planar cuts, i.e. the smallest rank-shared vertex set.
-static void rcb(std::vector<int> &idx, int lo, int hi, int parts, int firstPart, const std::vector<float> &cent,
+// Recursive coordinate bisection of the tets into `parts` pieces of (nearly) equal tet count: split
+// the longest axis of the piece's bounding box at the proportional quantile of the tets' LOWEST
+// vertex coordinate, ties all going to the upper piece.  On structured meshes (beam: every tet of a
+// cell layer has the same lowest x) the cut then falls between two cell layers, so only ONE vertex
+// plane is shared; on unstructured meshes it is an ordinary median split.
+static void rcb(std::vector<int> &idx, int lo, int hi, int parts, int firstPart, const std::vector<float> &key,
                 std::vector<int> &partOf) {
     if (parts <= 1 || hi - lo <= 1) {
         for (int i = lo; i < hi; i++) partOf[idx[i]] = firstPart;
@@ -174,19 +176,26 @@ static void rcb(std::vector<int> &idx, int lo, int hi, int parts, int firstPart,
     float bl[3] = {INFINITY, INFINITY, INFINITY}, bh[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (int i = lo; i < hi; i++)
         for (int c = 0; c < 3; c++) {
-            float x = cent[3 * (size_t)idx[i] + c];
+            float x = key[3 * (size_t)idx[i] + c];
             bl[c] = std::min(bl[c], x); bh[c] = std::max(bh[c], x);
         }
     int ax = 0;
     for (int c = 1; c < 3; c++) if (bh[c] - bl[c] > bh[ax] - bl[ax]) ax = c;
     const int pl = parts / 2;
-    const int mid = lo + (int)((int64_t)(hi - lo) * pl / parts);
+    int mid = lo + (int)((int64_t)(hi - lo) * pl / parts);
     std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi, [&](int a, int b) {
-        float xa = cent[3 * (size_t)a + ax], xb = cent[3 * (size_t)b + ax];
+        float xa = key[3 * (size_t)a + ax], xb = key[3 * (size_t)b + ax];
         return xa != xb ? xa < xb : a < b;
     });
-    rcb(idx, lo, mid, pl, firstPart, cent, partOf);
-    rcb(idx, mid, hi, parts - pl, firstPart + pl, cent, partOf);
+    // move the cut to the nearer end of the run of equal keys around the quantile
+    const float m = key[3 * (size_t)idx[mid] + ax];
+    auto below = std::partition(idx.begin() + lo, idx.begin() + hi, [&](int a) { return key[3 * (size_t)a + ax] < m; });
+    auto notAbove = std::partition(below, idx.begin() + hi, [&](int a) { return key[3 * (size_t)a + ax] <= m; });
+    const int cutLo = (int)(below - idx.begin()), cutHi = (int)(notAbove - idx.begin());
+    int cut = (mid - cutLo <= cutHi - mid) ? cutLo : cutHi;
+    if (cut <= lo || cut >= hi) cut = (cutLo > lo && cutLo < hi) ? cutLo : ((cutHi > lo && cutHi < hi) ? cutHi : mid);
+    rcb(idx, lo, cut, pl, firstPart, key, partOf);
+    rcb(idx, cut, hi, parts - pl, firstPart + pl, key, partOf);
 }
 
 std::vector<int> solver_order(int numVerts, int numTets, const float *verts, const int *tetIds, bool reorder,
@@ -203,8 +212,8 @@ std::vector<int> solver_order(int numVerts, int numTets, const float *verts, con
     for (int e = 0; e < numTets; e++) {
         const int *t = tetIds + 4 * (size_t)e;
         for (int c = 0; c < 3; c++)
-            cent[3 * (size_t)e + c] = 0.25f * (verts[3 * (size_t)t[0] + c] + verts[3 * (size_t)t[1] + c] +
-                                               verts[3 * (size_t)t[2] + c] + verts[3 * (size_t)t[3] + c]);
+            cent[3 * (size_t)e + c] = std::min(std::min(verts[3 * (size_t)t[0] + c], verts[3 * (size_t)t[1] + c]),
+                                               std::min(verts[3 * (size_t)t[2] + c], verts[3 * (size_t)t[3] + c]));
     }
     std::vector<int> idx((size_t)numTets), partOf((size_t)numTets, 0);
     std::iota(idx.begin(), idx.end(), 0);
@@ -275,7 +284,9 @@ bool build_cluster_plan(int numVerts, int numTets, const int *tetIds, const std:
     // global valence and rank-shared (boundary) vertices
     std::vector<int> valence((size_t)numVerts, 0);
     std::vector<int> rmin, rmax;
+    std::vector<uint64_t> rmask;  // ranks touching each vertex (worldSize <= 64)
     if (worldSize > 1) { rmin.assign((size_t)numVerts, worldSize); rmax.assign((size_t)numVerts, -1); }
+    if (worldSize > 1 && worldSize <= 64) rmask.assign((size_t)numVerts, 0ull);
     {
         int r = 0, cl = 0;
         for (int pos = 0; pos < numTets; pos++) {
@@ -287,6 +298,7 @@ bool build_cluster_plan(int numVerts, int numTets, const int *tetIds, const std:
             for (int k = 0; k < 4; k++) {
                 valence[t[k]]++;
                 if (worldSize > 1) { rmin[t[k]] = std::min(rmin[t[k]], r); rmax[t[k]] = std::max(rmax[t[k]], r); }
+                if (!rmask.empty()) rmask[t[k]] |= 1ull << r;
             }
         }
     }
@@ -299,6 +311,42 @@ bool build_cluster_plan(int numVerts, int numTets, const int *tetIds, const std:
         for (int v = 0; v < numVerts; v++)
             if (rmax[v] > rmin[v]) boundary.push_back(v);
     P.numBoundary = (int)boundary.size();
+    if (!rmask.empty()) {  // neighbour exchange lists
+        P.haloOk = true;
+        const int nB = P.numBoundary;
+        P.boundaryActive.assign((size_t)nB, 0);
+        std::vector<std::vector<int>> shared((size_t)worldSize);  // per peer: boundary indices shared with it, ascending
+        for (int b = 0; b < nB; b++) {
+            const uint64_t m = rmask[boundary[b]];
+            if (!(m >> rank & 1ull)) continue;
+            P.boundaryActive[b] = 1;
+            for (int q = 0; q < worldSize; q++)
+                if (q != rank && (m >> q & 1ull)) shared[q].push_back(b);
+        }
+        std::vector<int> segOf((size_t)worldSize, -1);
+        P.hxSegStart.assign(1, 0);
+        for (int q = 0; q < worldSize; q++)
+            if (!shared[q].empty()) {
+                segOf[q] = (int)P.hxPeers.size();
+                P.hxPeers.push_back(q);
+                P.hxSendIdx.insert(P.hxSendIdx.end(), shared[q].begin(), shared[q].end());
+                P.hxSegStart.push_back((int)P.hxSendIdx.size());
+            }
+        // sources of each active boundary vertex in ascending rank order
+        std::vector<int> cursor((size_t)worldSize, 0);
+        P.hxSrcStart.assign((size_t)nB + 1, 0);
+        for (int b = 0; b < nB; b++) {
+            P.hxSrcStart[b] = (int)P.hxSrc.size();
+            if (!P.boundaryActive[b]) continue;
+            const uint64_t m = rmask[boundary[b]];
+            for (int q = 0; q < worldSize; q++) {
+                if (!(m >> q & 1ull)) continue;
+                if (q == rank) P.hxSrc.push_back(b);
+                else P.hxSrc.push_back(nB + P.hxSegStart[segOf[q]] + cursor[q]++);  // shared[q] is ascending in b
+            }
+        }
+        P.hxSrcStart[nB] = (int)P.hxSrc.size();
+    }
     P.localTets = std::max(0, tileStart[c1] - tileStart[c0]);
     for (int v : boundary) local[v] = -2;
     // Tiles that touch a rank-shared vertex go FIRST: a multi-GPU handle launches them alone, starts

@@ -41,6 +41,16 @@ struct ClusterPlan {
     int T = 0;                          // tets per tile
     int numClusters = 0;                // tiles on this rank
     int numBoundaryTiles = 0;           // the first numBoundaryTiles tiles touch rank-shared vertices
+    // Neighbour ("halo") exchange of the boundary sums, the alternative to an all-reduce over all ranks:
+    // rank r and q exchange their partial sums of the boundary vertices BOTH touch, then every sharer
+    // adds the contributions of all sharers in ascending rank order (identical on every sharer).
+    bool haloOk = false;                // false when worldSize > 64 (falls back to the all-reduce)
+    std::vector<uint8_t> boundaryActive;  // [numBoundary] 1 = touched by this rank's tets
+    std::vector<int> hxPeers;           // neighbour ranks, ascending
+    std::vector<int> hxSegStart;        // [peers + 1] segment offsets (in boundary entries) of send AND recv buffers
+    std::vector<int> hxSendIdx;         // boundary index of each send entry (same order on both sides of a pair)
+    std::vector<int> hxSrcStart;        // [numBoundary + 1] CSR over the sources of each active boundary vertex
+    std::vector<int> hxSrc;             // < numBoundary: own partial sum; >= numBoundary: recv entry - numBoundary
     int numLocalVerts = 0;              // interior + all boundary vertices
     int numInterior = 0;
     int numBoundary = 0;                // global count of rank-shared vertices (same on every rank)

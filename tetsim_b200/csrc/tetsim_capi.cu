@@ -44,6 +44,10 @@ struct NcclApi {
     int (*GetUniqueId)(NcclUniqueId *) = nullptr;
     int (*CommInitRank)(NcclComm *, int, NcclUniqueId, int) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*Send)(const void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     int (*CommDestroy)(NcclComm) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
     std::string why;
@@ -60,9 +64,13 @@ struct NcclApi {
         GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
         CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
         AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+        Send = (decltype(Send))dlsym(lib, "ncclSend");
+        Recv = (decltype(Recv))dlsym(lib, "ncclRecv");
+        GroupStart = (decltype(GroupStart))dlsym(lib, "ncclGroupStart");
+        GroupEnd = (decltype(GroupEnd))dlsym(lib, "ncclGroupEnd");
         CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
         GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
-        if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy || !GetErrorString) {
+        if (!GetUniqueId || !CommInitRank || !AllReduce || !Send || !Recv || !GroupStart || !GroupEnd || !CommDestroy || !GetErrorString) {
             why = "libnccl is missing a required symbol";
             lib = nullptr;
             return false;
@@ -165,6 +173,9 @@ struct tetsim {
     NcclComm comm = nullptr;
     cudaStream_t commStream = nullptr;      // the all-reduce runs here, beside the interior tiles
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    bool halo = false;                      // neighbour exchange instead of the all-reduce
+    DevBuf<int> hxSendIdx, hxSrcStart, hxSrc;
+    DevBuf<float4> hxSend, hxRecv;
     int maxValence = 0;
 
     int64_t deviceBytes() const {
@@ -364,6 +375,17 @@ int build_jacobi_cluster(tetsim *h, const std::vector<float> &verts, const std::
     if (P.numBoundary > 0) CK(h->bsum.alloc((size_t)P.numBoundary));
     if (h->trackVol) { CK(h->volTerm.alloc(1)); CK(cudaMemsetAsync(h->volTerm.p, 0, sizeof(double), s)); }
     h->h_vertId = P.localToCaller;
+    h->halo = h->opt.worldSize > 1 && h->opt.exchange == 1 && P.haloOk;
+    if (h->halo) {
+        CK(h->hxSendIdx.upload(P.hxSendIdx, s));
+        CK(h->hxSrcStart.upload(P.hxSrcStart, s));
+        CK(h->hxSrc.upload(P.hxSrc, s));
+        CK(h->hxSend.alloc(P.hxSendIdx.size()));
+        CK(h->hxRecv.alloc(P.hxSendIdx.size()));
+        // replicas of boundary vertices this rank's tets never touch receive no sums: not maintained here
+        for (int b = 0; b < P.numBoundary; b++)
+            if (!P.boundaryActive[b]) h->h_vertId[(size_t)P.numInterior + b] = -1;
+    }
     bool identity = (int)h->h_vertId.size() == N;
     for (int i = 0; identity && i < N; i++) identity = h->h_vertId[i] == i;
     if (identity) h->h_vertId.clear();
@@ -464,17 +486,31 @@ int enqueue_substeps(tetsim *h, int count) {
                                 launch_boundary_pack(s, P.numInterior, P.numBoundary, h->vpStart.p, h->vpSlot.p, h->part.p, h->bsum.p);
                                 h->enq++;
                             }
-                            // 2. all-reduce over NVLink on the side stream ...
+                            if (h->halo) { launch_halo_pack(s, (int)P.hxSendIdx.size(), h->hxSendIdx.p, h->bsum.p, h->hxSend.p); h->enq++; }
+                            // 2. all-reduce (or neighbour exchange) over NVLink on the side stream ...
                             CK(cudaEventRecord(h->evFork, s));
                             CK(cudaStreamWaitEvent(h->commStream, h->evFork, 0));
-                            int rc = g_nccl.AllReduce(h->bsum.p, h->bsum.p, (size_t)P.numBoundary * 4, kNcclFloat, kNcclSum, h->comm, h->commStream);
-                            if (rc != 0) return fail(TETSIM_E_NCCL, std::string("ncclAllReduce: ") + g_nccl.GetErrorString(rc));
+                            int rc = 0;
+                            if (!h->halo) {
+                                rc = g_nccl.AllReduce(h->bsum.p, h->bsum.p, (size_t)P.numBoundary * 4, kNcclFloat, kNcclSum, h->comm, h->commStream);
+                            } else {  // pairwise exchange with the ranks that share vertices with this one
+                                rc = g_nccl.GroupStart();
+                                for (size_t q = 0; q < P.hxPeers.size() && rc == 0; q++) {
+                                    const size_t off = (size_t)P.hxSegStart[q], n = (size_t)(P.hxSegStart[q + 1] - P.hxSegStart[q]) * 4;
+                                    rc = g_nccl.Send(h->hxSend.p + off, n, kNcclFloat, P.hxPeers[q], h->comm, h->commStream);
+                                    if (rc == 0) rc = g_nccl.Recv(h->hxRecv.p + off, n, kNcclFloat, P.hxPeers[q], h->comm, h->commStream);
+                                }
+                                int rc2 = g_nccl.GroupEnd();
+                                if (rc == 0) rc = rc2;
+                            }
+                            if (rc != 0) return fail(TETSIM_E_NCCL, std::string("NCCL exchange: ") + g_nccl.GetErrorString(rc));
                             CK(cudaEventRecord(h->evJoin, h->commStream));
                             // 3. ... while the interior tiles run on the main stream
                             TileArgs ci = ca;
                             ci.tileBegin = P.numBoundaryTiles;
                             launch_jacobi_tiles(s, P.T, ci);
                             CK(cudaStreamWaitEvent(s, h->evJoin, 0));
+                            if (h->halo) { launch_halo_reduce(s, P.numBoundary, h->hxSrcStart.p, h->hxSrc.p, h->hxRecv.p, h->bsum.p); h->enq++; }
                             aa.bsum = h->bsum.p;
                             h->enq += 2 + (P.numBoundaryTiles > 0 && P.numBoundaryTiles < P.numClusters ? 1 : 0);
                         }
@@ -616,6 +652,7 @@ int tetsim_create(const float *verts, int32_t numVerts, const int32_t *tetIds, i
     const bool clustered = opt.solver == TETSIM_NH_JACOBI && opt.arithmetic == TETSIM_ARITH_FAST_F32;
     if (opt.worldSize > 1 && !clustered)
         return fail(TETSIM_E_STATE, "worldSize > 1 is only supported by the FAST_F32 Jacobi solver; shard independent bodies across processes instead");
+    if (opt.exchange < 0 || opt.exchange > 1) return fail(TETSIM_E_INVALID, "exchange must be 0 (all-reduce) or 1 (neighbour exchange)");
     if (opt.worldSize > 1 && !opt.ncclUniqueId) return fail(TETSIM_E_INVALID, "worldSize > 1 needs ncclUniqueId");
     for (int64_t c = 0; c < 4 * (int64_t)numTets; c++)
         if (tetIds[c] < 0 || tetIds[c] >= numVerts) return fail(TETSIM_E_INVALID, "tet " + std::to_string(c / 4) + " references vertex " + std::to_string(tetIds[c]) + " outside [0, numVerts)");
@@ -713,7 +750,7 @@ int tetsim_create(const float *verts, int32_t numVerts, const int32_t *tetIds, i
             const int *map = nullptr;
             if (!identity) {
                 c2i.assign((size_t)numVerts, -1);
-                for (int i = 0; i < h->nInt; i++) c2i[h->h_vertId[i]] = i;
+                for (int i = 0; i < h->nInt; i++) if (h->h_vertId[i] >= 0) c2i[h->h_vertId[i]] = i;
                 map = c2i.data();
             }
             std::vector<int4> hi((size_t)numTets);
@@ -761,7 +798,8 @@ void tetsim_destroy(tetsim_t *h) {
     DevBuf<float> *f1[] = {&h->Q9, &h->irv, &h->invMass, &h->invVal, &h->stage3, &h->visPos, &h->visNrm};
     for (auto *b : f1) b->release();
     h->ids.release(); h->I.release(); h->bodies.release(); h->volTerm.release(); h->volOut.release();
-    h->tileTets.release(); h->tileMeta.release(); h->metaOff.release(); h->sp.release(); h->grabP.release(); h->grabScratch.release();
+    h->tileTets.release(); h->tileMeta.release(); h->metaOff.release();
+    h->hxSendIdx.release(); h->hxSrcStart.release(); h->hxSrc.release(); h->hxSend.release(); h->hxRecv.release(); h->sp.release(); h->grabP.release(); h->grabScratch.release();
     if (h->ownStream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -788,7 +826,7 @@ int tetsim_get_resident(tetsim_t *h, uint8_t *out) {
     if (!h || !out) return fail(TETSIM_E_INVALID, "null argument");
     if (h->h_vertId.empty()) { memset(out, 1, (size_t)h->N); return TETSIM_OK; }
     memset(out, 0, (size_t)h->N);
-    for (int v : h->h_vertId) out[v] = 1;
+    for (int v : h->h_vertId) if (v >= 0) out[v] = 1;
     return TETSIM_OK;
 }
 
@@ -995,11 +1033,11 @@ int tetsim_nccl_unique_id(void *out128) {
 
 int tetsim_get_ipc_handle(tetsim_t *h, void *out64) {
     (void)h; (void)out64;
-    return fail(TETSIM_E_STATE, "fused peer-memory exchange is not built yet (TetSimOptions.exchange = 1)");
+    return fail(TETSIM_E_STATE, "fused peer-memory exchange is not built yet");
 }
 int tetsim_set_peers(tetsim_t *h, const void *handles) {
     (void)h; (void)handles;
-    return fail(TETSIM_E_STATE, "fused peer-memory exchange is not built yet (TetSimOptions.exchange = 1)");
+    return fail(TETSIM_E_STATE, "fused peer-memory exchange is not built yet");
 }
 
 int tetsim_level_schedule(const int32_t *tetIds, int32_t numTets, int32_t numVerts, int32_t *level) {

@@ -47,7 +47,7 @@ class _Body:
     def __init__(self, vertices, tetIds, tetEdgeIds, physicsParams, visVerts=None, visTriIds=None, visMaterial=None,
                  world=None, *, solver=None, arithmetic="fast", iters=1, deterministic=True, reference_table_bug=True,
                  reorder=True, cluster_size=256, track_vol_error=None, device=-1, stream=0, rank=0, world_size=1,
-                 nccl_unique_id=None):
+                 nccl_unique_id=None, exchange="allreduce"):
         self.physicsParams = physicsParams if physicsParams is not None else dict(DEFAULT_PHYSICS_PARAMS)
         v = np.ascontiguousarray(vertices, np.float32).reshape(-1)
         t = np.ascontiguousarray(tetIds, np.int32).reshape(-1)
@@ -70,7 +70,8 @@ class _Body:
             deterministic=int(bool(deterministic)), referenceTableBug=int(bool(reference_table_bug)),
             reorder=int(bool(reorder)), clusterSize=int(cluster_size),
             trackVolError=-1 if track_vol_error is None else int(bool(track_vol_error)),
-            device=int(device), rank=int(rank), worldSize=int(world_size), stream=int(stream) or None)
+            device=int(device), rank=int(rank), worldSize=int(world_size), stream=int(stream) or None,
+            exchange={"allreduce": 0, "halo": 1}[exchange])
         if nccl_unique_id is not None:
             self._nccl_id = C.create_string_buffer(bytes(nccl_unique_id), 128)
             opt.ncclUniqueId = C.cast(self._nccl_id, C.c_void_p)

@@ -28,6 +28,7 @@ ap.add_argument("--cells", default="64,16,16")
 ap.add_argument("--substeps", type=int, default=40)
 ap.add_argument("--iters", type=int, default=2)
 ap.add_argument("--cluster-size", type=int, default=256)
+ap.add_argument("--exchange", default="allreduce")
 a = ap.parse_args()
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -47,7 +48,7 @@ nccl_id = bytes(buf.cpu().numpy().tobytes())
 
 pp = dict(ts.DEFAULT_PHYSICS_PARAMS, numSubsteps=20, worldBounds=list(mesh.wide_bounds(16.0)))
 body = ts.SoftBody(v, t, None, pp, solver="jacobi", iters=a.iters, cluster_size=a.cluster_size, device=local,
-                   rank=rank, world_size=world, nccl_unique_id=nccl_id)
+                   rank=rank, world_size=world, nccl_unique_id=nccl_id, exchange=a.exchange)
 info = body.info()
 for _ in range(a.substeps // 20):
     body.step(pp)
