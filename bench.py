@@ -57,8 +57,9 @@ def parse():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong: the same 10M-tet mesh split over N GPUs (BASELINE config 4); weak: beam length x N")
     ap.add_argument("--cpu-substeps", type=int, default=2, help="substeps of the CPU baseline sample (rank 0, N=1)")
-    ap.add_argument("--exchange", default="allreduce", choices=["allreduce", "halo"],
-                    help="multi-GPU boundary exchange: ncclAllReduce over all ranks, or grouped ncclSend/ncclRecv with neighbours")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "allreduce", "halo"],
+                    help="multi-GPU boundary exchange: ncclAllReduce over all ranks, or grouped ncclSend/ncclRecv with the neighbour ranks; "
+                         "auto = all-reduce at 2 GPUs, neighbour exchange beyond (measured 22 %% faster at 8 GPUs, profiles/r1_scaling.md)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -138,6 +139,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.exchange == "auto":
+        args.exchange = "halo" if world > 2 else "allreduce"
     cells = tuple(int(c) for c in args.cells.split(","))
     if args.scaling == "weak":
         cells = (cells[0] * max(world, 1), cells[1], cells[2])
