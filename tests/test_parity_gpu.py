@@ -456,3 +456,59 @@ def test_free_vertices_and_empty_mesh():
     empty = ts.SoftBody(v, np.zeros(0, np.int32), None, None)
     empty.simulate(DT600)
     assert empty.pos[1] < 1.0
+
+
+# ------------------------------------------------------------------------------------------------
+# Full-size configs of BASELINE.json
+# ------------------------------------------------------------------------------------------------
+def test_config5_64_tiled_dragons_with_ground_bitexact(dragon):
+    """BASELINE config 5 (64 copies = 245,760 tets, 78,976 vertices): every copy against the oracle run
+    on the same translated copy, through first floor contact (~substep 63 at dt = 1/600)."""
+    v, t = mesh.tile_bodies(dragon["tet_verts"], dragon["tet_ids"], 8, 8, y_shift=-0.40)
+    wb = list(mesh.wide_bounds(64.0))
+    p = dict(ts.DEFAULT_PHYSICS_PARAMS, worldBounds=wb, numSubsteps=10)
+    ref = oracle.SoftBodyOracle(v, t, worldBounds=wb)
+    sb = ts.SoftBody(v, t, None, p, solver="gs_exact", arithmetic="bitexact")
+    info = sb.info()
+    assert info["numComponents"] == 64 and info["bodyKernel"] == 1 and info["numTets"] == 245760
+    for _ in range(7):
+        sb.step(p)
+        for _ in range(10):
+            ref.simulate(DT600)
+    assert np.any(ref.pos.reshape(-1, 3)[:, 1] == 0.0)
+    assert_bit_equal(sb.pos, ref.pos, "64 dragons pos")
+    assert_bit_equal(sb.vel, ref.vel, "64 dragons vel")
+    fast = ts.SoftBody(v, t, None, p, solver="gs_exact", arithmetic="fast")
+    for _ in range(5):
+        fast.step(p)
+    ref2 = oracle.SoftBodyOracle(v, t, worldBounds=wb)
+    for _ in range(50):
+        ref2.simulate(DT600)
+    x, r = fast.pos.reshape(64, -1, 3), ref2.pos.reshape(64, -1, 3)   # per copy, about the copy's own centre
+    c = r.mean(axis=1, keepdims=True)
+    err = np.max(np.linalg.norm(x - r, axis=2) / np.linalg.norm(r - c + [0, 1, 0], axis=2))
+    assert err <= TOL, err
+
+
+def test_config4_full_size_beam_jacobi():
+    """BASELINE config 4 at full size (10,002,432 tets): two substeps of the tile kernel against the
+    oracle's Jacobi on the same mesh, and the size-independent properties of the step."""
+    v, t = mesh.make_beam()
+    p = dict(ts.DEFAULT_PHYSICS_PARAMS, numSubsteps=2, worldBounds=list(mesh.wide_bounds(64.0)))
+    sb = ts.SoftBody(v, t, None, p, solver="jacobi", track_vol_error=True)
+    assert sb.info()["numTets"] == 10002432 and sb.info()["numVerts"] == 1723800
+    sb.step(p)
+    ref = oracle.SoftBodyOracle(v, t, worldBounds=p["worldBounds"])
+    for _ in range(2):
+        ref.simulate_jacobi(DT1200 * 10, 1)     # frame dt 1/60 over 2 substeps
+    x = sb.pos
+    assert np.isfinite(x).all()
+    assert vec_rel_err(x, ref.pos) <= 1e-5
+    assert abs(sb.volError - ref.volError) < 1e-5
+    # velocity is exactly (x - prev) / dt of the stored state
+    dt = (1.0 / 60.0) / 2
+    np.testing.assert_allclose(sb.vel, (x - sb.prevPos) * np.float32(1.0 / dt), rtol=0, atol=2e-4)
+    # run-to-run reproducibility (no atomics in the default flush)
+    sb2 = ts.SoftBody(v, t, None, p, solver="jacobi")
+    sb2.step(p)
+    assert_bit_equal(sb2.pos, x, "tile kernel is deterministic")
