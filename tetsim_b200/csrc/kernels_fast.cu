@@ -144,10 +144,8 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
         const int nl = reinterpret_cast<const int *>(m)[1];
         const int *ids = reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3]);
         float4 *sx = reinterpret_cast<float4 *>(ws + L.sx(buf));
-        if (!(a.debugSkip & 4)) {
-#pragma unroll 1
+        if (!(a.debugSkip & 4))
             for (int j = tid; j < nl; j += NT) cp_async16(sx + j, a.x4 + ids[j]);
-        }
         cp_async_commit();
     };
 
@@ -210,10 +208,8 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
                     const int nl = reinterpret_cast<const int *>(m)[1];
                     const int *ids = reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3]);
                     float4 *sx = reinterpret_cast<float4 *>(ws + L.sx(buf));
-                    if (!(a.debugSkip & 4)) {
-#pragma unroll 1
+                    if (!(a.debugSkip & 4))
                         for (int j = it; j < nl; j += NI) cp_async16(sx + j, a.x4 + ids[j]);
-                    }
                 }
             }
             cp_async_commit();
@@ -262,25 +258,13 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
         const int v0 = reinterpret_cast<const int *>(m)[0];
         const int nl = reinterpret_cast<const int *>(m)[1];
         const uint16_t *scol = reinterpret_cast<const uint16_t *>(m + 16);
-        if (!(a.debugSkip & 1)) {
-#pragma unroll 1
+        if (!(a.debugSkip & 1))
             for (int j = tid; j < nl; j += NT) {
                 const int val = m[a.metaValOff + j];
                 const unsigned char *base = sdx + j * 16;
                 float ax = 0.0f, ay = 0.0f, az = 0.0f;
-                int i = 0;
-                for (; i + 4 <= val; i += 4) {  // four diagonal offsets per 64-bit shared load
-                    const uint2 o = *reinterpret_cast<const uint2 *>(scol + i);
-                    const float4 d0 = *reinterpret_cast<const float4 *>(base + (o.x & 0xffffu));
-                    const float4 d1 = *reinterpret_cast<const float4 *>(base + (o.x >> 16));
-                    const float4 d2 = *reinterpret_cast<const float4 *>(base + (o.y & 0xffffu));
-                    const float4 d3 = *reinterpret_cast<const float4 *>(base + (o.y >> 16));
-                    ax += d0.x; ay += d0.y; az += d0.z;
-                    ax += d1.x; ay += d1.y; az += d1.z;
-                    ax += d2.x; ay += d2.y; az += d2.z;
-                    ax += d3.x; ay += d3.y; az += d3.z;
-                }
-                for (; i < val; i++) {
+#pragma unroll 4
+                for (int i = 0; i < val; i++) {
                     const float4 d = *reinterpret_cast<const float4 *>(base + scol[i]);
                     ax += d.x; ay += d.y; az += d.z;
                 }
@@ -288,7 +272,6 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
                                      make_float4(ax, ay, az, 0.0f));
                 else a.part[v0 + j] = make_float4(ax, ay, az, 0.0f);
             }
-        }
     }
 }
 
