@@ -56,7 +56,7 @@ def parse():
     ap.add_argument("--atomic", action="store_true", help="deterministic=0: REDG flush instead of per-tile partials")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong: the same 10M-tet mesh split over N GPUs (BASELINE config 4); weak: beam length x N")
-    ap.add_argument("--cpu-substeps", type=int, default=2, help="substeps of the CPU baseline sample (rank 0, N=1)")
+    ap.add_argument("--cpu-substeps", type=int, default=6, help="substeps of the CPU baseline sample (rank 0, N=1)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "allreduce", "halo"],
                     help="multi-GPU boundary exchange: ncclAllReduce over all ranks, or grouped ncclSend/ncclRecv with the neighbour ranks; "
                          "auto = all-reduce at 2 GPUs, neighbour exchange beyond (measured 22 %% faster at 8 GPUs, profiles/r1_scaling.md)")

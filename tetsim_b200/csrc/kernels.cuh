@@ -241,11 +241,33 @@ __global__ void k_gs_body(const BodyDesc *__restrict__ bodies, const int *__rest
         }
         sx[j] = x;
     }
+    // this body's level offsets -> shared memory (one pointer chase fewer per level)
+    int *sLevel = reinterpret_cast<int *>(sx + nv);
+    const int nLev = bd.levelEnd - bd.levelBegin;
+    for (int j = tid; j <= nLev; j += nt) sLevel[j] = levelStart[bd.levelBegin + j];
     __syncthreads();
-    // level sweep
-    for (int l = bd.levelBegin; l < bd.levelEnd; l++) {
-        const int b = levelStart[l], e = levelStart[l + 1];
-        for (int t = b + tid; t < e; t += nt) {
+    // level sweep.  A level is a handful of tets (Dragon: <= 22), so the sweep is a chain of ~700
+    // dependent steps and each step's record fetch (HBM/L2, ~1 us) would sit on the critical path:
+    // the first record of level l+1 is loaded into registers before level l is solved.
+    int4 rI = make_int4(0, 0, 0, 0);
+    float4 rA = make_float4(0.f, 0.f, 0.f, 0.f), rB = rA, rC = rA;
+    if (nLev > 0 && sLevel[0] + tid < sLevel[1]) {
+        const int t = sLevel[0] + tid;
+        rI = I[t]; rA = ldg4(A + t); rB = ldg4(B + t); rC = ldg4(C + t);
+    }
+    for (int l = 0; l < nLev; l++) {
+        const int b = sLevel[l], e = sLevel[l + 1];
+        const int4 cI = rI;
+        const float4 cA = rA, cB = rB, cC = rC;
+        if (l + 1 < nLev && e + tid < sLevel[l + 2]) {  // prefetch for the next level
+            const int t = e + tid;
+            rI = I[t]; rA = ldg4(A + t); rB = ldg4(B + t); rC = ldg4(C + t);
+        }
+        if (b + tid < e) {
+            double vm1 = gs_solve_one<EXACT>(sx, cI, cA, cB, cC, sp);
+            if (volTerm) volTerm[order[b + tid]] = vm1;
+        }
+        for (int t = b + tid + nt; t < e; t += nt) {  // levels wider than the CTA (rare)
             double vm1 = gs_solve_one<EXACT>(sx, I[t], ldg4(A + t), ldg4(B + t), ldg4(C + t), sp);
             if (volTerm) volTerm[order[t]] = vm1;
         }

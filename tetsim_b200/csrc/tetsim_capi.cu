@@ -236,7 +236,8 @@ int build_gs(tetsim *h, const std::vector<float> &verts, const std::vector<int> 
     int maxCompVerts = 0;
     for (int c : compVerts) maxCompVerts = std::max(maxCompVerts, c);
     const char *forceLevel = getenv("TETSIM_FORCE_LEVEL_KERNEL");
-    h->bodyKernel = (size_t)maxCompVerts * sizeof(float4) <= (size_t)h->K->gs_body_max_smem() && !(forceLevel && forceLevel[0] == '1');
+    // vertices (16 B each) + the body's level table (at most numLevels + 1 ints) must fit in one CTA's shared memory
+    h->bodyKernel = (size_t)maxCompVerts * sizeof(float4) + ((size_t)nl + 1) * sizeof(int) <= (size_t)h->K->gs_body_max_smem() && !(forceLevel && forceLevel[0] == '1');
 
     // internal vertex numbering: bodies contiguous
     std::vector<int> c2i((size_t)N);
@@ -297,7 +298,9 @@ int build_gs(tetsim *h, const std::vector<float> &verts, const std::vector<int> 
         h->numLevels = nl;
         h->bodyThreads = maxCompVerts > 512 ? 128 : 64;
         h->bodyThreads = std::max(h->bodyThreads, std::min(256, 32 * ((h->maxLevelSize + 31) / 32)));
-        h->bodySmem = (size_t)maxCompVerts * sizeof(float4);
+        int maxBodyLevels = 0;
+        for (const BodyDesc &bd : bodies) maxBodyLevels = std::max(maxBodyLevels, bd.levelEnd - bd.levelBegin);
+        h->bodySmem = (size_t)maxCompVerts * sizeof(float4) + ((size_t)maxBodyLevels + 1) * sizeof(int);
         h->launchesPerSubstep = 1;
     } else {
         int lastLevel = -1, runStart = 0;
