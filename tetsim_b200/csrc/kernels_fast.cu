@@ -289,6 +289,15 @@ __global__ void __launch_bounds__(T, MINB) k_jacobi_tiles(TileArgs a) {
     tile_worker<T, 1, S, false>(a, smem, threadIdx.x, a.tileBegin + blockIdx.x, gridDim.x);
 }
 
+// Same, two tets per thread (T/2 threads per tile): per-tile overhead is shared by twice the tets and
+// every thread carries two independent dependency chains.
+template <int T, int S, int MINB>
+__global__ void __launch_bounds__(T / 2, MINB) k_jacobi_tiles2(TileArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    if (a.tileBegin + (int)blockIdx.x >= a.numTiles) return;
+    tile_worker<T / 2, 2, S, false>(a, smem, threadIdx.x, a.tileBegin + blockIdx.x, gridDim.x);
+}
+
 // Warp tiles: every warp is its own worker with private staging and mbarriers (tile = 32 * TPL tets);
 // no block-level barrier anywhere, so warps drift apart and cover each other's load and sum phases.
 template <int TPL, int S>
@@ -313,16 +322,20 @@ static int tile_stages(int clusterSize) {
 size_t jacobi_tiles_smem(int clusterSize, const TileArgs &a) {
     const int S = tile_stages(clusterSize);
 #define TS_CASE(T_) case T_: return S == 2 ? tile_smem_bytes<T_, 2>(a) : (S == 3 ? tile_smem_bytes<T_, 3>(a) : tile_smem_bytes<T_, 4>(a));
-    switch (clusterSize) { TS_CASE(32) TS_CASE(64) TS_CASE(128) TS_CASE(256) default: return tile_smem_bytes<512, 2>(a); }
+    switch (clusterSize) { TS_CASE(32) TS_CASE(64) TS_CASE(128) TS_CASE(256) TS_CASE(512) default: return 0; }
 #undef TS_CASE
 }
 
+// Launch configuration is cached per (kernel instantiation, device): attributes such as the dynamic
+// shared-memory opt-in are per device, and a process may hold handles on several GPUs.
 struct LaunchCache { size_t smem = 0; int n = 0, sms = 0; };
+static int current_device() { int d = 0; cudaGetDevice(&d); return d < 0 || d >= 64 ? 0 : d; }
 
 template <int T, int S, int MINB>
 static void launch_tiles_T(cudaStream_t s, const TileArgs &a) {
     const size_t smem = tile_smem_bytes<T, S>(a);
-    static LaunchCache lc;
+    static LaunchCache cache[64];
+    LaunchCache &lc = cache[current_device()];
     if (smem != lc.smem) {
         cudaFuncSetAttribute(k_jacobi_tiles<T, S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lc.n, k_jacobi_tiles<T, S, MINB>, T, smem);
@@ -337,11 +350,31 @@ static void launch_tiles_T(cudaStream_t s, const TileArgs &a) {
     k_jacobi_tiles<T, S, MINB><<<grid, T, smem, s>>>(a);
 }
 
+template <int T, int S, int MINB>
+static void launch_tiles2_T(cudaStream_t s, const TileArgs &a) {
+    const size_t smem = tile_smem_bytes<T, S>(a);
+    static LaunchCache cache[64];
+    LaunchCache &lc = cache[current_device()];
+    if (smem != lc.smem) {
+        cudaFuncSetAttribute(k_jacobi_tiles2<T, S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lc.n, k_jacobi_tiles2<T, S, MINB>, T / 2, smem);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&lc.sms, cudaDevAttrMultiProcessorCount, dev);
+        if (lc.n < 1) lc.n = 1;
+        lc.smem = smem;
+    }
+    int grid = lc.sms * lc.n;
+    if (grid > a.numTiles - a.tileBegin) grid = a.numTiles - a.tileBegin;
+    k_jacobi_tiles2<T, S, MINB><<<grid, T / 2, smem, s>>>(a);
+}
+
 // Warp tiles: one CTA per SM holding as many warps as shared memory and registers allow.
 template <int TPL, int S>
 static void launch_warptiles(cudaStream_t s, const TileArgs &a) {
     const size_t perWarp = tile_smem_bytes<32 * TPL, S>(a);
-    static LaunchCache lc;
+    static LaunchCache cache[64];
+    LaunchCache &lc = cache[current_device()];
     if (perWarp != lc.smem) {
         int dev = 0, maxSmem = 0;
         cudaGetDevice(&dev);
@@ -367,6 +400,10 @@ static void launch_warptiles(cudaStream_t s, const TileArgs &a) {
 void launch_jacobi_tiles(cudaStream_t s, int clusterSize, const TileArgs &a) {
     if (a.numTiles - a.tileBegin <= 0) return;
     const int S = tile_stages(clusterSize);
+    if (const char *e = getenv("TETSIM_TILE_TPT")) {  // experiment switch: two tets per thread
+        if (atoi(e) == 2 && clusterSize == 256) { S == 2 ? launch_tiles2_T<256, 2, 4>(s, a) : launch_tiles2_T<256, 3, 4>(s, a); return; }
+        if (atoi(e) == 2 && clusterSize == 512) { S == 2 ? launch_tiles2_T<512, 2, 2>(s, a) : launch_tiles2_T<512, 3, 2>(s, a); return; }
+    }
     switch (clusterSize) {
         case 32: S == 2 ? launch_warptiles<1, 2>(s, a) : (S == 3 ? launch_warptiles<1, 3>(s, a) : launch_warptiles<1, 4>(s, a)); break;
         case 64: S == 2 ? launch_warptiles<2, 2>(s, a) : (S == 3 ? launch_warptiles<2, 3>(s, a) : launch_warptiles<2, 4>(s, a)); break;

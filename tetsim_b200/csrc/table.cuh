@@ -37,10 +37,13 @@ struct Launchers {
                         const float4 *A, const float4 *B, const float4 *C, const int *order, double *volTerm,
                         const SubstepParams *sp, const int *vertId) {
         if (numBodies <= 0) return;
-        static size_t configured = 0;
-        if (smemBytes > 48 * 1024 && smemBytes > configured) {
+        static size_t configured[64] = {0};  // per device: the opt-in is a per-device function attribute
+        int dev = 0;
+        cudaGetDevice(&dev);
+        size_t &c = configured[dev < 0 || dev >= 64 ? 0 : dev];
+        if (smemBytes > 48 * 1024 && smemBytes > c) {
             cudaFuncSetAttribute(k_gs_body<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
-            configured = smemBytes;
+            c = smemBytes;
         }
         k_gs_body<E><<<numBodies, threads, smemBytes, s>>>(bodies, levelStart, x4, prev4, vel4, I, A, B, C, order,
                                                           volTerm, sp, vertId);

@@ -82,9 +82,13 @@ NcclApi g_nccl;
 constexpr int kNcclFloat = 7, kNcclSum = 0;
 
 template <class T>
-struct DevBuf {
+struct DevBuf {  // owning device array; frees on scope exit so early error returns do not leak
     T *p = nullptr;
     size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
     cudaError_t alloc(size_t count) {
         release();
         n = count;
