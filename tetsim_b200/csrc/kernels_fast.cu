@@ -289,13 +289,13 @@ __global__ void __launch_bounds__(T, MINB) k_jacobi_tiles(TileArgs a) {
     tile_worker<T, 1, S, false>(a, smem, threadIdx.x, a.tileBegin + blockIdx.x, gridDim.x);
 }
 
-// Same, two tets per thread (T/2 threads per tile): per-tile overhead is shared by twice the tets and
-// every thread carries two independent dependency chains.
-template <int T, int S, int MINB>
-__global__ void __launch_bounds__(T / 2, MINB) k_jacobi_tiles2(TileArgs a) {
+// Same with TPT tets per thread (T/TPT threads per tile): per-tile overhead (barriers, prefetch issue,
+// loop control) is shared by TPT times the tets and every thread carries TPT independent chains.
+template <int T, int TPT, int S, int MINB>
+__global__ void __launch_bounds__(T / TPT, MINB) k_jacobi_tilesN(TileArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     if (a.tileBegin + (int)blockIdx.x >= a.numTiles) return;
-    tile_worker<T / 2, 2, S, false>(a, smem, threadIdx.x, a.tileBegin + blockIdx.x, gridDim.x);
+    tile_worker<T / TPT, TPT, S, false>(a, smem, threadIdx.x, a.tileBegin + blockIdx.x, gridDim.x);
 }
 
 // Warp tiles: every warp is its own worker with private staging and mbarriers (tile = 32 * TPL tets);
@@ -350,14 +350,14 @@ static void launch_tiles_T(cudaStream_t s, const TileArgs &a) {
     k_jacobi_tiles<T, S, MINB><<<grid, T, smem, s>>>(a);
 }
 
-template <int T, int S, int MINB>
-static void launch_tiles2_T(cudaStream_t s, const TileArgs &a) {
+template <int T, int TPT, int S, int MINB>
+static void launch_tilesN(cudaStream_t s, const TileArgs &a) {
     const size_t smem = tile_smem_bytes<T, S>(a);
     static LaunchCache cache[64];
     LaunchCache &lc = cache[current_device()];
     if (smem != lc.smem) {
-        cudaFuncSetAttribute(k_jacobi_tiles2<T, S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lc.n, k_jacobi_tiles2<T, S, MINB>, T / 2, smem);
+        cudaFuncSetAttribute(k_jacobi_tilesN<T, TPT, S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lc.n, k_jacobi_tilesN<T, TPT, S, MINB>, T / TPT, smem);
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&lc.sms, cudaDevAttrMultiProcessorCount, dev);
@@ -366,7 +366,7 @@ static void launch_tiles2_T(cudaStream_t s, const TileArgs &a) {
     }
     int grid = lc.sms * lc.n;
     if (grid > a.numTiles - a.tileBegin) grid = a.numTiles - a.tileBegin;
-    k_jacobi_tiles2<T, S, MINB><<<grid, T / 2, smem, s>>>(a);
+    k_jacobi_tilesN<T, TPT, S, MINB><<<grid, T / TPT, smem, s>>>(a);
 }
 
 // Warp tiles: one CTA per SM holding as many warps as shared memory and registers allow.
@@ -400,9 +400,13 @@ static void launch_warptiles(cudaStream_t s, const TileArgs &a) {
 void launch_jacobi_tiles(cudaStream_t s, int clusterSize, const TileArgs &a) {
     if (a.numTiles - a.tileBegin <= 0) return;
     const int S = tile_stages(clusterSize);
-    if (const char *e = getenv("TETSIM_TILE_TPT")) {  // experiment switch: two tets per thread
-        if (atoi(e) == 2 && clusterSize == 256) { S == 2 ? launch_tiles2_T<256, 2, 4>(s, a) : launch_tiles2_T<256, 3, 4>(s, a); return; }
-        if (atoi(e) == 2 && clusterSize == 512) { S == 2 ? launch_tiles2_T<512, 2, 2>(s, a) : launch_tiles2_T<512, 3, 2>(s, a); return; }
+    if (const char *e = getenv("TETSIM_TILE_TPT")) {  // experiment switch: tets per thread
+        const int tpt = atoi(e);
+        if (tpt == 2 && clusterSize == 128) { launch_tilesN<128, 2, 2, 8>(s, a); return; }
+        if (tpt == 2 && clusterSize == 256) { S == 2 ? launch_tilesN<256, 2, 2, 4>(s, a) : launch_tilesN<256, 2, 3, 4>(s, a); return; }
+        if (tpt == 2 && clusterSize == 512) { S == 2 ? launch_tilesN<512, 2, 2, 2>(s, a) : launch_tilesN<512, 2, 3, 2>(s, a); return; }
+        if (tpt == 4 && clusterSize == 256) { launch_tilesN<256, 4, 2, 4>(s, a); return; }
+        if (tpt == 4 && clusterSize == 512) { launch_tilesN<512, 4, 2, 2>(s, a); return; }
     }
     switch (clusterSize) {
         case 32: S == 2 ? launch_warptiles<1, 2>(s, a) : (S == 3 ? launch_warptiles<1, 3>(s, a) : launch_warptiles<1, 4>(s, a)); break;
