@@ -291,8 +291,9 @@ __global__ void __launch_bounds__(T, MINB) k_jacobi_tiles(TileArgs a) {
 
 // Same with TPT tets per thread (T/TPT threads per tile): per-tile overhead (barriers, prefetch issue,
 // loop control) is shared by TPT times the tets and every thread carries TPT independent chains.
+constexpr int tilesN_minb(int T, int TPT, int MINB) { return MINB > 0 ? MINB : 1024 / T; }
 template <int T, int TPT, int S, int MINB>
-__global__ void __launch_bounds__(T / TPT, MINB) k_jacobi_tilesN(TileArgs a) {
+__global__ void __launch_bounds__(T / TPT, tilesN_minb(T, TPT, MINB)) k_jacobi_tilesN(TileArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     if (a.tileBegin + (int)blockIdx.x >= a.numTiles) return;
     tile_worker<T / TPT, TPT, S, false>(a, smem, threadIdx.x, a.tileBegin + blockIdx.x, gridDim.x);
@@ -400,13 +401,16 @@ static void launch_warptiles(cudaStream_t s, const TileArgs &a) {
 void launch_jacobi_tiles(cudaStream_t s, int clusterSize, const TileArgs &a) {
     if (a.numTiles - a.tileBegin <= 0) return;
     const int S = tile_stages(clusterSize);
-    if (const char *e = getenv("TETSIM_TILE_TPT")) {  // experiment switch: tets per thread
+    if (const char *e = getenv("TETSIM_TILE_TPT")) {  // experiment switch: tets per thread (and CTAs per SM the registers are capped for)
         const int tpt = atoi(e);
-        if (tpt == 2 && clusterSize == 128) { launch_tilesN<128, 2, 2, 8>(s, a); return; }
-        if (tpt == 2 && clusterSize == 256) { S == 2 ? launch_tilesN<256, 2, 2, 4>(s, a) : launch_tilesN<256, 2, 3, 4>(s, a); return; }
-        if (tpt == 2 && clusterSize == 512) { S == 2 ? launch_tilesN<512, 2, 2, 2>(s, a) : launch_tilesN<512, 2, 3, 2>(s, a); return; }
-        if (tpt == 4 && clusterSize == 256) { launch_tilesN<256, 4, 2, 4>(s, a); return; }
-        if (tpt == 4 && clusterSize == 512) { launch_tilesN<512, 4, 2, 2>(s, a); return; }
+        int minb = 0;
+        if (const char *m = getenv("TETSIM_TILE_MINB")) minb = atoi(m);
+#define TN_CASE(T_, TPT_, S_, MINB_) if (clusterSize == T_ && tpt == TPT_ && S == S_ && minb == MINB_) { launch_tilesN<T_, TPT_, S_, MINB_>(s, a); return; }
+        TN_CASE(128, 2, 2, 0) TN_CASE(128, 2, 3, 0)
+        TN_CASE(256, 2, 2, 0) TN_CASE(256, 2, 3, 0) TN_CASE(256, 2, 2, 6) TN_CASE(256, 2, 3, 6)
+        TN_CASE(512, 2, 2, 0) TN_CASE(512, 2, 3, 0) TN_CASE(512, 2, 2, 3) TN_CASE(512, 2, 3, 3)
+        TN_CASE(256, 4, 2, 0) TN_CASE(256, 4, 3, 0) TN_CASE(512, 4, 2, 0) TN_CASE(512, 4, 3, 0)
+#undef TN_CASE
     }
     switch (clusterSize) {
         case 32: S == 2 ? launch_warptiles<1, 2>(s, a) : (S == 3 ? launch_warptiles<1, 3>(s, a) : launch_warptiles<1, 4>(s, a)); break;
