@@ -237,6 +237,51 @@ __device__ __forceinline__ float nh_solve_fast_metric(V3 p[4], const float w[4],
     return vol - 1.0f;
 }
 
+// Same two projections as nh_solve_fast_metric, restated for the tile kernel's inner loop: returns the four corner
+// displacements d[i] = x_i(after both projections) - q[i] directly (the kernel scatters displacements, so the
+// positions themselves are never rebuilt), the second stage works on the edge matrix only
+// (P'_k = P_k + d_k - d_0), the gradient of corner 0 is kept with flipped sign (nG0 = G1 + G2 + G3, the sign goes
+// into its scale) and both step scales are branch-free (reciprocal always formed, result selected):
+// ~178 FP instructions, no divergent code.  VOL = false drops the det F - 1 sample.
+__device__ __forceinline__ float rcp_approx(float x) {  // MUFU.RCP, no range fix-up (the result is selected away when unusable)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+template <bool VOL>
+__device__ __forceinline__ float nh_solve_tile(const V3 q[4], const float w[4], const float Bm[6], float irv, float detQ,
+                                               float alphaDev, float alphaVol, float gammaVol, V3 d[4]) {
+    V3 P0 = q[1] - q[0], P1 = q[2] - q[0], P2 = q[3] - q[0];
+    V3 G1 = fma3(P2, Bm[2], fma3(P1, Bm[1], P0 * Bm[0]));
+    V3 G2 = fma3(P2, Bm[4], fma3(P1, Bm[3], P0 * Bm[1]));
+    V3 G3 = fma3(P2, Bm[5], fma3(P1, Bm[4], P0 * Bm[2]));
+    float rs2 = P0.x * G1.x;
+    rs2 = fmaf(P0.y, G1.y, rs2); rs2 = fmaf(P0.z, G1.z, rs2);
+    rs2 = fmaf(P1.x, G2.x, rs2); rs2 = fmaf(P1.y, G2.y, rs2); rs2 = fmaf(P1.z, G2.z, rs2);
+    rs2 = fmaf(P2.x, G3.x, rs2); rs2 = fmaf(P2.y, G3.y, rs2); rs2 = fmaf(P2.z, G3.z, rs2);
+    const V3 nG0 = {G1.x + G2.x + G3.x, G1.y + G2.y + G3.y, G1.z + G2.z + G3.z};
+    const float wG = fmaf(w[3], dot(G3, G3), fmaf(w[2], dot(G2, G2), fmaf(w[1], dot(G1, G1), w[0] * dot(nG0, nG0))));
+    const float r1 = rs2 * rcp_approx(fmaf(alphaDev * irv, rs2, wG));
+    const float s = (rs2 > 0.0f && wG > 0.0f) ? -r1 : 0.0f;
+    const float s1 = s * w[1], s2 = s * w[2], s3 = s * w[3];
+    const V3 d0 = nG0 * (-(s * w[0]));
+    // edges after the deviatoric projection
+    P0 = fma3(G1, s1, P0) - d0; P1 = fma3(G2, s2, P1) - d0; P2 = fma3(G3, s3, P2) - d0;
+    const V3 c1 = cross(P1, P2), c2 = cross(P2, P0), c3 = cross(P0, P1);
+    const float vol = dot(P0, c1) * detQ;
+    const V3 nc0 = {c1.x + c2.x + c3.x, c1.y + c2.y + c3.y, c1.z + c2.z + c3.z};
+    const float wC = fmaf(w[3], dot(c3, c3), fmaf(w[2], dot(c2, c2), fmaf(w[1], dot(c1, c1), w[0] * dot(nc0, nc0))));
+    const float C = vol - gammaVol;
+    // true gradients are detQ * c_i:  dlambda = -C / (detQ^2 wC + alpha);  step_i = c_i * (detQ * dlambda * w_i)
+    const float r2 = (C * detQ) * rcp_approx(fmaf(detQ * detQ, wC, alphaVol * irv));
+    const float t = (C != 0.0f && wC > 0.0f) ? -r2 : 0.0f;
+    d[0] = fma3(nc0, -(t * w[0]), d0);
+    d[1] = fma3(c1, t * w[1], G1 * s1);
+    d[2] = fma3(c2, t * w[2], G2 * s2);
+    d[3] = fma3(c3, t * w[3], G3 * s3);
+    return VOL ? vol - 1.0f : 0.0f;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Polar-decomposition shape matching (src/SoftbodyGPU.js:80-262), f32.
 // EXACT: every op separately rounded (TU compiled -fmad=false), IEEE div/sqrt, sin via double.

@@ -108,10 +108,12 @@ __device__ __forceinline__ void cp_async_wait_pending() { asm volatile("cp.async
 // first, first + stride, ...  NT = threads of the worker, TPT = tets per thread, T = NT * TPT.
 // S-stage ring: at tile k the tet block and vertex gather of tile k+S-1 and the meta block of tile
 // k+S are put in flight, so S-1 tiles of HBM/L2 latency are covered by math.
-template <int NT, int TPT, int S, bool WARP_SCOPE>
+template <int NT, int TPT, int S, bool WARP_SCOPE, bool DBG = false>
 __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws, const int tid, const int first,
                                             const int stride) {
     constexpr int T = NT * TPT;
+    const int dbg = DBG ? a.debugSkip : 0;  // ablation switches exist only in the DBG instantiation (tetsim_time_kernel)
+    const bool trackVol = a.volAcc != nullptr;
     const TileSmem<T, S> L(a.metaStride, a.maxTileVertsPad);
     uint64_t *metaFull = reinterpret_cast<uint64_t *>(ws + L.bars);  // [S + 1]
     unsigned char *const sdx = ws + L.sdx;
@@ -144,7 +146,7 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
         const int nl = reinterpret_cast<const int *>(m)[1];
         const int *ids = reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3]);
         float4 *sx = reinterpret_cast<float4 *>(ws + L.sx(buf));
-        if (!(a.debugSkip & 4))
+        if (!(dbg & 4))
             for (int j = tid; j < nl; j += NT) cp_async16(sx + j, a.x4 + ids[j]);
         cp_async_commit();
     };
@@ -177,7 +179,7 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
 #pragma unroll
         for (int u = 0; u < TPT; u++) {
             const int t = tid + NT * u;
-            if (a.debugSkip & 8) {  // measurement only: synthetic record, no HBM stream
+            if (dbg & 8) {  // measurement only: synthetic record, no HBM stream
                 const float f = 1.0f + 1e-3f * (float)(t & 7);
                 rA[u] = make_float4(f, 0.01f, 0.02f, f); rB[u] = make_float4(0.03f, f, 6.0f, 1.0f);
                 rC[u] = make_float4(__uint_as_float(((t * 16) & 0x3ff) | (((t * 16 + 16) & 0x3ff) << 16)),
@@ -208,7 +210,7 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
                     const int nl = reinterpret_cast<const int *>(m)[1];
                     const int *ids = reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3]);
                     float4 *sx = reinterpret_cast<float4 *>(ws + L.sx(buf));
-                    if (!(a.debugSkip & 4))
+                    if (!(dbg & 4))
                         for (int j = it; j < nl; j += NI) cp_async16(sx + j, a.x4 + ids[j]);
                 }
             }
@@ -234,18 +236,20 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
             const float4 q1 = *reinterpret_cast<const float4 *>(sxb + (s01 >> 16));
             const float4 q2 = *reinterpret_cast<const float4 *>(sxb + (s23 & 0xffffu));
             const float4 q3 = *reinterpret_cast<const float4 *>(sxb + (s23 >> 16));
-            V3 p[4] = {{q0.x, q0.y, q0.z}, {q1.x, q1.y, q1.z}, {q2.x, q2.y, q2.z}, {q3.x, q3.y, q3.z}};
+            const V3 q[4] = {{q0.x, q0.y, q0.z}, {q1.x, q1.y, q1.z}, {q2.x, q2.y, q2.z}, {q3.x, q3.y, q3.z}};
             const float w[4] = {q0.w, q1.w, q2.w, q3.w};
             const float Bm[6] = {A.x, A.y, A.z, A.w, B.x, B.y};
-            const float vm1 = (a.debugSkip & 2) ? 0.0f : nh_solve_fast_metric(p, w, Bm, B.z, B.w, alphaDev, alphaVol, gammaVol);
-            if ((a.debugSkip & 16) && p[0].x + p[1].y + p[2].z + p[3].x != 123.456f) continue;  // measurement only: no scatter
-            *reinterpret_cast<float4 *>(sdx + (D.x & 0xffffu)) = make_float4(p[0].x - q0.x, p[0].y - q0.y, p[0].z - q0.z, 0.f);
-            *reinterpret_cast<float4 *>(sdx + (D.x >> 16)) = make_float4(p[1].x - q1.x, p[1].y - q1.y, p[1].z - q1.z, 0.f);
-            *reinterpret_cast<float4 *>(sdx + (D.y & 0xffffu)) = make_float4(p[2].x - q2.x, p[2].y - q2.y, p[2].z - q2.z, 0.f);
-            *reinterpret_cast<float4 *>(sdx + (D.y >> 16)) = make_float4(p[3].x - q3.x, p[3].y - q3.y, p[3].z - q3.z, 0.f);
-            vsum += (B.z != 0.0f) ? vm1 : 0.0f;  // padding records carry invRestVolume = 0
+            V3 d[4] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+            float vm1 = 0.0f;
+            if (!(dbg & 2)) vm1 = nh_solve_tile<true>(q, w, Bm, B.z, B.w, alphaDev, alphaVol, gammaVol, d);
+            if ((dbg & 16) && d[0].x + d[1].y + d[2].z + d[3].x != 123.456f) continue;  // measurement only: no scatter
+            *reinterpret_cast<float4 *>(sdx + (D.x & 0xffffu)) = make_float4(d[0].x, d[0].y, d[0].z, 0.f);
+            *reinterpret_cast<float4 *>(sdx + (D.x >> 16)) = make_float4(d[1].x, d[1].y, d[1].z, 0.f);
+            *reinterpret_cast<float4 *>(sdx + (D.y & 0xffffu)) = make_float4(d[2].x, d[2].y, d[2].z, 0.f);
+            *reinterpret_cast<float4 *>(sdx + (D.y >> 16)) = make_float4(d[3].x, d[3].y, d[3].z, 0.f);
+            if (trackVol) vsum += (B.z != 0.0f) ? vm1 : 0.0f;  // padding records carry invRestVolume = 0
         }
-        if (a.volAcc) {  // volError (src/Softbody.js:163): warp-reduce, one double atomic per warp
+        if (trackVol) {  // volError (src/Softbody.js:163): warp-reduce, one double atomic per warp
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
             if ((tid & 31) == 0) atomicAdd(a.volAcc, (double)vsum);
@@ -258,7 +262,7 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
         const int v0 = reinterpret_cast<const int *>(m)[0];
         const int nl = reinterpret_cast<const int *>(m)[1];
         const uint16_t *scol = reinterpret_cast<const uint16_t *>(m + 16);
-        if (!(a.debugSkip & 1))
+        if (!(dbg & 1))
             for (int j = tid; j < nl; j += NT) {
                 const int val = m[a.metaValOff + j];
                 const unsigned char *base = sdx + j * 16;
@@ -275,8 +279,9 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
     }
 }
 
-// CTA tiles: T tets per tile, one tet per thread, two __syncthreads per tile.
-template <int T, int S, int MINB>
+// CTA tiles: T tets per tile, one tet per thread, two __syncthreads per tile.  DBG = true compiles the ablation
+// switches of TileArgs::debugSkip in (tetsim_time_kernel with TETSIM_TILE_DEBUG only).
+template <int T, int S, int MINB, bool DBG = false>
 __global__ void __launch_bounds__(T, MINB) k_jacobi_tiles(TileArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     if (a.tileBegin + (int)blockIdx.x >= a.numTiles) return;
@@ -286,7 +291,7 @@ __global__ void __launch_bounds__(T, MINB) k_jacobi_tiles(TileArgs a) {
         const unsigned slot = blockIdx.x / (unsigned)sms;
         if (slot) __nanosleep(slot * (unsigned)a.staggerNs);
     }
-    tile_worker<T, 1, S, false>(a, smem, threadIdx.x, a.tileBegin + blockIdx.x, gridDim.x);
+    tile_worker<T, 1, S, false, DBG>(a, smem, threadIdx.x, a.tileBegin + blockIdx.x, gridDim.x);
 }
 
 // Same with TPT tets per thread (T/TPT threads per tile): per-tile overhead (barriers, prefetch issue,
@@ -332,14 +337,14 @@ size_t jacobi_tiles_smem(int clusterSize, const TileArgs &a) {
 struct LaunchCache { size_t smem = 0; int n = 0, sms = 0; };
 static int current_device() { int d = 0; cudaGetDevice(&d); return d < 0 || d >= 64 ? 0 : d; }
 
-template <int T, int S, int MINB>
+template <int T, int S, int MINB, bool DBG = false>
 static void launch_tiles_T(cudaStream_t s, const TileArgs &a) {
     const size_t smem = tile_smem_bytes<T, S>(a);
     static LaunchCache cache[64];
     LaunchCache &lc = cache[current_device()];
     if (smem != lc.smem) {
-        cudaFuncSetAttribute(k_jacobi_tiles<T, S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lc.n, k_jacobi_tiles<T, S, MINB>, T, smem);
+        cudaFuncSetAttribute(k_jacobi_tiles<T, S, MINB, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lc.n, k_jacobi_tiles<T, S, MINB, DBG>, T, smem);
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&lc.sms, cudaDevAttrMultiProcessorCount, dev);
@@ -348,7 +353,7 @@ static void launch_tiles_T(cudaStream_t s, const TileArgs &a) {
     }
     int grid = lc.sms * lc.n;  // persistent: every CTA resident, tiles strided over the grid
     if (grid > a.numTiles - a.tileBegin) grid = a.numTiles - a.tileBegin;
-    k_jacobi_tiles<T, S, MINB><<<grid, T, smem, s>>>(a);
+    k_jacobi_tiles<T, S, MINB, DBG><<<grid, T, smem, s>>>(a);
 }
 
 template <int T, int TPT, int S, int MINB>
@@ -401,6 +406,7 @@ static void launch_warptiles(cudaStream_t s, const TileArgs &a) {
 void launch_jacobi_tiles(cudaStream_t s, int clusterSize, const TileArgs &a) {
     if (a.numTiles - a.tileBegin <= 0) return;
     const int S = tile_stages(clusterSize);
+    if (a.debugSkip && clusterSize == 256) { launch_tiles_T<256, 3, 4, true>(s, a); return; }  // ablations: one instantiation
     if (const char *e = getenv("TETSIM_TILE_TPT")) {  // experiment switch: tets per thread (and CTAs per SM the registers are capped for)
         const int tpt = atoi(e);
         int minb = 0;
@@ -408,8 +414,8 @@ void launch_jacobi_tiles(cudaStream_t s, int clusterSize, const TileArgs &a) {
 #define TN_CASE(T_, TPT_, S_, MINB_) if (clusterSize == T_ && tpt == TPT_ && S == S_ && minb == MINB_) { launch_tilesN<T_, TPT_, S_, MINB_>(s, a); return; }
         TN_CASE(128, 2, 2, 0) TN_CASE(128, 2, 3, 0)
         TN_CASE(256, 2, 2, 0) TN_CASE(256, 2, 3, 0) TN_CASE(256, 2, 2, 6) TN_CASE(256, 2, 3, 6)
-        TN_CASE(512, 2, 2, 0) TN_CASE(512, 2, 3, 0) TN_CASE(512, 2, 2, 3) TN_CASE(512, 2, 3, 3)
-        TN_CASE(256, 4, 2, 0) TN_CASE(256, 4, 3, 0) TN_CASE(512, 4, 2, 0) TN_CASE(512, 4, 3, 0)
+        TN_CASE(512, 2, 2, 0) TN_CASE(512, 2, 3, 0) TN_CASE(512, 2, 2, 3) TN_CASE(512, 2, 3, 3) TN_CASE(512, 2, 2, 4)
+        TN_CASE(256, 4, 2, 0) TN_CASE(256, 4, 3, 0) TN_CASE(512, 4, 2, 0) TN_CASE(512, 4, 3, 0) TN_CASE(512, 4, 2, 3)
 #undef TN_CASE
     }
     switch (clusterSize) {

@@ -346,6 +346,42 @@ bool build_cluster_plan(int numVerts, int numTets, const int *tetIds, const std:
             }
         }
         P.hxSrcStart[nB] = (int)P.hxSrc.size();
+        // peer-memory exchange: where my entries land in each sharer's receive buffer.  pair[q][p] = number of
+        // boundary vertices ranks q and p both touch = length of the segment they exchange.
+        const size_t W = (size_t)worldSize;
+        std::vector<int> pair(W * W, 0);
+        for (int b = 0; b < nB; b++) {
+            const uint64_t m = rmask[boundary[b]];
+            for (int q = 0; q < worldSize; q++) {
+                if (!(m >> q & 1ull)) continue;
+                for (int p2 = 0; p2 < worldSize; p2++)
+                    if (p2 != q && (m >> p2 & 1ull)) pair[(size_t)q * W + p2]++;
+            }
+        }
+        for (int q : P.hxPeers) {
+            int off = 0, total = 0, slot = 0;
+            for (int p2 = 0; p2 < worldSize; p2++) {
+                const int n = pair[(size_t)q * W + p2];
+                if (p2 < rank) { off += n; slot += n > 0; }
+                total += n;
+            }
+            P.pxRemoteOff.push_back(off);
+            P.pxRemoteTotal.push_back(total);
+            P.pxRemoteSlot.push_back(slot);
+        }
+        std::fill(cursor.begin(), cursor.end(), 0);
+        P.pxStart.assign((size_t)nB + 1, 0);
+        for (int b = 0; b < nB; b++) {
+            P.pxStart[b] = (int)P.pxPeer.size();
+            if (!P.boundaryActive[b]) continue;
+            const uint64_t m = rmask[boundary[b]];
+            for (int q = 0; q < worldSize; q++) {
+                if (q == rank || !(m >> q & 1ull)) continue;
+                P.pxPeer.push_back(segOf[q]);
+                P.pxEntry.push_back(P.pxRemoteOff[segOf[q]] + cursor[q]++);  // both sides list the shared set ascending in b
+            }
+        }
+        P.pxStart[nB] = (int)P.pxPeer.size();
     }
     P.localTets = std::max(0, tileStart[c1] - tileStart[c0]);
     for (int v : boundary) local[v] = -2;

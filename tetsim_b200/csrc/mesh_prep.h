@@ -51,6 +51,15 @@ struct ClusterPlan {
     std::vector<int> hxSendIdx;         // boundary index of each send entry (same order on both sides of a pair)
     std::vector<int> hxSrcStart;        // [numBoundary + 1] CSR over the sources of each active boundary vertex
     std::vector<int> hxSrc;             // < numBoundary: own partial sum; >= numBoundary: recv entry - numBoundary
+    // Peer-memory ("fused") exchange: the same segments, but every rank STORES its boundary sums straight into the
+    // receive buffer of each sharer through a mapped peer pointer.  All of it follows from the global rank masks, so
+    // every rank derives its peers' layouts locally and nothing but the memory handles has to be exchanged.
+    std::vector<int> pxRemoteOff;       // [peers] offset (entries) of MY segment inside peer q's receive buffer
+    std::vector<int> pxRemoteTotal;     // [peers] total entries of peer q's receive buffer (its parity stride)
+    std::vector<int> pxRemoteSlot;      // [peers] my index in peer q's ascending peer list (which of its flags is mine)
+    std::vector<int> pxStart;           // [numBoundary + 1] CSR over the push destinations of each active boundary vertex
+    std::vector<int> pxPeer;            //   index into hxPeers
+    std::vector<int> pxEntry;           //   entry inside that peer's receive buffer
     int numLocalVerts = 0;              // interior + all boundary vertices
     int numInterior = 0;
     int numBoundary = 0;                // global count of rank-shared vertices (same on every rank)
