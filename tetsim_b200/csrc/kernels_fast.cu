@@ -413,8 +413,8 @@ void launch_jacobi_tiles(cudaStream_t s, int clusterSize, const TileArgs &a) {
         if (const char *m = getenv("TETSIM_TILE_MINB")) minb = atoi(m);
 #define TN_CASE(T_, TPT_, S_, MINB_) if (clusterSize == T_ && tpt == TPT_ && S == S_ && minb == MINB_) { launch_tilesN<T_, TPT_, S_, MINB_>(s, a); return; }
         TN_CASE(128, 2, 2, 0) TN_CASE(128, 2, 3, 0)
-        TN_CASE(256, 2, 2, 0) TN_CASE(256, 2, 3, 0) TN_CASE(256, 2, 2, 6) TN_CASE(256, 2, 3, 6)
-        TN_CASE(512, 2, 2, 0) TN_CASE(512, 2, 3, 0) TN_CASE(512, 2, 2, 3) TN_CASE(512, 2, 3, 3) TN_CASE(512, 2, 2, 4)
+        TN_CASE(256, 2, 2, 0) TN_CASE(256, 2, 3, 0) TN_CASE(256, 2, 2, 6) TN_CASE(256, 2, 3, 6) TN_CASE(256, 2, 2, 8) TN_CASE(256, 2, 3, 8)
+        TN_CASE(512, 2, 2, 0) TN_CASE(512, 2, 3, 0) TN_CASE(512, 2, 2, 3) TN_CASE(512, 2, 3, 3) TN_CASE(512, 2, 2, 4) TN_CASE(512, 2, 3, 4)
         TN_CASE(256, 4, 2, 0) TN_CASE(256, 4, 3, 0) TN_CASE(512, 4, 2, 0) TN_CASE(512, 4, 3, 0) TN_CASE(512, 4, 2, 3)
 #undef TN_CASE
     }
@@ -558,6 +558,95 @@ __global__ void k_halo_reduce(int nB, const int *__restrict__ srcStart, const in
 }
 void launch_halo_reduce(cudaStream_t s, int nB, const int *srcStart, const int *src, const float4 *recv, float4 *bsum) {
     if (nB > 0) k_halo_reduce<<<cdiv(nB, 256), 256, 0, s>>>(nB, srcStart, src, recv, bsum);
+}
+
+// ---- peer-memory exchange (layout and protocol: launch.h, PeerArgs) ----
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void k_peer_push(PeerArgs a) {
+    unsigned *ctl = reinterpret_cast<unsigned *>(a.self + kPeerCtlOff);
+    // every block reads the epoch before it takes its ticket, the last ticket holder advances it: no block sees the new value
+    const unsigned e = *reinterpret_cast<volatile unsigned *>(ctl) + 1u;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < a.numBoundary) {
+        const int p0 = a.pxStart[b], p1 = a.pxStart[b + 1];
+        if (p1 > p0) {  // active: touched by this rank's tets
+            const int i = a.boundaryBegin + b;
+            float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a.acc) {
+                sum = a.acc[i];
+                sum.w = 0.f;
+                a.acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                for (int j = a.vpStart[i]; j < a.vpStart[i + 1]; j++) {
+                    const float4 s = ldg4(a.part + a.vpSlot[j]);
+                    sum.x += s.x; sum.y += s.y; sum.z += s.z;
+                }
+            }
+            a.bsum[b] = sum;
+            for (int j = p0; j < p1; j++) {
+                const int q = a.pxPeer[j];
+                float4 *dst = reinterpret_cast<float4 *>(a.peerBase[q] + kPeerRecvOff) + (size_t)(e & 1u) * a.remoteTotal[q] + a.pxEntry[j];
+                *dst = sum;  // NVLink store into the sharer's receive buffer
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();  // this block's remote stores are ordered before the ticket
+        const unsigned ticket = atomicAdd(ctl + 1, 1u);
+        if (ticket == gridDim.x - 1) {
+            __threadfence_system();  // ... and every block's before the flags
+            for (int q = 0; q < a.numPeers; q++)
+                st_release_sys(reinterpret_cast<unsigned *>(a.peerBase[q]) + a.remoteSlot[q], e);
+            ctl[1] = 0u;
+            *reinterpret_cast<volatile unsigned *>(ctl) = e;
+        }
+    }
+}
+void launch_peer_push(cudaStream_t s, const PeerArgs &a) {
+    if (a.numBoundary > 0) k_peer_push<<<cdiv(a.numBoundary, 256), 256, 0, s>>>(a);
+}
+
+__global__ void k_peer_reduce(PeerArgs a) {
+    unsigned *ctl = reinterpret_cast<unsigned *>(a.self + kPeerCtlOff);
+    const unsigned e = *reinterpret_cast<volatile unsigned *>(ctl);  // advanced by this iteration's k_peer_push
+    if ((int)threadIdx.x < a.numPeers) {
+        const unsigned *flag = reinterpret_cast<const unsigned *>(a.self) + threadIdx.x;
+        const unsigned long long t0 = global_timer_ns();
+        while ((int)(ld_acquire_sys(flag) - e) < 0) {
+            if (global_timer_ns() - t0 > a.timeoutNs) { atomicExch(ctl + 2, 1u); break; }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.numBoundary) return;
+    const int s0 = a.srcStart[b], s1 = a.srcStart[b + 1];
+    if (s0 == s1) return;
+    const float4 *recv = reinterpret_cast<const float4 *>(a.self + kPeerRecvOff) + (size_t)(e & 1u) * a.selfTotal;
+    float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+    for (int j = s0; j < s1; j++) {
+        const int k = a.src[j];
+        const float4 v = k < a.numBoundary ? a.bsum[k] : __ldcg(recv + (k - a.numBoundary));  // written by a peer: not through L1
+        sx += v.x; sy += v.y; sz += v.z;
+    }
+    a.bsum[b] = make_float4(sx, sy, sz, 0.0f);
+}
+void launch_peer_reduce(cudaStream_t s, const PeerArgs &a) {
+    if (a.numBoundary > 0) k_peer_reduce<<<cdiv(a.numBoundary, 256), 256, 0, s>>>(a);
 }
 
 // =================================================================================================

@@ -92,6 +92,33 @@ void launch_halo_pack(cudaStream_t, int n, const int *sendIdx, const float4 *bsu
 void launch_halo_reduce(cudaStream_t, int numBoundary, const int *srcStart, const int *src, const float4 *recv,
                         float4 *bsum);
 
+// Peer-memory exchange (TetSimOptions.exchange = 2): no NCCL, no side stream.  Every rank owns one exchange
+// allocation, mapped into its sharers with cudaIpc:
+//   [0, 256)  uint32 flag[64]   flag[s] = last epoch whose entries the s-th peer (ascending rank) has delivered
+//   [256, ..) uint32 ctl[]      ctl[0] epoch of this rank, ctl[1] block ticket, ctl[2] error (wait timed out)
+//   [1024, ..) float4 recv[2][total]  receive buffer, double-buffered by epoch parity
+// k_peer_push sums this rank's partials of every active boundary vertex, keeps the sum in bsum[] and STORES it over
+// NVLink into the receive buffer of every sharer; the last block to finish publishes the epoch into the sharers'
+// flags (release at system scope).  k_peer_reduce (after the interior tiles) waits for the sharers' flags (acquire)
+// and adds the contributions of all sharers in ascending rank order -- identical on every sharer.
+constexpr int kPeerFlagBytes = 256, kPeerCtlOff = 256, kPeerRecvOff = 1024, kPeerMaxPeers = 64;
+struct PeerArgs {
+    int numBoundary, boundaryBegin, numPeers;
+    const int *vpStart, *vpSlot;          // boundary vertex -> partial-sum slots (deterministic flush)
+    const float4 *part;
+    float4 *acc;                          // atomic-flush accumulator (read and re-zeroed) or NULL
+    float4 *bsum;                         // [numBoundary] own sums in, reduced sums out
+    const int *pxStart, *pxPeer, *pxEntry;  // push destinations (ClusterPlan)
+    unsigned char *const *peerBase;       // [numPeers] mapped exchange allocation of each peer
+    const int *remoteTotal, *remoteSlot;  // [numPeers] parity stride of the peer's buffer; my flag index there
+    unsigned char *self;                  // this rank's exchange allocation
+    int selfTotal;                        // parity stride of my receive buffer
+    const int *srcStart, *src;            // reduce sources (ClusterPlan hxSrcStart / hxSrc)
+    unsigned long long timeoutNs;         // give up waiting after this long (sets ctl[2])
+};
+void launch_peer_push(cudaStream_t, const PeerArgs &a);
+void launch_peer_reduce(cudaStream_t, const PeerArgs &a);
+
 // ---- utility kernels (kernels_fast.cu) ----
 void launch_pack3(cudaStream_t, int N, const float4 *src, const int *perm, float *dst3);       // dst[perm[i]] = src[i].xyz
 void launch_unpack3(cudaStream_t, int N, const float *src3, const int *perm, float4 *dst, int keepW);
