@@ -51,13 +51,13 @@ def parse():
     ap.add_argument("--cells", default="407,64,64", help="beam cells x,y,z (default = 10,002,432 tets)")
     ap.add_argument("--substeps", type=int, default=20, help="substeps per step (frame)")
     ap.add_argument("--iters", type=int, default=1)
-    ap.add_argument("--cluster-size", type=int, default=256)
+    ap.add_argument("--cluster-size", type=int, default=512, help="tets per tile (512 measured fastest on one GPU, profiles/r1_tile_sweep.txt)")
     ap.add_argument("--no-reorder", action="store_true")
     ap.add_argument("--atomic", action="store_true", help="deterministic=0: REDG flush instead of per-tile partials")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong: the same 10M-tet mesh split over N GPUs (BASELINE config 4); weak: beam length x N")
     ap.add_argument("--cpu-substeps", type=int, default=6, help="substeps of the CPU baseline sample (rank 0, N=1)")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "allreduce", "halo"],
+    ap.add_argument("--exchange", default="auto", choices=["auto", "allreduce", "halo", "peer"],
                     help="multi-GPU boundary exchange: ncclAllReduce over all ranks, or grouped ncclSend/ncclRecv with the neighbour ranks; "
                          "auto = all-reduce at 2 GPUs, neighbour exchange beyond (measured 22 %% faster at 8 GPUs, profiles/r1_scaling.md)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -193,7 +193,7 @@ def main():
     verts, tets = mesh.make_beam(cells)
     N, M = verts.size // 3, tets.size // 4
     nccl_id = None
-    if world > 1:
+    if world > 1 and args.exchange != "peer":
         buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             import ctypes
@@ -209,6 +209,12 @@ def main():
                        cluster_size=args.cluster_size, reorder=not args.no_reorder, deterministic=not args.atomic,
                        device=local_rank, stream=stream.cuda_stream, rank=rank, world_size=world,
                        nccl_unique_id=nccl_id, exchange=args.exchange)
+    if world > 1 and args.exchange == "peer":   # hand-shake of the peer-memory exchange buffers
+        mine = torch.frombuffer(bytearray(body.ipc_handle()), dtype=torch.uint8).cuda()
+        blobs = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(blobs, mine)
+        body.set_peers([bytes(b.cpu().numpy().tobytes()) for b in blobs])
+        dist.barrier()
     info = body.info()
 
     def barrier():
@@ -254,7 +260,7 @@ def main():
             traffic = json.load(open(tp)).get("k_jacobi_cluster_dram_bytes_per_launch") if world == 1 else None
         except Exception:
             traffic = None
-    roofline = {"kernel": "k_jacobi_tiles<%d> (persistent tile kernel, tetsim_b200/csrc/kernels_fast.cu)" % args.cluster_size, "bound": "hbm", "achieved": achieved,
+    roofline = {"kernel": "k_jacobi_tilesN<%d, 2 tets/thread> (persistent tile kernel, tetsim_b200/csrc/kernels_fast.cu)" % args.cluster_size, "bound": "hbm", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": k_bytes, "ms_per_launch": k_ms,
                 "share_of_step": k_ms * args.iters * args.substeps / ms_step,
@@ -312,12 +318,13 @@ def main():
             "config": {"workload": workload, "tets": M, "verts": N, "iters": args.iters, "substeps_per_step": args.substeps,
                        "cluster_size": info["clusterSize"], "clusters_rank0": info["numClusters"],
                        "boundary_verts": info["boundaryVerts"], "boundary_tiles_rank0": info["boundaryTiles"], "deterministic": not args.atomic,
-                       "parallelism": ("tet-partition x%d (RCB), %s of boundary dx per iteration, overlapped with interior tiles" % (world, "ncclAllReduce" if args.exchange == "allreduce" else "neighbour ncclSend/ncclRecv")) if world > 1 else "single GPU",
+                       "parallelism": ("tet-partition x%d (RCB), %s of boundary dx per iteration, overlapped with interior tiles" % (world, {"allreduce": "ncclAllReduce", "halo": "neighbour ncclSend/ncclRecv", "peer": "peer-memory stores (cudaIpc over NVLink, no NCCL)"}[args.exchange])) if world > 1 else "single GPU",
                        "l2": "working set per substep (%.0f MB) exceeds the 126 MB L2; no flush needed" % ((56.0 * M + 144.0 * N) / 1e6)},
             "scalar_constraints_per_s_M": 2 * value,
             "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line))
+    barrier()   # every rank idle before any rank frees its (possibly peer-mapped) buffers
     body.close()
     if world > 1:
         dist.destroy_process_group()

@@ -97,7 +97,11 @@ typedef struct TetSimOptions {
     int32_t worldSize;         /* multi-GPU Jacobi: number of tet partitions / processes, default 1   */
     int32_t exchange;          /* multi-GPU: 0 = ncclAllReduce of the boundary dx over all ranks (default),
                                   1 = neighbour exchange: grouped ncclSend/ncclRecv with the ranks that share
-                                  vertices with this one, sharers' sums added in ascending rank order      */
+                                  vertices with this one, sharers' sums added in ascending rank order,
+                                  2 = peer-memory exchange: the kernel that forms this rank's boundary sums stores
+                                  them over NVLink straight into the sharers' receive buffers (cudaIpc mappings,
+                                  tetsim_get_ipc_handle / tetsim_set_peers) and publishes a flag; no NCCL, no
+                                  ncclUniqueId, same rank-ordered sums as 1                                     */
     void *stream;              /* cudaStream_t to enqueue on; NULL = a stream owned by the handle     */
     const void *ncclUniqueId;  /* 128-byte ncclUniqueId from tetsim_nccl_unique_id (rank 0's), or NULL */
 } TetSimOptions;
@@ -193,10 +197,17 @@ int tetsim_time_kernel(tetsim_t *h, int32_t reps, double *msPerLaunch, int64_t *
 /* Multi-GPU plumbing (one process per GPU).  Rank 0 calls tetsim_nccl_unique_id and broadcasts the
  * 128 bytes out of band (torch.distributed in this repo); every rank passes them in TetSimOptions. */
 int tetsim_nccl_unique_id(void *out128);
-/* Reserved for a fused peer-memory exchange (tile kernel storing boundary sums straight into the
- * neighbour's accumulator through a cudaIpc mapping).  Not built yet: both return TETSIM_E_STATE. */
-int tetsim_get_ipc_handle(tetsim_t *h, void *out64);
-int tetsim_set_peers(tetsim_t *h, const void *handles);
+/* Peer-memory exchange (exchange = 2).  After tetsim_create every rank calls tetsim_get_ipc_handle, the ranks
+ * all-gather the TETSIM_PEER_BLOB_BYTES-byte blobs by any means (torch.distributed in bench.py), and every rank
+ * passes the worldSize blobs, in rank order, to tetsim_set_peers, which maps the exchange buffers of the ranks it
+ * shares vertices with.  simulate/step fail with TETSIM_E_STATE until then.  Ranks must issue the same sequence of
+ * simulate/step calls (as with NCCL); a rank that waits longer than TETSIM_PEER_TIMEOUT_MS (default 10000) for a
+ * sharer gives up and the next tetsim_synchronize / tetsim_get_* reports TETSIM_E_STATE.  All ranks must be idle
+ * (synchronized) before any of them destroys its handle.  Handles of one process may also be peers of each other
+ * (the blob carries the owner's pointer), which is how the single-process test drives the protocol. */
+#define TETSIM_PEER_BLOB_BYTES 128
+int tetsim_get_ipc_handle(tetsim_t *h, void *outBlob);
+int tetsim_set_peers(tetsim_t *h, const void *blobs /* worldSize * TETSIM_PEER_BLOB_BYTES */);
 
 /* Host-side mesh tools used by tests and the benchmark (the reference has none; README.md:25). */
 /* Order-preserving dependency levels of the sequential sweep: level[numTets] out; returns #levels. */
@@ -213,6 +224,15 @@ int tetsim_greedy_colors(const int32_t *tetIds, int32_t numTets, int32_t numVert
 int tetsim_plan_partition(const float *verts, int32_t numVerts, const int32_t *tetIds, int32_t numTets,
                           int32_t clusterSize, int32_t reorder, int32_t rank, int32_t worldSize, int32_t counts[4],
                           int32_t *localToCaller, int32_t *localTets);
+
+/* The neighbour lists the halo / peer-memory exchanges of (rank, worldSize) would use, without touching a GPU:
+ * returns the number of peers P (<= capacity, else TETSIM_E_INVALID); peers[P] ascending ranks; segStart[P + 1]
+ * offsets of the per-peer segments of this rank's send/receive buffers (entries); remoteOff[P], remoteTotal[P],
+ * remoteSlot[P]: where this rank's segment starts inside peer q's receive buffer, that buffer's size, and this
+ * rank's index in q's peer list -- what the peer-memory exchange derives locally instead of communicating. */
+int tetsim_plan_halo(const float *verts, int32_t numVerts, const int32_t *tetIds, int32_t numTets, int32_t clusterSize,
+                     int32_t reorder, int32_t rank, int32_t worldSize, int32_t capacity, int32_t *peers,
+                     int32_t *segStart, int32_t *remoteOff, int32_t *remoteTotal, int32_t *remoteSlot);
 
 #ifdef __cplusplus
 }

@@ -49,12 +49,14 @@ def test_sass_is_sm100a_without_tensor_or_cas_loops():
     contraction on this path) and no shared-memory CAS spin loops in the clustered Jacobi kernel."""
     out = subprocess.run(["cuobjdump", "-lelf", _capi.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
-    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN4tsim14k_jacobi_tilesILi256ELi2ELi4EEEvNS_8TileArgsE",
-                           _capi.LIB_PATH], capture_output=True, text=True).stdout
-    # TMA bulk copies on mbarriers, cp.async gathers, 128-bit shared-memory traffic
-    assert "UBLKCP" in sass and "SYNCS" in sass and "LDGSTS.E.BYPASS.128" in sass
-    assert "STS.128" in sass and "LDS.128" in sass and "STG.E.128" in sass
-    assert "ATOMS.CAST" not in sass and "HMMA" not in sass and "UTCHMMA" not in sass
+    # the default tile kernels: T = 512 and T = 256, two tets per thread, two stages
+    for fun in ("_ZN4tsim15k_jacobi_tilesNILi512ELi2ELi2ELi4EEEvNS_8TileArgsE",
+                "_ZN4tsim15k_jacobi_tilesNILi256ELi2ELi2ELi0EEEvNS_8TileArgsE"):
+        sass = subprocess.run(["cuobjdump", "-sass", "-fun", fun, _capi.LIB_PATH], capture_output=True, text=True).stdout
+        # TMA bulk copies on mbarriers, bulk L2 prefetch, cp.async gathers, 128-bit shared-memory traffic
+        assert "UBLKCP" in sass and "UBLKPF" in sass and "SYNCS" in sass and "LDGSTS.E.BYPASS.128" in sass, fun
+        assert "STS.128" in sass and "LDS.128" in sass and "STG.E.128" in sass, fun
+        assert "ATOMS.CAST" not in sass and "HMMA" not in sass and "UTCHMMA" not in sass and "CALL" not in sass, fun
 
 
 @pytest.mark.skipif(_capi.lib().tetsim_device_count() > 0, reason="a B200 is present")

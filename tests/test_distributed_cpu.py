@@ -91,3 +91,27 @@ def test_partition_and_exchange_world2(cluster_size):
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     got = sorted(q.get(timeout=5) for _ in range(2))
     assert got[0][2] == got[1][2] > 0
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+def test_peer_exchange_layouts_agree_across_ranks(world):
+    """The peer-memory exchange communicates nothing but memory handles: every rank DERIVES where its entries land
+    in each sharer's receive buffer.  Check those derived layouts against the sharers' own (host only, no GPU)."""
+    from tetsim_b200 import _capi, mesh
+    v, t = mesh.make_beam((40, 6, 6), h=0.05, y0=0.5, jitter=0.2)
+    plans = [_capi.plan_halo(v, t, 128, True, r, world) for r in range(world)]
+    pairs = 0
+    for r, p in enumerate(plans):
+        assert list(p["peers"]) == sorted(set(p["peers"])) and r not in p["peers"]
+        for i, q in enumerate(p["peers"]):
+            pq = plans[q]
+            assert r in pq["peers"], "sharing must be symmetric"
+            j = list(pq["peers"]).index(r)
+            seg_r = p["segStart"][i + 1] - p["segStart"][i]
+            seg_q = pq["segStart"][j + 1] - pq["segStart"][j]
+            assert seg_r == seg_q > 0, "both sides exchange the same shared set"
+            assert p["remoteOff"][i] == pq["segStart"][j], "my entries start where the sharer expects them"
+            assert p["remoteTotal"][i] == pq["segStart"][-1], "parity stride of the sharer's buffer"
+            assert p["remoteSlot"][i] == j, "which of the sharer's flags is mine"
+            pairs += 1
+    assert pairs >= 2 * (world - 1)

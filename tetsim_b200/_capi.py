@@ -19,6 +19,7 @@ NH_GS_EXACT, NH_GS_COLOR, NH_JACOBI, POLAR_JACOBI = 0, 1, 2, 3
 ARITH_FAST_F32, ARITH_BITEXACT = 0, 1
 
 E_INVALID, E_CUDA, E_NCCL, E_STATE, E_NOMEM = -1, -2, -3, -4, -5
+PEER_BLOB_BYTES = 128  # TETSIM_PEER_BLOB_BYTES
 
 # every symbol include/tetsim_b200.h declares (tests/test_capi_symbols.py checks the header against this)
 SYMBOLS = [
@@ -28,7 +29,7 @@ SYMBOLS = [
     "tetsim_get_resident", "tetsim_set_state", "tetsim_get_rest", "tetsim_get_vol_error",
     "tetsim_get_polar_state", "tetsim_start_grab", "tetsim_move_grabbed", "tetsim_end_grab", "tetsim_skin",
     "tetsim_get_info", "tetsim_time_kernel", "tetsim_nccl_unique_id", "tetsim_get_ipc_handle", "tetsim_set_peers",
-    "tetsim_level_schedule", "tetsim_greedy_colors", "tetsim_plan_partition",
+    "tetsim_level_schedule", "tetsim_greedy_colors", "tetsim_plan_partition", "tetsim_plan_halo",
 ]
 
 
@@ -132,6 +133,8 @@ def lib() -> C.CDLL:
     L.tetsim_greedy_colors.argtypes = [i32p, C.c_int32, C.c_int32, i32p]
     L.tetsim_plan_partition.argtypes = [f32p, C.c_int32, i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         i32p, i32p, i32p]
+    L.tetsim_plan_halo.argtypes = [f32p, C.c_int32, i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_int32, i32p, i32p, i32p, i32p, i32p]
     _lib = L
     return L
 
@@ -197,3 +200,18 @@ def plan_partition(verts, tet_ids, cluster_size: int, reorder: bool, rank: int, 
     nloc = int(counts[1] + counts[2])
     return dict(localTets=lt[: counts[0]].copy(), numInterior=int(counts[1]), numBoundary=int(counts[2]),
                 numClusters=int(counts[3]), localToCaller=l2c[:nloc].copy())
+
+
+def plan_halo(verts, tet_ids, cluster_size: int, reorder: bool, rank: int, world_size: int) -> dict:
+    """Host-only view of the neighbour lists of the halo / peer-memory exchange (no GPU needed)."""
+    v = np.ascontiguousarray(verts, np.float32).reshape(-1)
+    t = np.ascontiguousarray(tet_ids, np.int32).reshape(-1)
+    cap = max(world_size, 1)
+    i32p = C.POINTER(C.c_int32)
+    arrs = [np.zeros(cap + 1, np.int32) for _ in range(5)]
+    n = check(lib().tetsim_plan_halo(v.ctypes.data_as(C.POINTER(C.c_float)), v.size // 3, t.ctypes.data_as(i32p),
+                                     t.size // 4, int(cluster_size), int(bool(reorder)), int(rank), int(world_size), cap,
+                                     *[x.ctypes.data_as(i32p) for x in arrs]))
+    peers, seg, off, tot, slot = arrs
+    return dict(peers=peers[:n].copy(), segStart=seg[: n + 1].copy(), remoteOff=off[:n].copy(),
+                remoteTotal=tot[:n].copy(), remoteSlot=slot[:n].copy())

@@ -68,6 +68,29 @@ __device__ __forceinline__ void cp_async16(void *dst, const void *src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// the same on 32-bit shared-window addresses (converted once per worker, not per call)
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_a(uint32_t dst, const void *src, uint32_t bytes, uint32_t b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(b)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t b, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done)
+            : "r"(b), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void cp_async16_a(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
 template <int T, int S>
 struct TileSmem {
     static constexpr int TET_BYTES = T * 48;
@@ -117,6 +140,8 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
     const TileSmem<T, S> L(a.metaStride, a.maxTileVertsPad);
     uint64_t *metaFull = reinterpret_cast<uint64_t *>(ws + L.bars);  // [S + 1]
     unsigned char *const sdx = ws + L.sdx;
+    const uint32_t wsa = smem_u32(ws);           // shared-window address of the worker's region
+    const uint32_t barA = wsa + (uint32_t)L.bars;  // mbarrier i at barA + 8 i
     auto sync = [&]() { if (WARP_SCOPE) __syncwarp(); else __syncthreads(); };
 
     if (tid == 0) {
@@ -130,8 +155,8 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
 
     auto issue_meta = [&](uint32_t o, uint32_t end, int slot) {  // one thread; block = [16*o, 16*end)
         const uint32_t bytes = (end - o) * 16u;
-        mbar_expect_tx(metaFull + slot, bytes);
-        bulk_g2s(ws + L.meta(slot), a.meta + (size_t)o * 16, bytes, metaFull + slot);
+        mbar_expect_tx_a(barA + 8u * (uint32_t)slot, bytes);
+        bulk_g2s_a(wsa + (uint32_t)L.meta(slot), a.meta + (size_t)o * 16, bytes, barA + 8u * (uint32_t)slot);
     };
     // The tet stream is read once, straight into registers (3.5 coalesced LDG.128 per tet: staging it in
     // shared memory would cost a write and a read of the SM's 128 B/clk shared-memory pipe, which the
@@ -145,9 +170,9 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
         const unsigned char *m = ws + L.meta(slot);
         const int nl = reinterpret_cast<const int *>(m)[1];
         const int *ids = reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3]);
-        float4 *sx = reinterpret_cast<float4 *>(ws + L.sx(buf));
+        const uint32_t sxa = wsa + (uint32_t)L.sx(buf);
         if (!(dbg & 4))
-            for (int j = tid; j < nl; j += NT) cp_async16(sx + j, a.x4 + ids[j]);
+            for (int j = tid; j < nl; j += NT) cp_async16_a(sxa + 16u * (uint32_t)j, a.x4 + ids[j]);
         cp_async_commit();
     };
 
@@ -166,7 +191,7 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
     }
 #pragma unroll
     for (int i = 0; i < S - 1; i++) {
-        if (first + i * stride < a.numTiles) { mbar_wait(metaFull + i, 0); issue_gather(i, i); }
+        if (first + i * stride < a.numTiles) { mbar_wait_a(barA + 8u * (uint32_t)i, 0); issue_gather(i, i); }
         else cp_async_commit();
     }
 
@@ -205,13 +230,13 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
             if (cn < a.numTiles) {
                 const int mslot = kn % (S + 1), buf = kn % S;
                 if (it >= 0) {
-                    mbar_wait(metaFull + mslot, (kn / (S + 1)) & 1);
+                    mbar_wait_a(barA + 8u * (uint32_t)mslot, (kn / (S + 1)) & 1);
                     const unsigned char *m = ws + L.meta(mslot);
                     const int nl = reinterpret_cast<const int *>(m)[1];
                     const int *ids = reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3]);
-                    float4 *sx = reinterpret_cast<float4 *>(ws + L.sx(buf));
+                    const uint32_t sxa = wsa + (uint32_t)L.sx(buf);
                     if (!(dbg & 4))
-                        for (int j = it; j < nl; j += NI) cp_async16(sx + j, a.x4 + ids[j]);
+                        for (int j = it; j < nl; j += NI) cp_async16_a(sxa + 16u * (uint32_t)j, a.x4 + ids[j]);
                 }
             }
             cp_async_commit();
@@ -319,11 +344,22 @@ __global__ void __launch_bounds__(TPL == 1 ? 832 : 448, 1) k_jacobi_warptiles(Ti
 template <int T, int S>
 static size_t tile_smem_bytes(const TileArgs &a) { return (size_t)TileSmem<T, S>(a.metaStride, a.maxTileVertsPad).total; }
 
-static int tile_stages(int clusterSize) {
-    int s = 3;
-    if (const char *e = getenv("TETSIM_TILE_STAGES")) { int v = atoi(e); if (v >= 2 && v <= 4) s = v; }
-    return s;
+// Kernel shape per tile size.  Defaults are the round-1 sweep winners on the 10M-tet beam (profiles/r1_tile_sweep.txt):
+// two tets per thread (independent dependency chains, half the per-tile barrier/prefetch overhead per tet, corner sums
+// spread over all warps), two pipeline stages, registers capped so 4 x 256 threads (T = 512) stay resident per SM.
+// TETSIM_TILE_TPT / TETSIM_TILE_STAGES / TETSIM_TILE_MINB override them for experiments (tools/tile_sweep.py).
+struct TileShape { int tpt, stages, minb; };
+static TileShape tile_shape(int clusterSize) {
+    TileShape sh{clusterSize >= 128 ? 2 : 1, 0, 0};
+    if (const char *e = getenv("TETSIM_TILE_TPT")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) sh.tpt = v; }
+    if (clusterSize < 128) sh.tpt = 1;  // warp tiles
+    sh.stages = sh.tpt == 1 ? 3 : 2;
+    if (const char *e = getenv("TETSIM_TILE_STAGES")) { int v = atoi(e); if (v >= 2 && v <= 4) sh.stages = v; }
+    sh.minb = (clusterSize == 512 && sh.tpt == 2) ? 4 : 0;
+    if (const char *e = getenv("TETSIM_TILE_MINB")) sh.minb = atoi(e);
+    return sh;
 }
+static int tile_stages(int clusterSize) { return tile_shape(clusterSize).stages; }
 
 size_t jacobi_tiles_smem(int clusterSize, const TileArgs &a) {
     const int S = tile_stages(clusterSize);
@@ -405,18 +441,18 @@ static void launch_warptiles(cudaStream_t s, const TileArgs &a) {
 
 void launch_jacobi_tiles(cudaStream_t s, int clusterSize, const TileArgs &a) {
     if (a.numTiles - a.tileBegin <= 0) return;
-    const int S = tile_stages(clusterSize);
+    const TileShape sh = tile_shape(clusterSize);
+    const int S = sh.stages;
     if (a.debugSkip && clusterSize == 256) { launch_tiles_T<256, 3, 4, true>(s, a); return; }  // ablations: one instantiation
-    if (const char *e = getenv("TETSIM_TILE_TPT")) {  // experiment switch: tets per thread (and CTAs per SM the registers are capped for)
-        const int tpt = atoi(e);
-        int minb = 0;
-        if (const char *m = getenv("TETSIM_TILE_MINB")) minb = atoi(m);
+    if (sh.tpt > 1) {
+        const int tpt = sh.tpt, minb = sh.minb;
 #define TN_CASE(T_, TPT_, S_, MINB_) if (clusterSize == T_ && tpt == TPT_ && S == S_ && minb == MINB_) { launch_tilesN<T_, TPT_, S_, MINB_>(s, a); return; }
         TN_CASE(128, 2, 2, 0) TN_CASE(128, 2, 3, 0)
-        TN_CASE(256, 2, 2, 0) TN_CASE(256, 2, 3, 0) TN_CASE(256, 2, 2, 6) TN_CASE(256, 2, 3, 6) TN_CASE(256, 2, 2, 8) TN_CASE(256, 2, 3, 8)
-        TN_CASE(512, 2, 2, 0) TN_CASE(512, 2, 3, 0) TN_CASE(512, 2, 2, 3) TN_CASE(512, 2, 3, 3) TN_CASE(512, 2, 2, 4) TN_CASE(512, 2, 3, 4)
-        TN_CASE(256, 4, 2, 0) TN_CASE(256, 4, 3, 0) TN_CASE(512, 4, 2, 0) TN_CASE(512, 4, 3, 0) TN_CASE(512, 4, 2, 3)
+        TN_CASE(256, 2, 2, 0) TN_CASE(256, 2, 3, 0) TN_CASE(256, 2, 2, 6) TN_CASE(256, 2, 2, 8)
+        TN_CASE(512, 2, 2, 0) TN_CASE(512, 2, 2, 3) TN_CASE(512, 2, 2, 4) TN_CASE(512, 2, 3, 4)
+        TN_CASE(256, 4, 2, 0) TN_CASE(512, 4, 2, 0) TN_CASE(512, 4, 2, 3)
 #undef TN_CASE
+        // no such instantiation: fall through to the one-tet-per-thread kernels
     }
     switch (clusterSize) {
         case 32: S == 2 ? launch_warptiles<1, 2>(s, a) : (S == 3 ? launch_warptiles<1, 3>(s, a) : launch_warptiles<1, 4>(s, a)); break;
@@ -623,7 +659,8 @@ void launch_peer_push(cudaStream_t s, const PeerArgs &a) {
 __global__ void k_peer_reduce(PeerArgs a) {
     unsigned *ctl = reinterpret_cast<unsigned *>(a.self + kPeerCtlOff);
     const unsigned e = *reinterpret_cast<volatile unsigned *>(ctl);  // advanced by this iteration's k_peer_push
-    if ((int)threadIdx.x < a.numPeers) {
+    // a wait that timed out once is never repeated (the error is sticky and reported by the host): no pile-up of timeouts
+    if ((int)threadIdx.x < a.numPeers && *reinterpret_cast<volatile unsigned *>(ctl + 2) == 0u) {
         const unsigned *flag = reinterpret_cast<const unsigned *>(a.self) + threadIdx.x;
         const unsigned long long t0 = global_timer_ns();
         while ((int)(ld_acquire_sys(flag) - e) < 0) {

@@ -2,6 +2,7 @@
 // solver scheduling, CUDA-graph capture of the substep loop, multi-GPU exchange.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cmath>
@@ -180,6 +181,12 @@ struct tetsim {
     bool halo = false;                      // neighbour exchange instead of the all-reduce
     DevBuf<int> hxSendIdx, hxSrcStart, hxSrc;
     DevBuf<float4> hxSend, hxRecv;
+    // peer-memory exchange (exchange = 2): this rank's exchange allocation, the sharers' mapped ones
+    bool peer = false, peersSet = false;
+    DevBuf<unsigned char> peerBuf;
+    std::vector<void *> peerOpened;         // bases returned by cudaIpcOpenMemHandle (closed at destroy)
+    DevBuf<unsigned char *> peerBase;       // [peers] mapped exchange allocation of each sharer
+    DevBuf<int> pxStart, pxPeer, pxEntry, pxRemoteTotal, pxRemoteSlot;
     int maxValence = 0;
 
     int64_t deviceBytes() const {
@@ -195,6 +202,35 @@ struct tetsim {
 };
 
 namespace {
+// What ranks hand each other for the peer-memory exchange (tetsim_get_ipc_handle / tetsim_set_peers).
+struct PeerBlob {
+    unsigned char ipc[64];      // cudaIpcMemHandle_t of the allocation holding the exchange buffer
+    uint64_t offset;            // of the exchange buffer inside that allocation
+    uint64_t rawPtr;            // the owner's own pointer: used instead of the IPC mapping inside the owner's process
+    int32_t pid, device, rank, total, numPeers;
+    uint32_t magic;
+    unsigned char pad[TETSIM_PEER_BLOB_BYTES - 64 - 16 - 20 - 4];
+};
+static_assert(sizeof(PeerBlob) == TETSIM_PEER_BLOB_BYTES, "PeerBlob layout");
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+constexpr uint32_t kPeerMagic = 0x54455450u;  // "PTET"
+
+// Offset of p inside its cudaMalloc allocation: an IPC handle always names the whole allocation and small buffers
+// may be carved out of a shared block.  cuMemGetAddressRange lives in the driver library the runtime already loaded.
+size_t allocation_offset(const void *p) {
+    typedef int (*Fn)(unsigned long long *, size_t *, unsigned long long);
+    static Fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        if (void *lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL)) fn = (Fn)dlsym(lib, "cuMemGetAddressRange_v2");
+    }
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (fn && fn(&base, &size, (unsigned long long)(uintptr_t)p) == 0 && base) return (size_t)((uintptr_t)p - (uintptr_t)base);
+    return 0;
+}
+
 struct DeviceGuard {
     int prev = -1;
     explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); }
@@ -393,6 +429,23 @@ int build_jacobi_cluster(tetsim *h, const std::vector<float> &verts, const std::
         for (int b = 0; b < P.numBoundary; b++)
             if (!P.boundaryActive[b]) h->h_vertId[(size_t)P.numInterior + b] = -1;
     }
+    h->peer = h->opt.worldSize > 1 && h->opt.exchange == 2;
+    if (h->peer) {
+        if (!P.haloOk) return fail(TETSIM_E_STATE, "the peer-memory exchange needs the neighbour lists (worldSize <= 64)");
+        const size_t total = P.hxSendIdx.size();  // entries I receive == entries I send
+        CK(h->peerBuf.alloc(kPeerRecvOff + 2 * std::max<size_t>(total, 1) * sizeof(float4)));
+        CK(cudaMemsetAsync(h->peerBuf.p, 0, h->peerBuf.bytes(), s));
+        CK(h->hxSrcStart.upload(P.hxSrcStart, s));
+        CK(h->hxSrc.upload(P.hxSrc, s));
+        CK(h->pxStart.upload(P.pxStart, s));
+        CK(h->pxPeer.upload(P.pxPeer, s));
+        CK(h->pxEntry.upload(P.pxEntry, s));
+        CK(h->pxRemoteTotal.upload(P.pxRemoteTotal, s));
+        CK(h->pxRemoteSlot.upload(P.pxRemoteSlot, s));
+        CK(h->peerBase.alloc(std::max<size_t>(P.hxPeers.size(), 1)));
+        for (int b = 0; b < P.numBoundary; b++)
+            if (!P.boundaryActive[b]) h->h_vertId[(size_t)P.numInterior + b] = -1;
+    }
     bool identity = (int)h->h_vertId.size() == N;
     for (int i = 0; identity && i < N; i++) identity = h->h_vertId[i] == i;
     if (identity) h->h_vertId.clear();
@@ -426,6 +479,21 @@ TileArgs tile_args(const tetsim *h) {
     a.part = h->part.p; a.acc = nullptr; a.volAcc = nullptr; a.sp = h->sp.p;
     a.staggerNs = 0;
     if (const char *e = getenv("TETSIM_TILE_STAGGER_NS")) a.staggerNs = atoi(e);
+    return a;
+}
+
+PeerArgs peer_args(const tetsim *h) {
+    const ClusterPlan &P = h->plan;
+    PeerArgs a{};
+    a.numBoundary = P.numBoundary; a.boundaryBegin = P.numInterior; a.numPeers = (int)P.hxPeers.size();
+    a.vpStart = h->vpStart.p; a.vpSlot = h->vpSlot.p; a.part = h->part.p; a.acc = h->acc.p; a.bsum = h->bsum.p;
+    a.pxStart = h->pxStart.p; a.pxPeer = h->pxPeer.p; a.pxEntry = h->pxEntry.p;
+    a.peerBase = h->peerBase.p; a.remoteTotal = h->pxRemoteTotal.p; a.remoteSlot = h->pxRemoteSlot.p;
+    a.self = h->peerBuf.p; a.selfTotal = (int)P.hxSendIdx.size();
+    a.srcStart = h->hxSrcStart.p; a.src = h->hxSrc.p;
+    unsigned long long ms = 10000ull;
+    if (const char *e = getenv("TETSIM_PEER_TIMEOUT_MS")) { long v = atol(e); if (v > 0) ms = (unsigned long long)v; }
+    a.timeoutNs = ms * 1000000ull;
     return a;
 }
 
@@ -481,6 +549,20 @@ int enqueue_substeps(tetsim *h, int count) {
                         if (!multi) {
                             launch_jacobi_tiles(s, P.T, ca);
                             h->enq += 2;  // tile kernel + vertex kernel
+                        } else if (h->peer) {
+                            // boundary tiles -> push this rank's boundary sums into the sharers' buffers (+ flag)
+                            // -> interior tiles (the sharers' stores arrive meanwhile) -> wait + rank-ordered reduce
+                            TileArgs cb = ca;
+                            cb.numTiles = P.numBoundaryTiles;
+                            launch_jacobi_tiles(s, P.T, cb);
+                            PeerArgs pa = peer_args(h);
+                            launch_peer_push(s, pa);
+                            TileArgs ci = ca;
+                            ci.tileBegin = P.numBoundaryTiles;
+                            launch_jacobi_tiles(s, P.T, ci);
+                            launch_peer_reduce(s, pa);
+                            aa.bsum = h->bsum.p;
+                            h->enq += 4 + (P.numBoundaryTiles > 0 && P.numBoundaryTiles < P.numClusters ? 1 : 0);
                         } else {
                             // 1. the tiles that touch rank-shared vertices, then this rank's boundary sums
                             TileArgs cb = ca;
@@ -543,6 +625,7 @@ int run_substeps(tetsim *h, double dt, int count, const TetSimParams *params) {
     if (!h) return fail(TETSIM_E_INVALID, "null handle");
     if (count < 1) return fail(TETSIM_E_INVALID, "numSubsteps must be >= 1");
     if (!(dt == dt)) return fail(TETSIM_E_INVALID, "dt is NaN");
+    if (h->peer && !h->peersSet) return fail(TETSIM_E_STATE, "exchange = 2: call tetsim_set_peers before simulate/step");
     DeviceGuard g(h->device);
     if (params) h->params = *params;
     SubstepParams hs;
@@ -575,6 +658,15 @@ int run_substeps(tetsim *h, double dt, int count, const TetSimParams *params) {
     return TETSIM_OK;
 }
 
+// Peer-memory exchange: did a wait for a sharer time out?  (stream already synchronized by the caller)
+int peer_check(tetsim *h) {
+    if (!h->peer || !h->peerBuf.p) return TETSIM_OK;
+    unsigned err = 0;
+    CK(cudaMemcpy(&err, h->peerBuf.p + kPeerCtlOff + 8, sizeof(err), cudaMemcpyDeviceToHost));
+    if (err) return fail(TETSIM_E_STATE, "peer-memory exchange: a sharer's boundary sums did not arrive within the timeout (ranks out of step, or a peer died); state is invalid");
+    return TETSIM_OK;
+}
+
 int fetch3(tetsim *h, const float4 *src, float *out) {
     if (!h || !out) return fail(TETSIM_E_INVALID, "null argument");
     DeviceGuard g(h->device);
@@ -582,7 +674,7 @@ int fetch3(tetsim *h, const float4 *src, float *out) {
     launch_pack3(h->stream, h->nInt, src, h->vertId.p, h->stage3.p);
     CK(cudaMemcpyAsync(out, h->stage3.p, h->stage3.bytes(), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    return TETSIM_OK;
+    return peer_check(h);
 }
 }  // namespace
 
@@ -659,8 +751,9 @@ int tetsim_create(const float *verts, int32_t numVerts, const int32_t *tetIds, i
     const bool clustered = opt.solver == TETSIM_NH_JACOBI && opt.arithmetic == TETSIM_ARITH_FAST_F32;
     if (opt.worldSize > 1 && !clustered)
         return fail(TETSIM_E_STATE, "worldSize > 1 is only supported by the FAST_F32 Jacobi solver; shard independent bodies across processes instead");
-    if (opt.exchange < 0 || opt.exchange > 1) return fail(TETSIM_E_INVALID, "exchange must be 0 (all-reduce) or 1 (neighbour exchange)");
-    if (opt.worldSize > 1 && !opt.ncclUniqueId) return fail(TETSIM_E_INVALID, "worldSize > 1 needs ncclUniqueId");
+    if (opt.exchange < 0 || opt.exchange > 2) return fail(TETSIM_E_INVALID, "exchange must be 0 (all-reduce), 1 (neighbour exchange) or 2 (peer memory)");
+    if (opt.exchange == 2 && opt.worldSize > kPeerMaxPeers) return fail(TETSIM_E_INVALID, "the peer-memory exchange supports at most 64 ranks");
+    if (opt.worldSize > 1 && opt.exchange != 2 && !opt.ncclUniqueId) return fail(TETSIM_E_INVALID, "worldSize > 1 needs ncclUniqueId");
     for (int64_t c = 0; c < 4 * (int64_t)numTets; c++)
         if (tetIds[c] < 0 || tetIds[c] >= numVerts) return fail(TETSIM_E_INVALID, "tet " + std::to_string(c / 4) + " references vertex " + std::to_string(tetIds[c]) + " outside [0, numVerts)");
     for (int e = 0; e < numTets; e++) {
@@ -727,7 +820,7 @@ int tetsim_create(const float *verts, int32_t numVerts, const int32_t *tetIds, i
         int rc = TETSIM_OK;
         if (opt.solver == TETSIM_NH_GS_EXACT || opt.solver == TETSIM_NH_GS_COLOR) rc = build_gs(h, hv, ht);
         else if (clustered) {
-            if (opt.worldSize > 1) {
+            if (opt.worldSize > 1 && opt.exchange != 2) {
                 if (!g_nccl.load()) return fail(TETSIM_E_NCCL, g_nccl.why);
                 NcclUniqueId id;
                 memcpy(&id, opt.ncclUniqueId, sizeof(id));
@@ -794,6 +887,7 @@ void tetsim_destroy(tetsim_t *h) {
     DeviceGuard g(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second);
+    for (void *m : h->peerOpened) cudaIpcCloseMemHandle(m);
     if (h->comm) g_nccl.CommDestroy(h->comm);
     if (h->evFork) cudaEventDestroy(h->evFork);
     if (h->evJoin) cudaEventDestroy(h->evJoin);
@@ -822,7 +916,7 @@ int tetsim_synchronize(tetsim_t *h) {
     if (!h) return fail(TETSIM_E_INVALID, "null handle");
     DeviceGuard g(h->device);
     CK(cudaStreamSynchronize(h->stream));
-    return TETSIM_OK;
+    return peer_check(h);
 }
 
 int tetsim_get_positions(tetsim_t *h, float *out) { return h ? fetch3(h, h->x4.p, out) : fail(TETSIM_E_INVALID, "null handle"); }
@@ -1038,13 +1132,63 @@ int tetsim_nccl_unique_id(void *out128) {
     return TETSIM_OK;
 }
 
-int tetsim_get_ipc_handle(tetsim_t *h, void *out64) {
-    (void)h; (void)out64;
-    return fail(TETSIM_E_STATE, "fused peer-memory exchange is not built yet");
+int tetsim_get_ipc_handle(tetsim_t *h, void *outBlob) {
+    if (!h || !outBlob) return fail(TETSIM_E_INVALID, "null argument");
+    if (!h->peer) return fail(TETSIM_E_STATE, "tetsim_get_ipc_handle needs a multi-GPU handle created with exchange = 2");
+    DeviceGuard g(h->device);
+    PeerBlob b;
+    memset(&b, 0, sizeof(b));
+    cudaIpcMemHandle_t ipc;
+    CK(cudaIpcGetMemHandle(&ipc, h->peerBuf.p));
+    memcpy(b.ipc, &ipc, sizeof(ipc));
+    b.offset = allocation_offset(h->peerBuf.p);
+    b.rawPtr = (uint64_t)(uintptr_t)h->peerBuf.p;
+    b.pid = (int32_t)getpid(); b.device = h->device; b.rank = h->opt.rank;
+    b.total = (int32_t)h->plan.hxSendIdx.size(); b.numPeers = (int32_t)h->plan.hxPeers.size();
+    b.magic = kPeerMagic;
+    memcpy(outBlob, &b, sizeof(b));
+    return TETSIM_OK;
 }
-int tetsim_set_peers(tetsim_t *h, const void *handles) {
-    (void)h; (void)handles;
-    return fail(TETSIM_E_STATE, "fused peer-memory exchange is not built yet");
+
+int tetsim_set_peers(tetsim_t *h, const void *blobs) {
+    if (!h || !blobs) return fail(TETSIM_E_INVALID, "null argument");
+    if (!h->peer) return fail(TETSIM_E_STATE, "tetsim_set_peers needs a multi-GPU handle created with exchange = 2");
+    if (h->peersSet) return fail(TETSIM_E_STATE, "peers are already set");
+    DeviceGuard g(h->device);
+    const ClusterPlan &P = h->plan;
+    std::vector<unsigned char *> base(std::max<size_t>(P.hxPeers.size(), 1), nullptr);
+    for (size_t qi = 0; qi < P.hxPeers.size(); qi++) {
+        const int q = P.hxPeers[qi];
+        PeerBlob b;
+        memcpy(&b, (const unsigned char *)blobs + (size_t)q * sizeof(PeerBlob), sizeof(b));
+        if (b.magic != kPeerMagic || b.rank != q)
+            return fail(TETSIM_E_INVALID, "blob " + std::to_string(q) + " is not rank " + std::to_string(q) + "'s tetsim_get_ipc_handle output");
+        // both sides derive each other's layout from the same global partition: cross-check it
+        if (b.total != P.pxRemoteTotal[qi])
+            return fail(TETSIM_E_STATE, "rank " + std::to_string(q) + " reports " + std::to_string(b.total) + " exchange entries, this rank's plan expects " + std::to_string(P.pxRemoteTotal[qi]) + " (different mesh or options?)");
+        if (b.pid == (int32_t)getpid()) {  // a handle of this process: its pointer is valid here
+            if (b.device != h->device) {
+                int can = 0;
+                CK(cudaDeviceCanAccessPeer(&can, h->device, b.device));
+                if (!can) return fail(TETSIM_E_CUDA, "device " + std::to_string(h->device) + " cannot access device " + std::to_string(b.device));
+                cudaError_t pe = cudaDeviceEnablePeerAccess(b.device, 0);
+                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CK(pe);
+                cudaGetLastError();
+            }
+            base[qi] = (unsigned char *)(uintptr_t)b.rawPtr;
+        } else {
+            cudaIpcMemHandle_t ipc;
+            memcpy(&ipc, b.ipc, sizeof(ipc));
+            void *mapped = nullptr;
+            CK(cudaIpcOpenMemHandle(&mapped, ipc, cudaIpcMemLazyEnablePeerAccess));
+            h->peerOpened.push_back(mapped);
+            base[qi] = (unsigned char *)mapped + b.offset;
+        }
+    }
+    CK(cudaMemcpyAsync(h->peerBase.p, base.data(), base.size() * sizeof(unsigned char *), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->peersSet = true;
+    return TETSIM_OK;
 }
 
 int tetsim_level_schedule(const int32_t *tetIds, int32_t numTets, int32_t numVerts, int32_t *level) {
@@ -1076,6 +1220,29 @@ int tetsim_plan_partition(const float *verts, int32_t numVerts, const int32_t *t
         for (int t : P.recordTet) if (t >= 0) localTets[n++] = t;
     }
     return TETSIM_OK;
+}
+
+int tetsim_plan_halo(const float *verts, int32_t numVerts, const int32_t *tetIds, int32_t numTets, int32_t clusterSize,
+                     int32_t reorder, int32_t rank, int32_t worldSize, int32_t capacity, int32_t *peers,
+                     int32_t *segStart, int32_t *remoteOff, int32_t *remoteTotal, int32_t *remoteSlot) {
+    if (!verts || !tetIds || !peers || !segStart || !remoteOff || !remoteTotal || !remoteSlot) return fail(TETSIM_E_INVALID, "null argument");
+    if (clusterSize < 1 || worldSize < 1 || rank < 0 || rank >= worldSize) return fail(TETSIM_E_INVALID, "bad clusterSize/rank/worldSize");
+    for (int64_t c = 0; c < 4 * (int64_t)numTets; c++)
+        if (tetIds[c] < 0 || tetIds[c] >= numVerts) return fail(TETSIM_E_INVALID, "vertex id out of range");
+    std::vector<int> rankStart;
+    std::vector<int> order = solver_order(numVerts, numTets, verts, tetIds, reorder != 0, worldSize, rankStart);
+    ClusterPlan P;
+    std::string err;
+    if (!build_cluster_plan(numVerts, numTets, tetIds, order, rankStart, clusterSize, rank, worldSize, P, err)) return fail(TETSIM_E_INVALID, err);
+    if (worldSize > 1 && !P.haloOk) return fail(TETSIM_E_STATE, "neighbour lists need worldSize <= 64");
+    const int np = (int)P.hxPeers.size();
+    if (np > capacity) return fail(TETSIM_E_INVALID, "capacity too small");
+    for (int i = 0; i < np; i++) {
+        peers[i] = P.hxPeers[i]; segStart[i] = P.hxSegStart[i];
+        remoteOff[i] = P.pxRemoteOff[i]; remoteTotal[i] = P.pxRemoteTotal[i]; remoteSlot[i] = P.pxRemoteSlot[i];
+    }
+    segStart[np] = np ? P.hxSegStart[np] : 0;
+    return np;
 }
 
 }  // extern "C"

@@ -71,7 +71,7 @@ class _Body:
             reorder=int(bool(reorder)), clusterSize=int(cluster_size),
             trackVolError=-1 if track_vol_error is None else int(bool(track_vol_error)),
             device=int(device), rank=int(rank), worldSize=int(world_size), stream=int(stream) or None,
-            exchange={"allreduce": 0, "halo": 1}[exchange])
+            exchange={"allreduce": 0, "halo": 1, "peer": 2}[exchange])
         if nccl_unique_id is not None:
             self._nccl_id = C.create_string_buffer(bytes(nccl_unique_id), 128)
             opt.ncclUniqueId = C.cast(self._nccl_id, C.c_void_p)
@@ -122,6 +122,19 @@ class _Body:
 
     def synchronize(self):
         check(_capi.lib().tetsim_synchronize(self._h))
+
+    # ---- peer-memory exchange (exchange="peer"): hand-shake of the exchange buffers ----
+    def ipc_handle(self) -> bytes:
+        """This rank's blob for tetsim_set_peers (all-gather them in rank order)."""
+        buf = C.create_string_buffer(_capi.PEER_BLOB_BYTES)
+        check(_capi.lib().tetsim_get_ipc_handle(self._h, buf))
+        return buf.raw
+
+    def set_peers(self, blobs):
+        """blobs: the ipc_handle() of every rank, in rank order."""
+        raw = b"".join(bytes(b) for b in blobs)
+        assert len(raw) % _capi.PEER_BLOB_BYTES == 0
+        check(_capi.lib().tetsim_set_peers(self._h, C.create_string_buffer(raw, len(raw))))
 
     # ---- readable state (src/Softbody.js:12-20) ----
     def _fetch3(self, name, fn):

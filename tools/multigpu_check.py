@@ -28,7 +28,7 @@ ap.add_argument("--cells", default="64,16,16")
 ap.add_argument("--substeps", type=int, default=40)
 ap.add_argument("--iters", type=int, default=2)
 ap.add_argument("--cluster-size", type=int, default=256)
-ap.add_argument("--exchange", default="allreduce")
+ap.add_argument("--exchange", default="allreduce", choices=["allreduce", "halo", "peer"])
 a = ap.parse_args()
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -38,17 +38,25 @@ cells = tuple(int(c) for c in a.cells.split(","))
 v, t = mesh.make_beam(cells, h=0.02, y0=0.3, jitter=0.15)
 N = v.size // 3
 
-buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
-if rank == 0:
-    raw = ctypes.create_string_buffer(128)
-    _capi.check(_capi.lib().tetsim_nccl_unique_id(raw))
-    buf.copy_(torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8))
-dist.broadcast(buf, 0)
-nccl_id = bytes(buf.cpu().numpy().tobytes())
+nccl_id = None
+if a.exchange != "peer":   # the peer-memory exchange needs no NCCL communicator of its own
+    buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        raw = ctypes.create_string_buffer(128)
+        _capi.check(_capi.lib().tetsim_nccl_unique_id(raw))
+        buf.copy_(torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8))
+    dist.broadcast(buf, 0)
+    nccl_id = bytes(buf.cpu().numpy().tobytes())
 
 pp = dict(ts.DEFAULT_PHYSICS_PARAMS, numSubsteps=20, worldBounds=list(mesh.wide_bounds(16.0)))
 body = ts.SoftBody(v, t, None, pp, solver="jacobi", iters=a.iters, cluster_size=a.cluster_size, device=local,
                    rank=rank, world_size=world, nccl_unique_id=nccl_id, exchange=a.exchange)
+if a.exchange == "peer":   # hand-shake: all-gather the exchange-buffer handles, map the sharers'
+    mine = torch.frombuffer(bytearray(body.ipc_handle()), dtype=torch.uint8).cuda()
+    blobs = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(blobs, mine)
+    body.set_peers([bytes(b.cpu().numpy().tobytes()) for b in blobs])
+    dist.barrier()
 info = body.info()
 for _ in range(a.substeps // 20):
     body.step(pp)
@@ -89,6 +97,8 @@ if rank == 0:
         print("FAIL: N-rank result differs from the single-GPU result")
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.broadcast(flag, 0)
+body.synchronize()
+dist.barrier()   # every rank idle before any exchange buffer is freed
 body.close()
 dist.destroy_process_group()
 sys.exit(0 if int(flag.item()) == 1 else 1)

@@ -37,10 +37,10 @@ def V(tpt=0, stages=0, minb=0):
     return e
 
 
-VARIANTS = {   # T -> list of env dicts (the first is the default kernel: 1 tet per thread, 3 stages)
-    128: [V(), V(2, 2), V(2, 3)],
-    256: [V(), V(0, 2), V(2, 3), V(2, 2), V(2, 2, 6), V(2, 2, 8), V(2, 3, 8), V(4, 2)],
-    512: [V(), V(2, 2), V(2, 2, 3), V(2, 2, 4), V(2, 3, 4), V(4, 2), V(4, 2, 3)],
+VARIANTS = {   # T -> list of env dicts (the first is the default kernel of that tile size: 2 tets per thread, 2 stages)
+    128: [V(), V(1, 3), V(2, 3)],
+    256: [V(), V(1, 3), V(2, 3), V(2, 2, 6), V(4, 2)],
+    512: [V(), V(1), V(2, 2, 3), V(2, 3, 4), V(4, 2)],
 }
 KEYS = ("TETSIM_TILE_TPT", "TETSIM_TILE_STAGES", "TETSIM_TILE_MINB")
 
