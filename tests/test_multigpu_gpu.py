@@ -36,7 +36,7 @@ def test_peer_exchange_single_process(world, deterministic, monkeypatch):
     from tetsim_b200 import mesh
 
     monkeypatch.setenv("TETSIM_PEER_TIMEOUT_MS", "3000")   # a broken protocol fails in seconds instead of stalling the box
-    v, t = mesh.make_beam((48, 10, 10), h=0.02, y0=0.12, jitter=0.15)
+    v, t = mesh.make_beam((48, 10, 10), h=0.02, y0=0.004, jitter=0.15)   # reaches the floor within the 60 substeps
     N = v.size // 3
     pp = dict(ts.DEFAULT_PHYSICS_PARAMS, numSubsteps=20, worldBounds=list(mesh.wide_bounds(16.0)))
     kw = dict(solver="jacobi", iters=2, cluster_size=128, deterministic=deterministic)
