@@ -192,8 +192,7 @@ def main():
 
     verts, tets = mesh.make_beam(cells)
     N, M = verts.size // 3, tets.size // 4
-    nccl_id = None
-    if world > 1 and args.exchange != "peer":
+    def make_nccl_id():
         buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             import ctypes
@@ -201,20 +200,35 @@ def main():
             _capi.check(_capi.lib().tetsim_nccl_unique_id(raw))
             buf.copy_(torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8))
         dist.broadcast(buf, 0)
-        nccl_id = bytes(buf.cpu().numpy().tobytes())
+        return bytes(buf.cpu().numpy().tobytes())
+
     pp = dict(ts.DEFAULT_PHYSICS_PARAMS, numSubsteps=args.substeps, worldBounds=list(mesh.wide_bounds(64.0)))
     stream = torch.cuda.Stream(device=local_rank)   # a real (non-default) stream: the library enqueues on it, events time it
     torch.cuda.set_stream(stream)
-    body = ts.SoftBody(verts, tets, None, pp, solver="jacobi", arithmetic="fast", iters=args.iters,
-                       cluster_size=args.cluster_size, reorder=not args.no_reorder, deterministic=not args.atomic,
-                       device=local_rank, stream=stream.cuda_stream, rank=rank, world_size=world,
-                       nccl_unique_id=nccl_id, exchange=args.exchange)
+
+    def make_body(nccl_id):
+        return ts.SoftBody(verts, tets, None, pp, solver="jacobi", arithmetic="fast", iters=args.iters,
+                           cluster_size=args.cluster_size, reorder=not args.no_reorder, deterministic=not args.atomic,
+                           device=local_rank, stream=stream.cuda_stream, rank=rank, world_size=world,
+                           nccl_unique_id=nccl_id, exchange=args.exchange)
+
+    body = make_body(make_nccl_id() if world > 1 and args.exchange != "peer" else None)
     if world > 1 and args.exchange == "peer":   # hand-shake of the peer-memory exchange buffers
         mine = torch.frombuffer(bytearray(body.ipc_handle()), dtype=torch.uint8).cuda()
         blobs = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(blobs, mine)
-        body.set_peers([bytes(b.cpu().numpy().tobytes()) for b in blobs])
-        dist.barrier()
+        ok = torch.ones(1, dtype=torch.int32, device="cuda")
+        try:
+            body.set_peers([bytes(b.cpu().numpy().tobytes()) for b in blobs])
+        except ts.TetSimError as e:   # e.g. no peer access between two devices: every rank falls back together
+            sys.stderr.write("rank %d: peer-memory exchange unavailable (%s); falling back to the NCCL neighbour exchange\n" % (rank, e))
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            body.close()
+            args.exchange = "halo"
+            nccl_id = make_nccl_id()
+            body = make_body(nccl_id)
     info = body.info()
 
     def barrier():
