@@ -25,8 +25,9 @@ def test_partitioned_jacobi_matches_single_gpu(world, exchange):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
 
 
-@pytest.mark.parametrize("world,deterministic", [(2, True), (3, True), (2, False)])
-def test_peer_exchange_single_process(world, deterministic, monkeypatch):
+@pytest.mark.parametrize("world,deterministic,fused", [(2, True, True), (3, True, True), (4, True, True), (2, True, False),
+                                                       (2, False, False)])
+def test_peer_exchange_single_process(world, deterministic, fused, monkeypatch):
     """The peer-memory exchange protocol (push into the sharers' buffers + epoch flags, wait + rank-ordered reduce)
     driven on ONE GPU: `world` handles of this process, each owning one tet partition, are each other's peers (the
     blob carries the owner's pointer, so no cudaIpc mapping is involved).  Merged positions must agree with the
@@ -36,11 +37,15 @@ def test_peer_exchange_single_process(world, deterministic, monkeypatch):
     from tetsim_b200 import mesh
 
     monkeypatch.setenv("TETSIM_PEER_TIMEOUT_MS", "3000")   # a broken protocol fails in seconds instead of stalling the box
+    # fused: the tile kernel pushes and the vertex kernel waits + reduces (2 launches per iteration, the default with the
+    # deterministic flush); unfused: boundary tiles / push / interior tiles / wait + reduce / vertex kernel
+    monkeypatch.setenv("TETSIM_PEER_UNFUSED", "0" if fused else "1")
     v, t = mesh.make_beam((48, 10, 10), h=0.02, y0=0.004, jitter=0.15)   # reaches the floor within the 60 substeps
     N = v.size // 3
     pp = dict(ts.DEFAULT_PHYSICS_PARAMS, numSubsteps=20, worldBounds=list(mesh.wide_bounds(16.0)))
     kw = dict(solver="jacobi", iters=2, cluster_size=128, deterministic=deterministic)
     bodies = [ts.SoftBody(v, t, None, pp, rank=r, world_size=world, exchange="peer", **kw) for r in range(world)]
+    assert all(b.info()["launchesPerSubstep"] == (2 * 2 if fused else 4 * 2) for b in bodies)
     with pytest.raises(ts.TetSimError):
         bodies[0].step(pp)                       # peers not set yet
     blobs = [b.ipc_handle() for b in bodies]

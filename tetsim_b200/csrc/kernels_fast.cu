@@ -68,6 +68,67 @@ __device__ __forceinline__ void cp_async16(void *dst, const void *src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Peer-memory exchange, sender side for ONE active boundary vertex b (layout and protocol: launch.h, PeerArgs): add this
+// rank's tile partials in their fixed order, keep the sum, store it into every sharer's receive buffer; the caller
+// that completes the rank's last push publishes the epoch.
+__device__ __forceinline__ void peer_push_vertex(const PeerArgs &a, int b, unsigned e, bool coherentPartials) {
+    const int i = a.boundaryBegin + b;
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = a.vpStart[i]; j < a.vpStart[i + 1]; j++) {
+        const float4 s = coherentPartials ? __ldcg(a.part + a.vpSlot[j]) : __ldg(a.part + a.vpSlot[j]);
+        sum.x += s.x; sum.y += s.y; sum.z += s.z;
+    }
+    a.bsum[b] = sum;
+    for (int j = a.pxStart[b]; j < a.pxStart[b + 1]; j++) {
+        const int q = a.pxPeer[j];
+        float4 *dst = reinterpret_cast<float4 *>(a.peerBase[q] + kPeerRecvOff) + (size_t)(e & 1u) * a.remoteTotal[q] + a.pxEntry[j];
+        *dst = sum;  // NVLink store into the sharer's receive buffer
+    }
+}
+__device__ __forceinline__ void peer_publish(const PeerArgs &a, unsigned *ctl, unsigned e) {
+    __threadfence_system();  // every push of this rank is ordered before the flags
+    for (int q = 0; q < a.numPeers; q++) st_release_sys(reinterpret_cast<unsigned *>(a.peerBase[q]) + a.remoteSlot[q], e);
+    ctl[1] = 0u;
+    *reinterpret_cast<volatile unsigned *>(ctl) = e;
+}
+// Receiver side: wait until every sharer has published epoch e (a block calls this with all its threads).
+__device__ __forceinline__ void peer_wait_block(const PeerArgs &a, unsigned *ctl, unsigned e) {
+    // a wait that timed out once is never repeated (the error is sticky and reported by the host): no pile-up of timeouts
+    if ((int)threadIdx.x < a.numPeers && *reinterpret_cast<volatile unsigned *>(ctl + 2) == 0u) {
+        const unsigned *flag = reinterpret_cast<const unsigned *>(a.self) + threadIdx.x;
+        const unsigned long long t0 = global_timer_ns();
+        while ((int)(ld_acquire_sys(flag) - e) < 0) {
+            if (global_timer_ns() - t0 > a.timeoutNs) { atomicExch(ctl + 2, 1u); break; }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ float4 peer_reduce_vertex(const PeerArgs &a, int b, unsigned e) {
+    const float4 *recv = reinterpret_cast<const float4 *>(a.self + kPeerRecvOff) + (size_t)(e & 1u) * a.selfTotal;
+    float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+    for (int j = a.srcStart[b]; j < a.srcStart[b + 1]; j++) {
+        const int k = a.src[j];
+        const float4 v = k < a.numBoundary ? a.bsum[k] : __ldcg(recv + (k - a.numBoundary));  // written by a peer: not through L1
+        sx += v.x; sy += v.y; sz += v.z;
+    }
+    return make_float4(sx, sy, sz, 0.0f);
+}
+
 // the same on 32-bit shared-window addresses (converted once per worker, not per call)
 __device__ __forceinline__ void mbar_expect_tx_a(uint32_t b, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
@@ -300,6 +361,24 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
                 if (a.acc) atomicAdd(a.acc + reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3])[j],
                                      make_float4(ax, ay, az, 0.0f));
                 else a.part[v0 + j] = make_float4(ax, ay, az, 0.0f);
+                if (a.px) {  // multi-GPU, fused exchange: the last tile partial of a boundary vertex triggers its push
+                    const PeerArgs &px = *a.px;
+                    const int id = reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3])[j];
+                    if (id >= px.boundaryBegin) {
+                        const int b = id - px.boundaryBegin;
+                        __threadfence();  // my partial is visible device-wide before my ticket
+                        const unsigned need = (unsigned)(px.vpStart[id + 1] - px.vpStart[id]);
+                        if (atomicAdd(px.cnt + b, 1u) + 1u == need) {
+                            px.cnt[b] = 0u;   // every contributor of this iteration has passed: re-arm for the next one
+                            __threadfence();  // the other tiles' partials are visible to me
+                            unsigned *ctl = reinterpret_cast<unsigned *>(px.self + kPeerCtlOff);
+                            const unsigned e = *reinterpret_cast<volatile unsigned *>(ctl) + 1u;  // advanced only after the rank's last push
+                            peer_push_vertex(px, b, e, true);
+                            __threadfence_system();  // my remote stores are ordered before my ticket
+                            if (atomicAdd(ctl + 1, 1u) + 1u == (unsigned)px.numActive) peer_publish(px, ctl, e);
+                        }
+                    }
+                }
             }
     }
 }
@@ -508,9 +587,18 @@ void launch_build_tiles(cudaStream_t s, int clusterSize, int numRecords, const i
 template <int MODE>
 __global__ void k_jacobi_apply(int begin, int end, ApplyArgs a) {
     int i = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned epoch = 0u;
+    if (a.px && begin + (int)((blockIdx.x + 1) * blockDim.x) > a.boundaryBegin) {  // this block holds rank-shared vertices
+        unsigned *ctl = reinterpret_cast<unsigned *>(a.px->self + kPeerCtlOff);
+        epoch = *reinterpret_cast<volatile unsigned *>(ctl);  // advanced by the tile kernel's last push
+        peer_wait_block(*a.px, ctl, epoch);
+    }
     if (i >= end) return;
     float sx = 0.0f, sy = 0.0f, sz = 0.0f;
-    if (a.bsum && i >= a.boundaryBegin) {
+    if (a.px && i >= a.boundaryBegin) {  // sharers' sums added in ascending rank order: identical on every sharer
+        const float4 s = peer_reduce_vertex(*a.px, i - a.boundaryBegin, epoch);
+        sx = s.x; sy = s.y; sz = s.z;
+    } else if (a.bsum && i >= a.boundaryBegin) {
         float4 s = a.bsum[i - a.boundaryBegin];
         sx = s.x; sy = s.y; sz = s.z;
     } else if (a.acc) {
@@ -597,59 +685,33 @@ void launch_halo_reduce(cudaStream_t s, int nB, const int *srcStart, const int *
 }
 
 // ---- peer-memory exchange (layout and protocol: launch.h, PeerArgs) ----
-__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long global_timer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
 
 __global__ void k_peer_push(PeerArgs a) {
     unsigned *ctl = reinterpret_cast<unsigned *>(a.self + kPeerCtlOff);
     // every block reads the epoch before it takes its ticket, the last ticket holder advances it: no block sees the new value
     const unsigned e = *reinterpret_cast<volatile unsigned *>(ctl) + 1u;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < a.numBoundary) {
-        const int p0 = a.pxStart[b], p1 = a.pxStart[b + 1];
-        if (p1 > p0) {  // active: touched by this rank's tets
+    if (b < a.numBoundary && a.pxStart[b + 1] > a.pxStart[b]) {  // active: touched by this rank's tets
+        if (a.acc) {  // atomic flush: the accumulator holds the sum
             const int i = a.boundaryBegin + b;
-            float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (a.acc) {
-                sum = a.acc[i];
-                sum.w = 0.f;
-                a.acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            } else {
-                for (int j = a.vpStart[i]; j < a.vpStart[i + 1]; j++) {
-                    const float4 s = ldg4(a.part + a.vpSlot[j]);
-                    sum.x += s.x; sum.y += s.y; sum.z += s.z;
-                }
-            }
+            float4 sum = a.acc[i];
+            sum.w = 0.f;
+            a.acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             a.bsum[b] = sum;
-            for (int j = p0; j < p1; j++) {
+            for (int j = a.pxStart[b]; j < a.pxStart[b + 1]; j++) {
                 const int q = a.pxPeer[j];
                 float4 *dst = reinterpret_cast<float4 *>(a.peerBase[q] + kPeerRecvOff) + (size_t)(e & 1u) * a.remoteTotal[q] + a.pxEntry[j];
-                *dst = sum;  // NVLink store into the sharer's receive buffer
+                *dst = sum;
             }
+        } else {
+            peer_push_vertex(a, b, e, false);
         }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence_system();  // this block's remote stores are ordered before the ticket
         const unsigned ticket = atomicAdd(ctl + 1, 1u);
-        if (ticket == gridDim.x - 1) {
-            __threadfence_system();  // ... and every block's before the flags
-            for (int q = 0; q < a.numPeers; q++)
-                st_release_sys(reinterpret_cast<unsigned *>(a.peerBase[q]) + a.remoteSlot[q], e);
-            ctl[1] = 0u;
-            *reinterpret_cast<volatile unsigned *>(ctl) = e;
-        }
+        if (ticket == gridDim.x - 1) peer_publish(a, ctl, e);
     }
 }
 void launch_peer_push(cudaStream_t s, const PeerArgs &a) {
@@ -658,29 +720,11 @@ void launch_peer_push(cudaStream_t s, const PeerArgs &a) {
 
 __global__ void k_peer_reduce(PeerArgs a) {
     unsigned *ctl = reinterpret_cast<unsigned *>(a.self + kPeerCtlOff);
-    const unsigned e = *reinterpret_cast<volatile unsigned *>(ctl);  // advanced by this iteration's k_peer_push
-    // a wait that timed out once is never repeated (the error is sticky and reported by the host): no pile-up of timeouts
-    if ((int)threadIdx.x < a.numPeers && *reinterpret_cast<volatile unsigned *>(ctl + 2) == 0u) {
-        const unsigned *flag = reinterpret_cast<const unsigned *>(a.self) + threadIdx.x;
-        const unsigned long long t0 = global_timer_ns();
-        while ((int)(ld_acquire_sys(flag) - e) < 0) {
-            if (global_timer_ns() - t0 > a.timeoutNs) { atomicExch(ctl + 2, 1u); break; }
-            __nanosleep(64);
-        }
-    }
-    __syncthreads();
+    const unsigned e = *reinterpret_cast<volatile unsigned *>(ctl);  // advanced by this iteration's push
+    peer_wait_block(a, ctl, e);
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= a.numBoundary) return;
-    const int s0 = a.srcStart[b], s1 = a.srcStart[b + 1];
-    if (s0 == s1) return;
-    const float4 *recv = reinterpret_cast<const float4 *>(a.self + kPeerRecvOff) + (size_t)(e & 1u) * a.selfTotal;
-    float sx = 0.0f, sy = 0.0f, sz = 0.0f;
-    for (int j = s0; j < s1; j++) {
-        const int k = a.src[j];
-        const float4 v = k < a.numBoundary ? a.bsum[k] : __ldcg(recv + (k - a.numBoundary));  // written by a peer: not through L1
-        sx += v.x; sy += v.y; sz += v.z;
-    }
-    a.bsum[b] = make_float4(sx, sy, sz, 0.0f);
+    if (b >= a.numBoundary || a.srcStart[b] == a.srcStart[b + 1]) return;
+    a.bsum[b] = peer_reduce_vertex(a, b, e);  // the own term is bsum[b] itself: read before this write
 }
 void launch_peer_reduce(cudaStream_t s, const PeerArgs &a) {
     if (a.numBoundary > 0) k_peer_reduce<<<cdiv(a.numBoundary, 256), 256, 0, s>>>(a);

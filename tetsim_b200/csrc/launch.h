@@ -50,6 +50,7 @@ const KernelTable *fast_kernels();
 //   tet block  (T * 56 B, one bulk async copy): planes A[T] float4 (Q0..Q3), B[T] float4 (Q4..Q7),
 //              C[T] float4 (Q8, invRestVolume, slot01, slot23), D[T] uint2 (dest01, dest23)
 //   meta block (variable size, one bulk async copy): see ClusterPlan::tileMeta in mesh_prep.h
+struct PeerArgs;
 struct TileArgs {
     const float4 *x4;               // handle-local vertex records (x, y, z, invMass)
     const unsigned char *tets;      // [numTiles * T * 56]
@@ -63,6 +64,7 @@ struct TileArgs {
     const SubstepParams *sp;
     int staggerNs;                  // initial delay per resident-CTA slot (breaks phase lockstep of co-resident CTAs)
     int debugSkip;                  // measurement only (tetsim_time_kernel + TETSIM_TILE_DEBUG): 1 no vertex phase, 2 no math, 4 no gather
+    const PeerArgs *px;             // DEVICE copy of the peer-exchange arguments: fused push of the boundary sums, or NULL
 };
 void launch_jacobi_tiles(cudaStream_t, int clusterSize, const TileArgs &a);
 size_t jacobi_tiles_smem(int clusterSize, const TileArgs &a);
@@ -77,6 +79,7 @@ struct ApplyArgs {
     float4 *acc;                    // atomic-flush accumulator (read and re-zeroed) or NULL
     const float *invVal;            // 1 / valence
     const float4 *bsum;             // all-reduced boundary sums for vertices >= boundaryBegin, or NULL
+    const PeerArgs *px;             // DEVICE copy: wait for the sharers' flags and reduce in rank order here (fused), or NULL
     int boundaryBegin;
     const SubstepParams *sp;
     const int *vertId;              // handle-local -> caller's vertex id (for the grab test)
@@ -115,7 +118,15 @@ struct PeerArgs {
     int selfTotal;                        // parity stride of my receive buffer
     const int *srcStart, *src;            // reduce sources (ClusterPlan hxSrcStart / hxSrc)
     unsigned long long timeoutNs;         // give up waiting after this long (sets ctl[2])
+    unsigned *cnt;                        // [numBoundary] fused push: tile partials of each boundary vertex delivered so far
+    int numActive;                        // boundary vertices this rank's tets touch (= pushes per iteration)
 };
+// Fused form (deterministic flush): the tile kernel itself pushes.  The thread that stores the LAST tile partial of a
+// boundary vertex (per-vertex ticket) adds the partials in their fixed order, keeps the sum in bsum[], stores it into
+// the sharers' buffers, and the thread that completes the last push publishes the epoch flags -- boundary tiles run
+// first, so the sums cross NVLink while the interior tiles are still being solved, inside ONE launch.  The vertex
+// kernel (k_jacobi_apply) then waits for the sharers' flags and reduces in rank order: 2 launches per iteration, as on
+// a single GPU.
 void launch_peer_push(cudaStream_t, const PeerArgs &a);
 void launch_peer_reduce(cudaStream_t, const PeerArgs &a);
 

@@ -187,6 +187,10 @@ struct tetsim {
     std::vector<void *> peerOpened;         // bases returned by cudaIpcOpenMemHandle (closed at destroy)
     DevBuf<unsigned char *> peerBase;       // [peers] mapped exchange allocation of each sharer
     DevBuf<int> pxStart, pxPeer, pxEntry, pxRemoteTotal, pxRemoteSlot;
+    DevBuf<unsigned> pxCnt;                 // fused push: per boundary vertex, tile partials delivered this iteration
+    DevBuf<PeerArgs> pxArgs;                // device copy of peer_args(h), read by the tile and vertex kernels
+    bool peerFused = false;                 // the tile kernel pushes, the vertex kernel waits + reduces (2 launches/iteration)
+    int pxNumActive = 0;
     int maxValence = 0;
 
     int64_t deviceBytes() const {
@@ -443,14 +447,23 @@ int build_jacobi_cluster(tetsim *h, const std::vector<float> &verts, const std::
         CK(h->pxRemoteTotal.upload(P.pxRemoteTotal, s));
         CK(h->pxRemoteSlot.upload(P.pxRemoteSlot, s));
         CK(h->peerBase.alloc(std::max<size_t>(P.hxPeers.size(), 1)));
-        for (int b = 0; b < P.numBoundary; b++)
+        CK(h->pxCnt.alloc(std::max<size_t>((size_t)P.numBoundary, 1)));
+        CK(cudaMemsetAsync(h->pxCnt.p, 0, h->pxCnt.bytes(), s));
+        CK(h->pxArgs.alloc(1));
+        h->pxNumActive = 0;
+        for (int b = 0; b < P.numBoundary; b++) {
             if (!P.boundaryActive[b]) h->h_vertId[(size_t)P.numInterior + b] = -1;
+            else h->pxNumActive++;
+        }
+        const char *unfused = getenv("TETSIM_PEER_UNFUSED");
+        // the fused push counts tile partials, so it needs the deterministic flush (per-tile partial sums)
+        h->peerFused = h->opt.deterministic != 0 && h->pxNumActive > 0 && !(unfused && unfused[0] == '1');
     }
     bool identity = (int)h->h_vertId.size() == N;
     for (int i = 0; identity && i < N; i++) identity = h->h_vertId[i] == i;
     if (identity) h->h_vertId.clear();
     h->maxValence = P.maxValence;
-    h->launchesPerSubstep = 2 * h->opt.iters + (h->opt.worldSize > 1 ? 2 * h->opt.iters : 0);
+    h->launchesPerSubstep = 2 * h->opt.iters + (h->opt.worldSize > 1 && !h->peerFused ? 2 * h->opt.iters : 0);
     CK(cudaStreamSynchronize(s));
     return TETSIM_OK;
 }
@@ -491,6 +504,7 @@ PeerArgs peer_args(const tetsim *h) {
     a.peerBase = h->peerBase.p; a.remoteTotal = h->pxRemoteTotal.p; a.remoteSlot = h->pxRemoteSlot.p;
     a.self = h->peerBuf.p; a.selfTotal = (int)P.hxSendIdx.size();
     a.srcStart = h->hxSrcStart.p; a.src = h->hxSrc.p;
+    a.cnt = h->pxCnt.p; a.numActive = h->pxNumActive;
     unsigned long long ms = 10000ull;
     if (const char *e = getenv("TETSIM_PEER_TIMEOUT_MS")) { long v = atol(e); if (v > 0) ms = (unsigned long long)v; }
     a.timeoutNs = ms * 1000000ull;
@@ -549,6 +563,14 @@ int enqueue_substeps(tetsim *h, int count) {
                         if (!multi) {
                             launch_jacobi_tiles(s, P.T, ca);
                             h->enq += 2;  // tile kernel + vertex kernel
+                        } else if (h->peer && h->peerFused) {
+                            // ONE tile launch: boundary tiles first, the thread that completes a boundary vertex pushes
+                            // its sum into the sharers' buffers; the vertex kernel below waits for theirs and reduces
+                            TileArgs cf = ca;
+                            cf.px = h->pxArgs.p;
+                            launch_jacobi_tiles(s, P.T, cf);
+                            aa.px = h->pxArgs.p;
+                            h->enq += 2;
                         } else if (h->peer) {
                             // boundary tiles -> push this rank's boundary sums into the sharers' buffers (+ flag)
                             // -> interior tiles (the sharers' stores arrive meanwhile) -> wait + rank-ordered reduce
@@ -1186,6 +1208,8 @@ int tetsim_set_peers(tetsim_t *h, const void *blobs) {
         }
     }
     CK(cudaMemcpyAsync(h->peerBase.p, base.data(), base.size() * sizeof(unsigned char *), cudaMemcpyHostToDevice, h->stream));
+    const PeerArgs pa = peer_args(h);
+    CK(cudaMemcpyAsync(h->pxArgs.p, &pa, sizeof(pa), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->peersSet = true;
     return TETSIM_OK;
