@@ -129,6 +129,53 @@ __device__ __forceinline__ float4 peer_reduce_vertex(const PeerArgs &a, int b, u
     return make_float4(sx, sy, sz, 0.0f);
 }
 
+// ---- fused form: self-validating 32-byte entries (launch.h) ----
+__device__ __forceinline__ void st_volatile_u4(void *p, unsigned x, unsigned y, unsigned z, unsigned w) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_volatile_u4(const void *p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+// sender: one tile partial (px, py, pz) of boundary vertex b, partial index i of n, into every sharer's buffer
+__device__ __forceinline__ void peer_push_partial(const PeerArgs &a, int b, int i, int n, unsigned e, float px, float py, float pz) {
+    const unsigned tag = (e & 0x0fffffffu) * (unsigned)kPeerK + (unsigned)(n - 1);  // 28-bit epoch, count - 1
+    for (int j = a.pxStart[b]; j < a.pxStart[b + 1]; j++) {
+        const int q = a.pxPeer[j];
+        unsigned char *dst = a.peerBase[q] + kPeerRecvOff +
+                             (((size_t)(e & 1u) * a.remoteTotal[q] + a.pxEntry[j]) * kPeerK + i) * 32;
+        st_volatile_u4(dst, __float_as_uint(px), tag, __float_as_uint(py), tag);
+        st_volatile_u4(dst + 16, __float_as_uint(pz), tag, 0u, tag);
+    }
+}
+// receiver: the partials one sharer delivered for receive entry E, added in the sharer's order.  Spins until the
+// entries carry this epoch's tag; after a timeout the sticky error flag is set and whatever is there is used.
+__device__ __forceinline__ float4 peer_poll_entry(const PeerArgs &a, unsigned *ctl, int E, unsigned e) {
+    const unsigned char *base = a.self + kPeerRecvOff + (((size_t)(e & 1u) * a.selfTotal + E) * kPeerK) * 32;
+    float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+    int n = 1;
+    unsigned long long t0 = 0ull;
+    for (int i = 0; i < n; i++) {
+        uint4 u, v;
+        for (unsigned spin = 0;; spin++) {
+            u = ld_volatile_u4(base + i * 32);
+            v = ld_volatile_u4(base + i * 32 + 16);
+            const unsigned tag = u.y;
+            if (tag / (unsigned)kPeerK == (e & 0x0fffffffu) && u.w == tag && v.y == tag && v.w == tag) { n = (int)(tag % (unsigned)kPeerK) + 1; break; }
+            if ((spin & 63u) == 63u) {
+                if (*reinterpret_cast<volatile unsigned *>(ctl + 2)) break;  // already failed once: do not pile up timeouts
+                const unsigned long long now = global_timer_ns();
+                if (t0 == 0ull) t0 = now;
+                else if (now - t0 > a.timeoutNs) { atomicExch(ctl + 2, 1u); break; }
+                __nanosleep(100);
+            }
+        }
+        sx += __uint_as_float(u.x); sy += __uint_as_float(u.z); sz += __uint_as_float(v.x);
+    }
+    return make_float4(sx, sy, sz, 0.0f);
+}
+
 // the same on 32-bit shared-window addresses (converted once per worker, not per call)
 __device__ __forceinline__ void mbar_expect_tx_a(uint32_t b, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
@@ -369,21 +416,15 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
                 if (a.acc) atomicAdd(a.acc + reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3])[j],
                                      make_float4(ax, ay, az, 0.0f));
                 else a.part[v0 + j] = make_float4(ax, ay, az, 0.0f);
-                if (a.px) {  // multi-GPU, fused exchange: the last tile partial of a boundary vertex triggers its push
+                if (a.px) {  // multi-GPU, fused exchange: a rank-shared vertex's tile partial goes straight to the sharers
                     const PeerArgs &px = *a.px;
-                    const int id = reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3])[j];
-                    if (id >= px.boundaryBegin) {
-                        const int b = id - px.boundaryBegin;
-                        __threadfence();  // my partial is visible device-wide before my ticket
-                        const unsigned need = (unsigned)(px.vpStart[id + 1] - px.vpStart[id]);
-                        if (atomicAdd(px.cnt + b, 1u) + 1u == need) {
-                            px.cnt[b] = 0u;   // every contributor of this iteration has passed: re-arm for the next one
-                            __threadfence();  // the other tiles' partials are visible to me
-                            unsigned *ctl = reinterpret_cast<unsigned *>(px.self + kPeerCtlOff);
-                            const unsigned e = *reinterpret_cast<volatile unsigned *>(ctl) + 1u;  // advanced only after the rank's last push
-                            peer_push_vertex(px, b, e, true);
-                            __threadfence_system();  // my remote stores are ordered before my ticket
-                            if (atomicAdd(ctl + 1, 1u) + 1u == (unsigned)px.numActive) peer_publish(px, ctl, e);
+                    const int slot = v0 + j;
+                    if (slot < px.numBoundarySlots) {
+                        const unsigned i = px.slotIdx[slot];
+                        if (i != 0xffu) {
+                            const int id = reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3])[j];
+                            const unsigned e = *reinterpret_cast<volatile unsigned *>(px.self + kPeerCtlOff) + 1u;  // advanced by the vertex kernel
+                            peer_push_partial(px, id - px.boundaryBegin, (int)i, px.vpStart[id + 1] - px.vpStart[id], e, ax, ay, az);
                         }
                     }
                 }
@@ -597,20 +638,40 @@ void launch_build_tiles(cudaStream_t s, int clusterSize, int numRecords, const i
 // Vertex side of the clustered Jacobi: x += (sum of the vertex's tile partials) / valence, optionally
 // fused with post (simulate() :213-239) and with the NEXT substep's predict (:198-202) so a substep
 // inside tetsim_step costs exactly two launches.
-template <int MODE>
+template <int MODE, bool PEER>
 __global__ void k_jacobi_apply(int begin, int end, ApplyArgs a) {
     int i = begin + blockIdx.x * blockDim.x + threadIdx.x;
     unsigned epoch = 0u;
-    if (a.px && begin + (int)((blockIdx.x + 1) * blockDim.x) > a.boundaryBegin) {  // this block holds rank-shared vertices
+    if (PEER) {  // fused peer exchange: this launch consumes epoch ctl[0] + 1; the last block to pass here advances it
         unsigned *ctl = reinterpret_cast<unsigned *>(a.px->self + kPeerCtlOff);
-        epoch = *reinterpret_cast<volatile unsigned *>(ctl);  // advanced by the tile kernel's last push
-        peer_wait_block(*a.px, ctl, epoch);
+        epoch = *reinterpret_cast<volatile unsigned *>(ctl) + 1u;
+        __syncthreads();  // every thread of the block has read the epoch before the block's ticket
+        if (threadIdx.x == 0 && atomicAdd(ctl + 1, 1u) == gridDim.x - 1) {
+            ctl[1] = 0u;
+            *reinterpret_cast<volatile unsigned *>(ctl) = epoch;
+        }
     }
     if (i >= end) return;
     float sx = 0.0f, sy = 0.0f, sz = 0.0f;
-    if (a.px && i >= a.boundaryBegin) {  // sharers' sums added in ascending rank order: identical on every sharer
-        const float4 s = peer_reduce_vertex(*a.px, i - a.boundaryBegin, epoch);
-        sx = s.x; sy = s.y; sz = s.z;
+    if (PEER && i >= a.boundaryBegin) {
+        // each sharer's partials in that sharer's order, the sharers in ascending rank order: identical on every sharer
+        const PeerArgs &px = *a.px;
+        unsigned *ctl = reinterpret_cast<unsigned *>(px.self + kPeerCtlOff);
+        const int b = i - a.boundaryBegin;
+        for (int j = px.srcStart[b]; j < px.srcStart[b + 1]; j++) {
+            const int k = px.src[j];
+            float4 s;
+            if (k < px.numBoundary) {  // this rank's own partials
+                s = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int t = a.vpStart[i]; t < a.vpStart[i + 1]; t++) {
+                    const float4 v = ldg4(a.part + a.vpSlot[t]);
+                    s.x += v.x; s.y += v.y; s.z += v.z;
+                }
+            } else {
+                s = peer_poll_entry(px, ctl, k - px.numBoundary, epoch);
+            }
+            sx += s.x; sy += s.y; sz += s.z;
+        }
     } else if (a.bsum && i >= a.boundaryBegin) {
         float4 s = a.bsum[i - a.boundaryBegin];
         sx = s.x; sy = s.y; sz = s.z;
@@ -647,9 +708,15 @@ void launch_jacobi_apply(cudaStream_t s, int begin, int end, int mode, const App
     int n = end - begin;
     if (n <= 0) return;
     const int TB = 256;
-    if (mode == 0) k_jacobi_apply<0><<<cdiv(n, TB), TB, 0, s>>>(begin, end, a);
-    else if (mode == 1) k_jacobi_apply<1><<<cdiv(n, TB), TB, 0, s>>>(begin, end, a);
-    else k_jacobi_apply<2><<<cdiv(n, TB), TB, 0, s>>>(begin, end, a);
+    if (a.px) {  // multi-GPU, fused peer exchange: poll + rank-ordered reduce for the rank-shared vertices
+        if (mode == 0) k_jacobi_apply<0, true><<<cdiv(n, TB), TB, 0, s>>>(begin, end, a);
+        else if (mode == 1) k_jacobi_apply<1, true><<<cdiv(n, TB), TB, 0, s>>>(begin, end, a);
+        else k_jacobi_apply<2, true><<<cdiv(n, TB), TB, 0, s>>>(begin, end, a);
+        return;
+    }
+    if (mode == 0) k_jacobi_apply<0, false><<<cdiv(n, TB), TB, 0, s>>>(begin, end, a);
+    else if (mode == 1) k_jacobi_apply<1, false><<<cdiv(n, TB), TB, 0, s>>>(begin, end, a);
+    else k_jacobi_apply<2, false><<<cdiv(n, TB), TB, 0, s>>>(begin, end, a);
 }
 
 __global__ void k_boundary_pack(int boundaryBegin, int nB, const int *__restrict__ vpStart,

@@ -118,15 +118,21 @@ struct PeerArgs {
     int selfTotal;                        // parity stride of my receive buffer
     const int *srcStart, *src;            // reduce sources (ClusterPlan hxSrcStart / hxSrc)
     unsigned long long timeoutNs;         // give up waiting after this long (sets ctl[2])
-    unsigned *cnt;                        // [numBoundary] fused push: tile partials of each boundary vertex delivered so far
-    int numActive;                        // boundary vertices this rank's tets touch (= pushes per iteration)
+    const unsigned char *slotIdx;         // fused push: [numBoundarySlots] partial index of a boundary-tile slot, 0xff = not shared
+    int numBoundarySlots;
 };
-// Fused form (deterministic flush): the tile kernel itself pushes.  The thread that stores the LAST tile partial of a
-// boundary vertex (per-vertex ticket) adds the partials in their fixed order, keeps the sum in bsum[], stores it into
-// the sharers' buffers, and the thread that completes the last push publishes the epoch flags -- boundary tiles run
-// first, so the sums cross NVLink while the interior tiles are still being solved, inside ONE launch.  The vertex
-// kernel (k_jacobi_apply) then waits for the sharers' flags and reduces in rank order: 2 launches per iteration, as on
-// a single GPU.
+// Fused form (deterministic flush; the default of exchange = 2): the tile kernel itself pushes, with NO synchronisation
+// at all on the sending side.  A thread that has just formed a tile's partial sum of a rank-shared vertex stores it, next
+// to its normal place in part[], straight into the receive buffer of every sharer as one self-validating 32-byte entry
+//   uint4 {x, tag, y, tag}, uint4 {z, tag, 0, tag}     tag = epoch * 16 + (number of partials of this vertex - 1)
+// (every 8-byte half carries the tag, the granularity NVLink stores are not torn at -- the scheme of NCCL's LL
+// protocol), slot (entry * kPeerK + partial index) of the parity half of the buffer.  Boundary tiles run first, so the
+// partials cross NVLink while the interior tiles are still being solved, inside ONE launch and without fences, flags
+// or tickets.  The vertex kernel (k_jacobi_apply) polls the entries of its rank-shared vertices until their tags show
+// the current epoch, adds each sharer's partials in that sharer's own order and the sharers' sums in ascending rank
+// order (so every sharer computes the identical value), and the last vertex block advances the epoch: 2 launches per
+// iteration, as on a single GPU.
+constexpr int kPeerK = 16;                // most tile partials a rank may hold for one shared vertex (checked at create)
 void launch_peer_push(cudaStream_t, const PeerArgs &a);
 void launch_peer_reduce(cudaStream_t, const PeerArgs &a);
 

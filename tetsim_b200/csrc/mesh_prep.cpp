@@ -602,6 +602,20 @@ bool build_cluster_plan(int numVerts, int numTets, const int *tetIds, const std:
     P.vpSlot.resize(P.clVerts.size());
     std::vector<int> fill(P.vpStart.begin(), P.vpStart.end() - 1);
     for (size_t s = 0; s < P.clVerts.size(); s++) P.vpSlot[fill[P.clVerts[s]]++] = (int)s;
+    if (worldSize > 1 && P.haloOk) {  // fused peer exchange: partial index of every boundary-tile slot
+        const size_t nSlots = (size_t)P.clVertStart[P.numBoundaryTiles];
+        P.pxSlotIdx.assign(nSlots, 0xff);
+        for (int b = 0; b < P.numBoundary; b++) {
+            const int id = P.numInterior + b;
+            const int n = P.vpStart[id + 1] - P.vpStart[id];
+            P.pxMaxPartials = std::max(P.pxMaxPartials, n);
+            for (int i = 0; i < n; i++) {
+                const size_t slot = (size_t)P.vpSlot[P.vpStart[id] + i];
+                if (slot >= nSlots) { err = "internal: a rank-shared vertex has a partial outside the boundary tiles"; return false; }
+                P.pxSlotIdx[slot] = (uint8_t)std::min(i, 254);
+            }
+        }
+    }
     return true;
 }
 

@@ -60,6 +60,11 @@ struct ClusterPlan {
     std::vector<int> pxStart;           // [numBoundary + 1] CSR over the push destinations of each active boundary vertex
     std::vector<int> pxPeer;            //   index into hxPeers
     std::vector<int> pxEntry;           //   entry inside that peer's receive buffer
+    // fused form: every TILE pushes its own partial of a boundary vertex (no sum, no ticket).  Partial slots of the
+    // boundary tiles come first in part[]; pxSlotIdx[slot] = which of its vertex's partials this slot is (its rank-local
+    // order, 0 .. count-1), 0xff for slots of vertices that are not rank-shared.
+    std::vector<uint8_t> pxSlotIdx;     // [clVertStart[numBoundaryTiles]]
+    int pxMaxPartials = 0;              // most tile partials any boundary vertex has on this rank
     int numLocalVerts = 0;              // interior + all boundary vertices
     int numInterior = 0;
     int numBoundary = 0;                // global count of rank-shared vertices (same on every rank)

@@ -187,10 +187,9 @@ struct tetsim {
     std::vector<void *> peerOpened;         // bases returned by cudaIpcOpenMemHandle (closed at destroy)
     DevBuf<unsigned char *> peerBase;       // [peers] mapped exchange allocation of each sharer
     DevBuf<int> pxStart, pxPeer, pxEntry, pxRemoteTotal, pxRemoteSlot;
-    DevBuf<unsigned> pxCnt;                 // fused push: per boundary vertex, tile partials delivered this iteration
+    DevBuf<unsigned char> pxSlotIdx;        // fused push: partial index of every boundary-tile partial slot
     DevBuf<PeerArgs> pxArgs;                // device copy of peer_args(h), read by the tile and vertex kernels
-    bool peerFused = false;                 // the tile kernel pushes, the vertex kernel waits + reduces (2 launches/iteration)
-    int pxNumActive = 0;
+    bool peerFused = false;                 // the tile kernel pushes, the vertex kernel polls + reduces (2 launches/iteration)
     int maxValence = 0;
 
     int64_t deviceBytes() const {
@@ -437,7 +436,14 @@ int build_jacobi_cluster(tetsim *h, const std::vector<float> &verts, const std::
     if (h->peer) {
         if (!P.haloOk) return fail(TETSIM_E_STATE, "the peer-memory exchange needs the neighbour lists (worldSize <= 64)");
         const size_t total = P.hxSendIdx.size();  // entries I receive == entries I send
-        CK(h->peerBuf.alloc(kPeerRecvOff + 2 * std::max<size_t>(total, 1) * sizeof(float4)));
+        const char *unfused = getenv("TETSIM_PEER_UNFUSED");
+        // the fused push sends tile partials, so it needs the deterministic flush (per-tile partial sums).  The choice
+        // must be the same on every rank (it fixes the layout of the receive buffers): options + environment only.
+        h->peerFused = h->opt.deterministic != 0 && !(unfused && unfused[0] == '1');
+        if (h->peerFused && P.pxMaxPartials > kPeerK)
+            return fail(TETSIM_E_STATE, "a rank-shared vertex has " + std::to_string(P.pxMaxPartials) + " tile partials on this rank (limit " + std::to_string(kPeerK) + "): use a larger clusterSize or exchange = 1");
+        const size_t entryBytes = h->peerFused ? (size_t)kPeerK * 32 : sizeof(float4);
+        CK(h->peerBuf.alloc(kPeerRecvOff + 2 * std::max<size_t>(total, 1) * entryBytes));
         CK(cudaMemsetAsync(h->peerBuf.p, 0, h->peerBuf.bytes(), s));
         CK(h->hxSrcStart.upload(P.hxSrcStart, s));
         CK(h->hxSrc.upload(P.hxSrc, s));
@@ -447,17 +453,14 @@ int build_jacobi_cluster(tetsim *h, const std::vector<float> &verts, const std::
         CK(h->pxRemoteTotal.upload(P.pxRemoteTotal, s));
         CK(h->pxRemoteSlot.upload(P.pxRemoteSlot, s));
         CK(h->peerBase.alloc(std::max<size_t>(P.hxPeers.size(), 1)));
-        CK(h->pxCnt.alloc(std::max<size_t>((size_t)P.numBoundary, 1)));
-        CK(cudaMemsetAsync(h->pxCnt.p, 0, h->pxCnt.bytes(), s));
-        CK(h->pxArgs.alloc(1));
-        h->pxNumActive = 0;
-        for (int b = 0; b < P.numBoundary; b++) {
-            if (!P.boundaryActive[b]) h->h_vertId[(size_t)P.numInterior + b] = -1;
-            else h->pxNumActive++;
+        {
+            std::vector<unsigned char> si(P.pxSlotIdx.begin(), P.pxSlotIdx.end());
+            if (si.empty()) si.push_back(0xff);
+            CK(h->pxSlotIdx.upload(si, s));
         }
-        const char *unfused = getenv("TETSIM_PEER_UNFUSED");
-        // the fused push counts tile partials, so it needs the deterministic flush (per-tile partial sums)
-        h->peerFused = h->opt.deterministic != 0 && h->pxNumActive > 0 && !(unfused && unfused[0] == '1');
+        CK(h->pxArgs.alloc(1));
+        for (int b = 0; b < P.numBoundary; b++)
+            if (!P.boundaryActive[b]) h->h_vertId[(size_t)P.numInterior + b] = -1;
     }
     bool identity = (int)h->h_vertId.size() == N;
     for (int i = 0; identity && i < N; i++) identity = h->h_vertId[i] == i;
@@ -504,7 +507,7 @@ PeerArgs peer_args(const tetsim *h) {
     a.peerBase = h->peerBase.p; a.remoteTotal = h->pxRemoteTotal.p; a.remoteSlot = h->pxRemoteSlot.p;
     a.self = h->peerBuf.p; a.selfTotal = (int)P.hxSendIdx.size();
     a.srcStart = h->hxSrcStart.p; a.src = h->hxSrc.p;
-    a.cnt = h->pxCnt.p; a.numActive = h->pxNumActive;
+    a.slotIdx = h->pxSlotIdx.p; a.numBoundarySlots = (int)P.pxSlotIdx.size();
     unsigned long long ms = 10000ull;
     if (const char *e = getenv("TETSIM_PEER_TIMEOUT_MS")) { long v = atol(e); if (v > 0) ms = (unsigned long long)v; }
     a.timeoutNs = ms * 1000000ull;
