@@ -239,7 +239,7 @@ __device__ __forceinline__ void cp_async_wait_pending() { asm volatile("cp.async
 // first, first + stride, ...  NT = threads of the worker, TPT = tets per thread, T = NT * TPT.
 // S-stage ring: at tile k the tet block and vertex gather of tile k+S-1 and the meta block of tile
 // k+S are put in flight, so S-1 tiles of HBM/L2 latency are covered by math.
-template <int NT, int TPT, int S, bool WARP_SCOPE, bool DBG = false, bool RPF = false>
+template <int NT, int TPT, int S, bool WARP_SCOPE, bool DBG = false>
 __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws, const int tid, const int first,
                                             const int stride) {
     constexpr int T = NT * TPT;
@@ -270,7 +270,7 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
     // shared memory would cost a write and a read of the SM's 128 B/clk shared-memory pipe, which the
     // gather/scatter traffic of this kernel already loads heavily).  Its HBM latency is hidden by a
     // bulk L2 prefetch of the whole 56*T-byte block issued PF tiles ahead.
-    constexpr int PF = RPF ? 3 : 2;
+    constexpr int PF = 2;
     auto prefetch_tets = [&](int tile) {  // one thread
         bulk_prefetch_l2(a.tets + (size_t)tile * TileSmem<T, S>::TET_BYTES, (uint32_t)TileSmem<T, S>::TET_BYTES);
     };
@@ -303,11 +303,14 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
         else cp_async_commit();
     }
 
-    // RPF (record prefetch): the NEXT tile's records are loaded right after this tile's math, when the math registers are
-    // dead, so their L2 latency is covered by the corner sums and the barrier instead of stalling the first gather.
-    float4 rA[TPT], rB[TPT], rC[TPT];
-    auto load_records = [&](int tile) {
-        const unsigned char *tb = a.tets + (size_t)tile * TileSmem<T, S>::TET_BYTES;
+    // (Software-pipelining these loads one tile ahead -- issuing them right after the previous tile's math -- was
+    // measured twice in round 1 and is slower: 0.195 vs 0.188 ms with one tet per thread, 0.153 vs 0.141 ms with two.)
+    int k = 0;
+    for (int c = first; c < a.numTiles; c += stride, k++) {
+        const int cur = k % S, mcur = k % (S + 1);
+        // this tile's records: issue the loads first, they land while we wait and prefetch below
+        const unsigned char *tb = a.tets + (size_t)c * TileSmem<T, S>::TET_BYTES;
+        float4 rA[TPT], rB[TPT], rC[TPT];
 #pragma unroll
         for (int u = 0; u < TPT; u++) {
             const int t = tid + NT * u;
@@ -324,14 +327,6 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
             rB[u] = ldg_stream4(tb + T * 16 + t * 16);
             rC[u] = ldg_stream4(tb + T * 32 + t * 16);
         }
-    };
-    if (RPF && first < a.numTiles) load_records(first);
-
-    int k = 0;
-    for (int c = first; c < a.numTiles; c += stride, k++) {
-        const int cur = k % S, mcur = k % (S + 1);
-        // this tile's records: issue the loads first, they land while we wait and prefetch below
-        if (!RPF) load_records(c);
         cp_async_wait_pending<S - 2>();
         sync();  // this tile's gathers (all threads') landed; previous tile's corner sums are finished
 
@@ -396,7 +391,6 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
         }
         sync();
         prefetch_next();
-        if (RPF && c + stride < a.numTiles) load_records(c + stride);
 
         // ---- per-tile-vertex sum of corner dx, ascending (tet, corner) order ----
         const unsigned char *m = ws + L.meta(mcur);
@@ -450,11 +444,11 @@ __global__ void __launch_bounds__(T, MINB) k_jacobi_tiles(TileArgs a) {
 // Same with TPT tets per thread (T/TPT threads per tile): per-tile overhead (barriers, prefetch issue,
 // loop control) is shared by TPT times the tets and every thread carries TPT independent chains.
 constexpr int tilesN_minb(int T, int TPT, int MINB) { return MINB > 0 ? MINB : 1024 / T; }
-template <int T, int TPT, int S, int MINB, bool RPF = false>
+template <int T, int TPT, int S, int MINB>
 __global__ void __launch_bounds__(T / TPT, tilesN_minb(T, TPT, MINB)) k_jacobi_tilesN(TileArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     if (a.tileBegin + (int)blockIdx.x >= a.numTiles) return;
-    tile_worker<T / TPT, TPT, S, false, false, RPF>(a, smem, threadIdx.x, a.tileBegin + blockIdx.x, gridDim.x);
+    tile_worker<T / TPT, TPT, S, false>(a, smem, threadIdx.x, a.tileBegin + blockIdx.x, gridDim.x);
 }
 
 // Warp tiles: every warp is its own worker with private staging and mbarriers (tile = 32 * TPL tets);
@@ -520,14 +514,14 @@ static void launch_tiles_T(cudaStream_t s, const TileArgs &a) {
     k_jacobi_tiles<T, S, MINB, DBG><<<grid, T, smem, s>>>(a);
 }
 
-template <int T, int TPT, int S, int MINB, bool RPF = false>
+template <int T, int TPT, int S, int MINB>
 static void launch_tilesN(cudaStream_t s, const TileArgs &a) {
     const size_t smem = tile_smem_bytes<T, S>(a);
     static LaunchCache cache[64];
     LaunchCache &lc = cache[current_device()];
     if (smem != lc.smem) {
-        cudaFuncSetAttribute(k_jacobi_tilesN<T, TPT, S, MINB, RPF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lc.n, k_jacobi_tilesN<T, TPT, S, MINB, RPF>, T / TPT, smem);
+        cudaFuncSetAttribute(k_jacobi_tilesN<T, TPT, S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lc.n, k_jacobi_tilesN<T, TPT, S, MINB>, T / TPT, smem);
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&lc.sms, cudaDevAttrMultiProcessorCount, dev);
@@ -536,7 +530,7 @@ static void launch_tilesN(cudaStream_t s, const TileArgs &a) {
     }
     int grid = lc.sms * lc.n;
     if (grid > a.numTiles - a.tileBegin) grid = a.numTiles - a.tileBegin;
-    k_jacobi_tilesN<T, TPT, S, MINB, RPF><<<grid, T / TPT, smem, s>>>(a);
+    k_jacobi_tilesN<T, TPT, S, MINB><<<grid, T / TPT, smem, s>>>(a);
 }
 
 // Warp tiles: one CTA per SM holding as many warps as shared memory and registers allow.
@@ -574,11 +568,6 @@ void launch_jacobi_tiles(cudaStream_t s, int clusterSize, const TileArgs &a) {
     if (a.debugSkip && clusterSize == 256) { launch_tiles_T<256, 3, 4, true>(s, a); return; }  // ablations: one instantiation
     if (sh.tpt > 1) {
         const int tpt = sh.tpt, minb = sh.minb;
-        if (const char *e = getenv("TETSIM_TILE_RPF")) {  // experiment: software-pipelined record loads
-            if (e[0] == '1' && clusterSize == 512 && tpt == 2 && S == 2 && minb == 4) { launch_tilesN<512, 2, 2, 4, true>(s, a); return; }
-            if (e[0] == '1' && clusterSize == 512 && tpt == 2 && S == 3 && minb == 4) { launch_tilesN<512, 2, 3, 4, true>(s, a); return; }
-            if (e[0] == '1' && clusterSize == 256 && tpt == 2 && S == 2 && minb == 0) { launch_tilesN<256, 2, 2, 0, true>(s, a); return; }
-        }
 #define TN_CASE(T_, TPT_, S_, MINB_) if (clusterSize == T_ && tpt == TPT_ && S == S_ && minb == MINB_) { launch_tilesN<T_, TPT_, S_, MINB_>(s, a); return; }
         TN_CASE(128, 2, 2, 0) TN_CASE(128, 2, 3, 0)
         TN_CASE(256, 2, 2, 0) TN_CASE(256, 2, 3, 0) TN_CASE(256, 2, 2, 6) TN_CASE(256, 2, 2, 8)

@@ -29,9 +29,8 @@ ap.add_argument("--reps", type=int, default=30)
 ap.add_argument("--out", default="")
 a = ap.parse_args()
 
-def V(tpt=0, stages=0, minb=0, rpf=0):
+def V(tpt=0, stages=0, minb=0):
     e = {}
-    if rpf: e["TETSIM_TILE_RPF"] = "1"
     if tpt: e["TETSIM_TILE_TPT"] = str(tpt)
     if stages: e["TETSIM_TILE_STAGES"] = str(stages)
     if minb: e["TETSIM_TILE_MINB"] = str(minb)
@@ -40,10 +39,10 @@ def V(tpt=0, stages=0, minb=0, rpf=0):
 
 VARIANTS = {   # T -> list of env dicts (the first is the default kernel of that tile size: 2 tets per thread, 2 stages)
     128: [V(), V(1, 3), V(2, 3)],
-    256: [V(), V(rpf=1), V(1, 3), V(2, 3), V(4, 2)],
-    512: [V(), V(rpf=1), V(2, 3, 4, rpf=1), V(1), V(2, 3, 4), V(4, 2)],
+    256: [V(), V(1, 3), V(2, 3), V(2, 2, 6), V(4, 2)],
+    512: [V(), V(1), V(2, 2, 3), V(2, 3, 4), V(4, 2)],
 }
-KEYS = ("TETSIM_TILE_TPT", "TETSIM_TILE_STAGES", "TETSIM_TILE_MINB", "TETSIM_TILE_RPF")
+KEYS = ("TETSIM_TILE_TPT", "TETSIM_TILE_STAGES", "TETSIM_TILE_MINB")
 
 
 def set_env(env):
