@@ -11,33 +11,37 @@ const KernelTable *fast_kernels() { return Launchers<false>::table(); }
 //
 // Persistent CTAs (grid = SMs x resident CTAs), each walking tiles c = blockIdx.x, + gridDim.x, ...
 // One tile = up to T consecutive tets of the Hilbert-sorted tet stream (closed early if it would touch
-// more than a capped number of vertices), one tet per thread.  HBM layout per tile:
+// more than a capped number of vertices).  Default shape (k_jacobi_tilesN): TWO tets per thread -- T = 512 with
+// 256 threads (64 registers, 4 CTAs per SM) or T = 256 with 128 threads -- so every thread carries two independent
+// dependency chains, the per-tile overhead (two barriers, prefetch issue, loop control) is paid once per two tets
+// and the corner sums below keep all warps busy.  HBM layout per tile:
 //   tet block  T*48 B: planes A[T] float4 (B00,B01,B02,B11), B[T] float4 (B12,B22,invRestVolume,detQ),
 //              C[T] uint4 (4 vertex slots, 4 scatter destinations as 16-bit byte offsets); B = Q Q^T is
-//              the rest metric (see nh_solve_fast_metric) -- 28 B of physics + 16 B of indices per tet;
+//              the rest metric (see nh_solve_tile) -- 28 B of physics + 16 B of indices per tet;
 //   meta block (variable size): tile vertex ids, tile valences, jagged-diagonal offsets.
 // Data movement, all asynchronous and issued ahead of use:
 //   * tet block: one cp.async.bulk.prefetch.L2 per tile two tiles ahead, then three coalesced
-//     LDG.128 per thread straight into registers (staging the stream in shared memory would spend
+//     LDG.128 per tet straight into registers (staging the stream in shared memory would spend
 //     two passes of the 128 B/clk shared-memory pipe, which gather + scatter already load to 60 %);
 //   * meta block: ONE cp.async.bulk (TMA, UBLKCP) on an mbarrier, S tiles ahead;
 //   * the tile's vertex records float4(x,y,z,invMass): indexed gather with cp.async 16 B (LDGSTS),
-//     L2 -> shared memory without register staging, S-1 tiles ahead, issued by the warps that have
-//     no corner sums to do.
-// Per tile:  gather 4 corners (LDS.128) -> both Neo-Hookean projections in registers
-//   -> each corner's dx is stored (STS.128) at its precomputed slot of a jagged-diagonal buffer
-//   (entry (i, j) = i-th corner of tile vertex j; vertices sorted by descending tile valence)
+//     L2 -> shared memory without register staging, S-1 tiles ahead, issued by the upper half of the CTA.
+// Per tile:  gather 4 corners (LDS.128) -> both Neo-Hookean projections in registers, corner displacements formed
+//   directly (nh_solve_tile) -> each corner's dx is stored (STS.128) at its precomputed slot of a jagged-diagonal
+//   buffer (entry (i, j) = i-th corner of tile vertex j; vertices sorted by descending tile valence)
 //   -> barrier -> thread j sums entries (0..val_j, j): consecutive lanes read consecutive 16-B
 //   entries (conflict-free LDS.128, no index loads), in ascending (tet, corner) order
-//   -> one coalesced STG.128 of the tile's partial sum per tile vertex.
+//   -> one coalesced STG.128 of the tile's partial sum per tile vertex
+//   (-> on a multi-GPU handle with the fused peer exchange: the partial of a rank-shared vertex is also stored into
+//   the sharers' receive buffers over NVLink, see PeerArgs in launch.h).
 // No shared-memory float atomics (sm_100a has none natively: ATOMS.CAST spin loops) and, in the
-// default flush, no global atomics either: the vertex kernel adds the ~3 tile partials of a vertex in a
+// default flush, no global atomics either: the vertex kernel adds the ~2.4 tile partials of a vertex in a
 // fixed order -> results are bit-reproducible run to run.  (deterministic = 0 flushes with one
 // REDG.E.ADD.F32x4 per tile vertex instead.)
 // Algorithmic traffic per launch: 56 B/tet + 32 B/vertex; the kernel's own
 // DRAM traffic is lower on the tet stream (48 B) and adds ~3 B/tet of metadata and the partial sums.
-// Round-1 measurements: HBM is NOT the binding limit once the stream is prefetched; FP32
-// issue + shared-memory wavefronts are (math-only ablation 0.13 ms of 0.20 ms per 10M-tet launch).
+// Round-1 measurements: 0.141 ms per 10M-tet launch = 0.68 of the measured HBM peak; the
+// binding limits are FP32 issue + shared-memory wavefronts (64 % issue-active), not DRAM (3.65 TB/s).
 // =================================================================================================
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *b, uint32_t count) {
