@@ -52,7 +52,7 @@ def test_sass_is_sm100a_without_tensor_or_cas_loops():
     # the default tile kernels: T = 512 (64 registers, 4 CTAs of 256 threads per SM) and T = 256, two tets per thread, two stages
     res = subprocess.run(["cuobjdump", "-res-usage", _capi.LIB_PATH], capture_output=True, text=True).stdout
     names = re.findall(r"Function (\S+):", res)
-    for prefix in ("_ZN4tsim15k_jacobi_tilesNILi512ELi2ELi2ELi4EE", "_ZN4tsim15k_jacobi_tilesNILi256ELi2ELi2ELi0EE"):
+    for prefix in ("_ZN4tsim15k_jacobi_tilesNILi512ELi2ELi2ELi4ELb0E", "_ZN4tsim15k_jacobi_tilesNILi256ELi2ELi2ELi0ELb0E"):
         fun = [n for n in names if n.startswith(prefix)]
         assert len(fun) == 1, (prefix, fun)
         sass = subprocess.run(["cuobjdump", "-sass", "-fun", fun[0], _capi.LIB_PATH], capture_output=True, text=True).stdout
@@ -60,7 +60,12 @@ def test_sass_is_sm100a_without_tensor_or_cas_loops():
         assert "UBLKCP" in sass and "UBLKPF" in sass and "SYNCS" in sass and "LDGSTS.E.BYPASS.128" in sass, fun
         assert "STS.128" in sass and "LDS.128" in sass and "STG.E.128" in sass, fun
         assert "ATOMS.CAST" not in sass and "HMMA" not in sass and "UTCHMMA" not in sass and "CALL" not in sass, fun
-    assert "REG:64" in res[res.index("k_jacobi_tilesNILi512ELi2ELi2ELi4EE"):][:200]
+    assert "REG:64" in res[res.index("k_jacobi_tilesNILi512ELi2ELi2ELi4ELb0E"):][:200]
+    # the single-GPU kernels carry no peer-exchange code (volatile 128-bit remote stores exist only in the PEER variants)
+    peer = [n for n in names if n.startswith("_ZN4tsim15k_jacobi_tilesNILi512ELi2ELi2ELi4ELb1E")]
+    assert len(peer) == 1
+    psass = subprocess.run(["cuobjdump", "-sass", "-fun", peer[0], _capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "STG.E.128.STRONG.SYS" in psass and "STRONG.SYS" not in sass
 
 
 @pytest.mark.skipif(_capi.lib().tetsim_device_count() > 0, reason="a B200 is present")

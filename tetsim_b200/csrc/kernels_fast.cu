@@ -243,7 +243,7 @@ __device__ __forceinline__ void cp_async_wait_pending() { asm volatile("cp.async
 // first, first + stride, ...  NT = threads of the worker, TPT = tets per thread, T = NT * TPT.
 // S-stage ring: at tile k the tet block and vertex gather of tile k+S-1 and the meta block of tile
 // k+S are put in flight, so S-1 tiles of HBM/L2 latency are covered by math.
-template <int NT, int TPT, int S, bool WARP_SCOPE, bool DBG = false>
+template <int NT, int TPT, int S, bool WARP_SCOPE, bool DBG = false, bool PEER = false>
 __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws, const int tid, const int first,
                                             const int stride) {
     constexpr int T = NT * TPT;
@@ -414,10 +414,10 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
                 if (a.acc) atomicAdd(a.acc + reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3])[j],
                                      make_float4(ax, ay, az, 0.0f));
                 else a.part[v0 + j] = make_float4(ax, ay, az, 0.0f);
-                if (a.px) {  // multi-GPU, fused exchange: a rank-shared vertex's tile partial goes straight to the sharers
+                if (PEER) {  // multi-GPU, fused exchange: a rank-shared vertex's tile partial goes straight to the sharers
                     const PeerArgs &px = *a.px;
                     const int slot = v0 + j;
-                    if (slot < px.numBoundarySlots) {
+                    if (slot < ((a.pxFlags & kPeerV2SlotsByValue) ? a.pxSlots : px.numBoundarySlots)) {
                         const unsigned i = px.slotIdx[slot];
                         if (i != 0xffu) {
                             const int id = reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3])[j];
@@ -427,6 +427,18 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
                     }
                 }
             }
+    }
+    if (PEER && !WARP_SCOPE && (a.pxFlags & kPeerV2TileAdvances)) {
+        // every push of this CTA is issued (and has read the epoch): take a ticket, the last CTA advances the epoch
+        __syncthreads();
+        if (tid == 0) {
+            unsigned *ctl = reinterpret_cast<unsigned *>(a.px->self + kPeerCtlOff);
+            const unsigned e = *reinterpret_cast<volatile unsigned *>(ctl) + 1u;
+            if (atomicAdd(ctl + 1, 1u) == gridDim.x - 1) {
+                ctl[1] = 0u;
+                *reinterpret_cast<volatile unsigned *>(ctl) = e;
+            }
+        }
     }
 }
 
@@ -448,11 +460,12 @@ __global__ void __launch_bounds__(T, MINB) k_jacobi_tiles(TileArgs a) {
 // Same with TPT tets per thread (T/TPT threads per tile): per-tile overhead (barriers, prefetch issue,
 // loop control) is shared by TPT times the tets and every thread carries TPT independent chains.
 constexpr int tilesN_minb(int T, int TPT, int MINB) { return MINB > 0 ? MINB : 1024 / T; }
-template <int T, int TPT, int S, int MINB>
+// PEER = true adds the fused peer-memory push (TileArgs::px must be set); the single-GPU kernels carry none of it.
+template <int T, int TPT, int S, int MINB, bool PEER = false>
 __global__ void __launch_bounds__(T / TPT, tilesN_minb(T, TPT, MINB)) k_jacobi_tilesN(TileArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     if (a.tileBegin + (int)blockIdx.x >= a.numTiles) return;
-    tile_worker<T / TPT, TPT, S, false>(a, smem, threadIdx.x, a.tileBegin + blockIdx.x, gridDim.x);
+    tile_worker<T / TPT, TPT, S, false, false, PEER>(a, smem, threadIdx.x, a.tileBegin + blockIdx.x, gridDim.x);
 }
 
 // Warp tiles: every warp is its own worker with private staging and mbarriers (tile = 32 * TPL tets);
@@ -518,14 +531,14 @@ static void launch_tiles_T(cudaStream_t s, const TileArgs &a) {
     k_jacobi_tiles<T, S, MINB, DBG><<<grid, T, smem, s>>>(a);
 }
 
-template <int T, int TPT, int S, int MINB>
+template <int T, int TPT, int S, int MINB, bool PEER = false>
 static void launch_tilesN(cudaStream_t s, const TileArgs &a) {
     const size_t smem = tile_smem_bytes<T, S>(a);
     static LaunchCache cache[64];
     LaunchCache &lc = cache[current_device()];
     if (smem != lc.smem) {
-        cudaFuncSetAttribute(k_jacobi_tilesN<T, TPT, S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lc.n, k_jacobi_tilesN<T, TPT, S, MINB>, T / TPT, smem);
+        cudaFuncSetAttribute(k_jacobi_tilesN<T, TPT, S, MINB, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lc.n, k_jacobi_tilesN<T, TPT, S, MINB, PEER>, T / TPT, smem);
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&lc.sms, cudaDevAttrMultiProcessorCount, dev);
@@ -534,7 +547,7 @@ static void launch_tilesN(cudaStream_t s, const TileArgs &a) {
     }
     int grid = lc.sms * lc.n;
     if (grid > a.numTiles - a.tileBegin) grid = a.numTiles - a.tileBegin;
-    k_jacobi_tilesN<T, TPT, S, MINB><<<grid, T / TPT, smem, s>>>(a);
+    k_jacobi_tilesN<T, TPT, S, MINB, PEER><<<grid, T / TPT, smem, s>>>(a);
 }
 
 // Warp tiles: one CTA per SM holding as many warps as shared memory and registers allow.
@@ -565,21 +578,36 @@ static void launch_warptiles(cudaStream_t s, const TileArgs &a) {
     k_jacobi_warptiles<TPL, S><<<grid, 32 * lc.n, perWarp * lc.n, s>>>(a);
 }
 
+// The k_jacobi_tilesN instantiations that exist: (tile size, tets per thread, stages, CTAs per SM the registers are capped
+// for; 0 = 1024 / T).  The first of each tile size is the default shape, the rest are reachable through the
+// TETSIM_TILE_* overrides (tools/tile_sweep.py).
+#define TILESN_SHAPES(X)                                                              \
+    X(128, 2, 2, 0) X(128, 2, 3, 0)                                                   \
+    X(256, 2, 2, 0) X(256, 2, 3, 0) X(256, 2, 2, 6) X(256, 2, 2, 8) X(256, 4, 2, 0)   \
+    X(512, 2, 2, 4) X(512, 2, 2, 0) X(512, 2, 2, 3) X(512, 2, 3, 4) X(512, 4, 2, 0) X(512, 4, 2, 3)
+
+// The fused peer push exists only in the k_jacobi_tilesN instantiations (two or more tets per thread).
+bool jacobi_tiles_has_peer_push(int clusterSize) {
+    const TileShape sh = tile_shape(clusterSize);
+#define X(T_, TPT_, S_, MINB_) if (clusterSize == T_ && sh.tpt == TPT_ && sh.stages == S_ && sh.minb == MINB_) return true;
+    TILESN_SHAPES(X)
+#undef X
+    return false;
+}
+
 void launch_jacobi_tiles(cudaStream_t s, int clusterSize, const TileArgs &a) {
     if (a.numTiles - a.tileBegin <= 0) return;
     const TileShape sh = tile_shape(clusterSize);
     const int S = sh.stages;
     if (a.debugSkip && clusterSize == 256) { launch_tiles_T<256, 3, 4, true>(s, a); return; }  // ablations: one instantiation
-    if (sh.tpt > 1) {
-        const int tpt = sh.tpt, minb = sh.minb;
-#define TN_CASE(T_, TPT_, S_, MINB_) if (clusterSize == T_ && tpt == TPT_ && S == S_ && minb == MINB_) { launch_tilesN<T_, TPT_, S_, MINB_>(s, a); return; }
-        TN_CASE(128, 2, 2, 0) TN_CASE(128, 2, 3, 0)
-        TN_CASE(256, 2, 2, 0) TN_CASE(256, 2, 3, 0) TN_CASE(256, 2, 2, 6) TN_CASE(256, 2, 2, 8)
-        TN_CASE(512, 2, 2, 0) TN_CASE(512, 2, 2, 3) TN_CASE(512, 2, 2, 4) TN_CASE(512, 2, 3, 4)
-        TN_CASE(256, 4, 2, 0) TN_CASE(512, 4, 2, 0) TN_CASE(512, 4, 2, 3)
-#undef TN_CASE
-        // no such instantiation: fall through to the one-tet-per-thread kernels
+#define X(T_, TPT_, S_, MINB_)                                                                       \
+    if (clusterSize == T_ && sh.tpt == TPT_ && S == S_ && sh.minb == MINB_) {                        \
+        if (a.px) launch_tilesN<T_, TPT_, S_, MINB_, true>(s, a); else launch_tilesN<T_, TPT_, S_, MINB_>(s, a); \
+        return;                                                                                      \
     }
+    TILESN_SHAPES(X)
+#undef X
+    // no such instantiation (one tet per thread, warp tiles): the kernels below carry no peer push
     switch (clusterSize) {
         case 32: S == 2 ? launch_warptiles<1, 2>(s, a) : (S == 3 ? launch_warptiles<1, 3>(s, a) : launch_warptiles<1, 4>(s, a)); break;
         case 64: S == 2 ? launch_warptiles<2, 2>(s, a) : (S == 3 ? launch_warptiles<2, 3>(s, a) : launch_warptiles<2, 4>(s, a)); break;
@@ -633,15 +661,20 @@ void launch_build_tiles(cudaStream_t s, int clusterSize, int numRecords, const i
 // inside tetsim_step costs exactly two launches.
 template <int MODE, bool PEER>
 __global__ void k_jacobi_apply(int begin, int end, ApplyArgs a) {
-    int i = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned blk = (PEER && (a.pxFlags & kPeerV2ReverseBlocks)) ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+    int i = begin + blk * blockDim.x + threadIdx.x;
     unsigned epoch = 0u;
-    if (PEER) {  // fused peer exchange: this launch consumes epoch ctl[0] + 1; the last block to pass here advances it
+    if (PEER) {  // fused peer exchange
         unsigned *ctl = reinterpret_cast<unsigned *>(a.px->self + kPeerCtlOff);
-        epoch = *reinterpret_cast<volatile unsigned *>(ctl) + 1u;
-        __syncthreads();  // every thread of the block has read the epoch before the block's ticket
-        if (threadIdx.x == 0 && atomicAdd(ctl + 1, 1u) == gridDim.x - 1) {
-            ctl[1] = 0u;
-            *reinterpret_cast<volatile unsigned *>(ctl) = epoch;
+        if (a.pxFlags & kPeerV2TileAdvances) {
+            epoch = *reinterpret_cast<volatile unsigned *>(ctl);  // already advanced by the tile kernel's last CTA
+        } else {  // this launch consumes epoch ctl[0] + 1; the last block to pass here advances it
+            epoch = *reinterpret_cast<volatile unsigned *>(ctl) + 1u;
+            __syncthreads();  // every thread of the block has read the epoch before the block's ticket
+            if (threadIdx.x == 0 && atomicAdd(ctl + 1, 1u) == gridDim.x - 1) {
+                ctl[1] = 0u;
+                *reinterpret_cast<volatile unsigned *>(ctl) = epoch;
+            }
         }
     }
     if (i >= end) return;

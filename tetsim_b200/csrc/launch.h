@@ -65,8 +65,10 @@ struct TileArgs {
     int staggerNs;                  // initial delay per resident-CTA slot (breaks phase lockstep of co-resident CTAs)
     int debugSkip;                  // measurement only (tetsim_time_kernel + TETSIM_TILE_DEBUG): 1 no vertex phase, 2 no math, 4 no gather
     const PeerArgs *px;             // DEVICE copy of the peer-exchange arguments: fused push of the boundary sums, or NULL
+    int pxSlots, pxFlags;           // fused push experiments (TETSIM_PEER_V2 bit mask, see kPeerV2*): slot bound by value
 };
 void launch_jacobi_tiles(cudaStream_t, int clusterSize, const TileArgs &a);
+bool jacobi_tiles_has_peer_push(int clusterSize);  // can this tile size (and the TETSIM_TILE_* overrides in force) push?
 size_t jacobi_tiles_smem(int clusterSize, const TileArgs &a);
 // record r of the tile stream: Q/irv of tet order[r] (or zeros when order[r] < 0) + aux[r] -> tet blocks
 void launch_build_tiles(cudaStream_t, int clusterSize, int numRecords, const int *order, const float *Q9,
@@ -80,6 +82,7 @@ struct ApplyArgs {
     const float *invVal;            // 1 / valence
     const float4 *bsum;             // all-reduced boundary sums for vertices >= boundaryBegin, or NULL
     const PeerArgs *px;             // DEVICE copy: wait for the sharers' flags and reduce in rank order here (fused), or NULL
+    int pxFlags;                    // TETSIM_PEER_V2 bit mask (kPeerV2*)
     int boundaryBegin;
     const SubstepParams *sp;
     const int *vertId;              // handle-local -> caller's vertex id (for the grab test)
@@ -132,6 +135,11 @@ struct PeerArgs {
 // the current epoch, adds each sharer's partials in that sharer's own order and the sharers' sums in ascending rank
 // order (so every sharer computes the identical value), and the last vertex block advances the epoch: 2 launches per
 // iteration, as on a single GPU.
+// Round-2 experiments on the fused form, off by default (TETSIM_PEER_V2 = bit mask), one per suspected source of the
+// ~20 us/substep it still costs at 2 GPUs:
+constexpr int kPeerV2SlotsByValue = 1;    // tile kernel: "is this a boundary-tile slot" from a kernel parameter, not through px->
+constexpr int kPeerV2TileAdvances = 2;    // the tile kernel's CTAs (not the vertex kernel's blocks) advance the epoch
+constexpr int kPeerV2ReverseBlocks = 4;   // vertex kernel: blocks holding the rank-shared vertices are scheduled first
 constexpr int kPeerK = 16;                // most tile partials a rank may hold for one shared vertex (checked at create)
 void launch_peer_push(cudaStream_t, const PeerArgs &a);
 void launch_peer_reduce(cudaStream_t, const PeerArgs &a);

@@ -190,6 +190,7 @@ struct tetsim {
     DevBuf<unsigned char> pxSlotIdx;        // fused push: partial index of every boundary-tile partial slot
     DevBuf<PeerArgs> pxArgs;                // device copy of peer_args(h), read by the tile and vertex kernels
     bool peerFused = false;                 // the tile kernel pushes, the vertex kernel polls + reduces (2 launches/iteration)
+    int peerV2 = 0;                         // TETSIM_PEER_V2 experiment mask (kPeerV2*), read at create
     int maxValence = 0;
 
     int64_t deviceBytes() const {
@@ -439,7 +440,9 @@ int build_jacobi_cluster(tetsim *h, const std::vector<float> &verts, const std::
         const char *unfused = getenv("TETSIM_PEER_UNFUSED");
         // the fused push sends tile partials, so it needs the deterministic flush (per-tile partial sums).  The choice
         // must be the same on every rank (it fixes the layout of the receive buffers): options + environment only.
-        h->peerFused = h->opt.deterministic != 0 && !(unfused && unfused[0] == '1');
+        h->peerFused = h->opt.deterministic != 0 && !(unfused && unfused[0] == '1') && jacobi_tiles_has_peer_push(P.T);
+        if (const char *v2 = getenv("TETSIM_PEER_V2")) h->peerV2 = atoi(v2) & 7;
+        if (P.T < 128) h->peerV2 &= ~kPeerV2TileAdvances;  // warp-tile workers have no CTA-level ticket
         if (h->peerFused && P.pxMaxPartials > kPeerK)
             return fail(TETSIM_E_STATE, "a rank-shared vertex has " + std::to_string(P.pxMaxPartials) + " tile partials on this rank (limit " + std::to_string(kPeerK) + "): use a larger clusterSize or exchange = 1");
         const size_t entryBytes = h->peerFused ? (size_t)kPeerK * 32 : sizeof(float4);
@@ -571,8 +574,11 @@ int enqueue_substeps(tetsim *h, int count) {
                             // its sum into the sharers' buffers; the vertex kernel below waits for theirs and reduces
                             TileArgs cf = ca;
                             cf.px = h->pxArgs.p;
+                            cf.pxSlots = (int)P.pxSlotIdx.size();
+                            cf.pxFlags = h->peerV2;
                             launch_jacobi_tiles(s, P.T, cf);
                             aa.px = h->pxArgs.p;
+                            aa.pxFlags = h->peerV2;
                             h->enq += 2;
                         } else if (h->peer) {
                             // boundary tiles -> push this rank's boundary sums into the sharers' buffers (+ flag)
