@@ -134,6 +134,21 @@ def cpu_reference_run(verts, tets, substeps, dt):
     return (tets.size // 4) * substeps / sec / 1e6, sec
 
 
+def cpu_dragon_substeps_per_s(substeps=300):
+    """BASELINE config 1, the metric's "reference CPU substeps/s": the Dragon mesh, Neo-Hookean Gauss-Seidel in the
+    reference's order at dt = 1/600 (10 substeps per frame), C restatement of src/Softbody.js, 1 thread."""
+    import oracle
+    from tetsim_b200 import mesh
+    m = mesh.load_dragon()
+    ref = oracle.SoftBodyOracle(m["tet_verts"], m["tet_ids"])
+    for _ in range(10):
+        ref.simulate(FRAME_DT / 10)
+    t0 = time.perf_counter()
+    for _ in range(substeps):
+        ref.simulate(FRAME_DT / 10)
+    return substeps / (time.perf_counter() - t0)
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -172,7 +187,7 @@ def main():
                 "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64-expr/f32-store",
                 "data": "synthetic", "config": {"workload": workload, "tets": M, "verts": verts.size // 3},
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
-                                 "host_cores": os.cpu_count()},
+                                 "host_cores": os.cpu_count(), "dragon_substeps_per_s": cpu_dragon_substeps_per_s()},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
@@ -320,6 +335,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, sec = cpu_reference_run(verts, tets, args.cpu_substeps, dt)
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "host_cores": os.cpu_count(),
+               "dragon_substeps_per_s": cpu_dragon_substeps_per_s(),
                "sample": "%d substeps of the full %d-tet mesh (%.1f s), sequential Gauss-Seidel C restatement of "
                          "src/Softbody.js, 1 thread (the sweep is inherently sequential; no JS engine in image)"
                          % (args.cpu_substeps, M, sec)}
