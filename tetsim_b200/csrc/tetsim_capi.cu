@@ -200,7 +200,7 @@ struct tetsim {
                          volTerm.bytes() + dx.bytes() + vpStart.bytes() + vpSlot.bytes() + tileTets.bytes() +
                          tileMeta.bytes() + metaOff.bytes() + part.bytes() + acc.bytes() +
                          bsum.bytes() + invVal.bytes() + rest.bytes() + quat.bytes() + tStart.bytes() + tEnt.bytes() +
-                         stage3.bytes() + visV.bytes() + visTri.bytes() + vtStart.bytes() + vtEnt.bytes() +
+                         stage3.bytes() + peerBuf.bytes() + pxSlotIdx.bytes() + visV.bytes() + visTri.bytes() + vtStart.bytes() + vtEnt.bytes() +
                          visPos.bytes() + visNrm.bytes());
     }
 };
@@ -570,8 +570,8 @@ int enqueue_substeps(tetsim *h, int count) {
                             launch_jacobi_tiles(s, P.T, ca);
                             h->enq += 2;  // tile kernel + vertex kernel
                         } else if (h->peer && h->peerFused) {
-                            // ONE tile launch: boundary tiles first, the thread that completes a boundary vertex pushes
-                            // its sum into the sharers' buffers; the vertex kernel below waits for theirs and reduces
+                            // ONE tile launch: boundary tiles first, every tile stores its partials of rank-shared vertices
+                            // straight into the sharers' buffers; the vertex kernel below polls theirs and reduces
                             TileArgs cf = ca;
                             cf.px = h->pxArgs.p;
                             cf.pxSlots = (int)P.pxSlotIdx.size();
