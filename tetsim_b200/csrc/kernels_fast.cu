@@ -720,12 +720,17 @@ __global__ void k_jacobi_apply(int begin, int end, ApplyArgs a) {
         v.w = 0.0f;
         post_vertex<false>(a.vertId ? a.vertId[i] : i, x, p, v, sp);
         if (MODE == 2) {
+            // post of this substep + predict of the next: the velocity lives in registers only.  Storing it would be
+            // a dead 16 B/vertex write -- the next substep's post recomputes v from x and prev, and the LAST substep
+            // of a tetsim_step call always runs MODE 1, which stores the velocity the caller (and the next call's
+            // predict) sees.
             a.prev4[i] = x;
             v.y += sp->gDt;
             const float dt = sp->dtF;
             x.x = fmaf(v.x, dt, x.x); x.y = fmaf(v.y, dt, x.y); x.z = fmaf(v.z, dt, x.z);
+        } else {
+            a.vel4[i] = v;
         }
-        a.vel4[i] = v;
     }
     a.x4[i] = x;
 }
