@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Small driver for ncu: builds the bench workload, runs a few steps and the tile kernel alone.
 
-    ncu --set full --clock-control none --import-source on -k regex:k_jacobi_cluster -s 2 -c 2 \
+    ncu --set full --clock-control none --import-source on -k regex:k_jacobi_tiles -s 2 -c 1 \
         -o gpurun_out/prof python tools/profile_driver.py [--cells x,y,z] [--cluster-size T]
 """
 import argparse
