@@ -286,7 +286,7 @@ def main():
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("k_jacobi_cluster_dram_bytes_per_launch") if world == 1 else None
+            traffic = json.load(open(tp)).get("k_jacobi_tiles_dram_bytes_per_launch") if world == 1 else None
         except Exception:
             traffic = None
     roofline = {"kernel": "k_jacobi_tilesN<%d, 2 tets/thread> (persistent tile kernel, tetsim_b200/csrc/kernels_fast.cu)" % args.cluster_size, "bound": "hbm", "achieved": achieved,

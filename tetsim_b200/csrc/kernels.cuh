@@ -286,7 +286,7 @@ __global__ void k_gs_body(const BodyDesc *__restrict__ bodies, const int *__rest
 
 // ------------------------------------------------------------------------------------------------
 // Jacobi Neo-Hookean, gather formulation (the parity / reference-structure path; the throughput
-// path is k_jacobi_cluster in kernels_fast.cu).  Mirrors the WebGL solver's own split
+// path is k_jacobi_tilesN in kernels_fast.cu).  Mirrors the WebGL solver's own split
 // (src/SoftbodyGPU.js K4 writes 4 corner results per tet, K5 gathers them per vertex):
 //   k_jacobi_tet    : every tet runs solveElem on a private copy, writes dx for its 4 corners
 //   k_jacobi_gather : every vertex sums its corners' dx in ascending (tet, corner) order (f32) and
