@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Accuracy of the clustered-Jacobi tile kernel (FAST_F32) against the oracle's Jacobi on Dragon:
+"""(Test-side report, not collected by pytest: the oracle is the checker here.)  Accuracy of the clustered-Jacobi tile kernel (FAST_F32) against the oracle's Jacobi on Dragon:
 vector-relative position error, max velocity difference and volError difference after 100 substeps at
 dt = 1/1200, for every tile size (and whatever TETSIM_TILE_* variant switches are set)."""
 import os
@@ -9,7 +9,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import oracle  # noqa: E402
 import tetsim_b200 as ts  # noqa: E402
 from tetsim_b200 import mesh  # noqa: E402

@@ -69,11 +69,5 @@ for n in ([8, 28] if a.big else [8]):
     pj = dict(p20, worldBounds=wb)
     rate("C5       %dx tiled Dragon + ground, NH Jacobi tile kernel" % (n * n),
          ts.SoftBody(v, t, None, pj, solver="jacobi", stream=stream.cuda_stream), pj, a.frames)
-import oracle  # noqa: E402  (CPU baseline beside the GPU numbers; test infrastructure, not product)
-ref = oracle.SoftBodyOracle(m["tet_verts"], m["tet_ids"])
-t0 = time.perf_counter()
-for _ in range(1000):
-    ref.simulate(1.0 / 600.0)
-sec = time.perf_counter() - t0
-print("%-58s %9.0f substeps/s  %10.1f Mtet/s  (C restatement of src/Softbody.js, 1 of %d host cores)" % (
-    "C1       Dragon NH GS, CPU oracle", 1000 / sec, 3840 * 1000 / sec / 1e6, os.cpu_count()))
+# The CPU baseline of config 1 (the reference's algorithm on the Dragon, substeps/s) is measured by bench.py
+# (cpu_baseline.dragon_substeps_per_s): tools never load oracle/.
