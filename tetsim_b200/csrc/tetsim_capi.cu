@@ -191,6 +191,10 @@ struct tetsim {
     DevBuf<PeerArgs> pxArgs;                // device copy of peer_args(h), read by the tile and vertex kernels
     bool peerFused = false;                 // the tile kernel pushes, the vertex kernel polls + reduces (2 launches/iteration)
     int peerV2 = 0;                         // TETSIM_PEER_V2 experiment mask (kPeerV2*), read at create
+    // TETSIM_TRACE=1: in-situ per-launch timing of the clustered Jacobi substep (events between launches, no graph);
+    // the way to see where a multi-GPU substep spends its time, where ncu cannot be used
+    bool trace = false;
+    std::vector<std::pair<const char *, cudaEvent_t>> marks;
     int maxValence = 0;
 
     int64_t deviceBytes() const {
@@ -501,6 +505,38 @@ TileArgs tile_args(const tetsim *h) {
     return a;
 }
 
+void trace_mark(tetsim *h, const char *label) {  // the interval ending here is charged to `label`
+    cudaEvent_t ev = nullptr;
+    if (cudaEventCreate(&ev) != cudaSuccess) return;
+    cudaEventRecord(ev, h->stream);
+    h->marks.emplace_back(label, ev);
+}
+#define TR(label) do { if (h->trace) trace_mark(h, label); } while (0)
+
+// Print and reset the trace (stream must be idle).
+void trace_report(tetsim *h) {
+    if (h->marks.empty()) return;
+    std::map<std::string, std::pair<int, double>> agg;
+    std::vector<std::string> orderSeen;
+    for (size_t i = 1; i < h->marks.size(); i++) {
+        if (std::string(h->marks[i].first) == "begin") continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->marks[i - 1].second, h->marks[i].second) != cudaSuccess) continue;
+        auto it = agg.find(h->marks[i].first);
+        if (it == agg.end()) { orderSeen.push_back(h->marks[i].first); it = agg.emplace(h->marks[i].first, std::make_pair(0, 0.0)).first; }
+        it->second.first++; it->second.second += ms;
+    }
+    double total = 0.0;
+    for (auto &kv : agg) total += kv.second.second;
+    fprintf(stderr, "tetsim trace, rank %d of %d (event-to-event intervals, launches not graphed):\n", h->opt.rank, h->opt.worldSize);
+    for (const std::string &k : orderSeen)
+        fprintf(stderr, "  %-28s n=%6d  avg %8.2f us  share %5.1f %%\n", k.c_str(), agg[k].first,
+                1e3 * agg[k].second / std::max(agg[k].first, 1), 100.0 * agg[k].second / std::max(total, 1e-12));
+    for (auto &m : h->marks) cudaEventDestroy(m.second);
+    h->marks.clear();
+    cudaGetLastError();
+}
+
 PeerArgs peer_args(const tetsim *h) {
     const ClusterPlan &P = h->plan;
     PeerArgs a{};
@@ -553,7 +589,7 @@ int enqueue_substeps(tetsim *h, int count) {
                     K->post(s, h->nInt, h->x4.p, h->prev4.p, h->vel4.p, sp, vid);
                 } else {
                     const ClusterPlan &P = h->plan;
-                    if (step == 0) { K->predict(s, h->nInt, h->x4.p, h->prev4.p, h->vel4.p, sp); h->enq++; }
+                    if (step == 0) { TR("begin"); K->predict(s, h->nInt, h->x4.p, h->prev4.p, h->vel4.p, sp); h->enq++; TR("predict"); }
                     TileArgs ca = tile_args(h);
                     ca.acc = h->acc.p; ca.volAcc = h->volTerm.p;
                     ApplyArgs aa{};
@@ -568,6 +604,7 @@ int enqueue_substeps(tetsim *h, int count) {
                         const int mode = !last ? 0 : (step + 1 < count ? 2 : 1);
                         if (!multi) {
                             launch_jacobi_tiles(s, P.T, ca);
+                            TR("tiles");
                             h->enq += 2;  // tile kernel + vertex kernel
                         } else if (h->peer && h->peerFused) {
                             // ONE tile launch: boundary tiles first, every tile stores its partials of rank-shared vertices
@@ -577,6 +614,7 @@ int enqueue_substeps(tetsim *h, int count) {
                             cf.pxSlots = (int)P.pxSlotIdx.size();
                             cf.pxFlags = h->peerV2;
                             launch_jacobi_tiles(s, P.T, cf);
+                            TR("tiles + peer push");
                             aa.px = h->pxArgs.p;
                             aa.pxFlags = h->peerV2;
                             h->enq += 2;
@@ -586,12 +624,16 @@ int enqueue_substeps(tetsim *h, int count) {
                             TileArgs cb = ca;
                             cb.numTiles = P.numBoundaryTiles;
                             launch_jacobi_tiles(s, P.T, cb);
+                            TR("boundary tiles");
                             PeerArgs pa = peer_args(h);
                             launch_peer_push(s, pa);
+                            TR("peer push");
                             TileArgs ci = ca;
                             ci.tileBegin = P.numBoundaryTiles;
                             launch_jacobi_tiles(s, P.T, ci);
+                            TR("interior tiles");
                             launch_peer_reduce(s, pa);
+                            TR("peer wait + reduce");
                             aa.bsum = h->bsum.p;
                             h->enq += 4 + (P.numBoundaryTiles > 0 && P.numBoundaryTiles < P.numClusters ? 1 : 0);
                         } else {
@@ -599,6 +641,7 @@ int enqueue_substeps(tetsim *h, int count) {
                             TileArgs cb = ca;
                             cb.numTiles = P.numBoundaryTiles;
                             launch_jacobi_tiles(s, P.T, cb);
+                            TR("boundary tiles");
                             if (h->acc.p) {
                                 CK(cudaMemcpyAsync(h->bsum.p, h->acc.p + P.numInterior, h->bsum.bytes(), cudaMemcpyDeviceToDevice, s));
                                 CK(cudaMemsetAsync(h->acc.p + P.numInterior, 0, h->bsum.bytes(), s));
@@ -607,6 +650,7 @@ int enqueue_substeps(tetsim *h, int count) {
                                 h->enq++;
                             }
                             if (h->halo) { launch_halo_pack(s, (int)P.hxSendIdx.size(), h->hxSendIdx.p, h->bsum.p, h->hxSend.p); h->enq++; }
+                            TR("boundary pack");
                             // 2. all-reduce (or neighbour exchange) over NVLink on the side stream ...
                             CK(cudaEventRecord(h->evFork, s));
                             CK(cudaStreamWaitEvent(h->commStream, h->evFork, 0));
@@ -629,12 +673,15 @@ int enqueue_substeps(tetsim *h, int count) {
                             TileArgs ci = ca;
                             ci.tileBegin = P.numBoundaryTiles;
                             launch_jacobi_tiles(s, P.T, ci);
+                            TR("interior tiles");
                             CK(cudaStreamWaitEvent(s, h->evJoin, 0));
                             if (h->halo) { launch_halo_reduce(s, P.numBoundary, h->hxSrcStart.p, h->hxSrc.p, h->hxRecv.p, h->bsum.p); h->enq++; }
+                            TR("exchange wait + reduce");
                             aa.bsum = h->bsum.p;
                             h->enq += 2 + (P.numBoundaryTiles > 0 && P.numBoundaryTiles < P.numClusters ? 1 : 0);
                         }
                         launch_jacobi_apply(s, 0, h->nInt, mode, aa);
+                        TR("vertex kernel");
                     }
                 }
                 break;
@@ -664,7 +711,7 @@ int run_substeps(tetsim *h, double dt, int count, const TetSimParams *params) {
     // pageable source: the runtime stages the 300 bytes before returning, so `hs` may die here
     CK(cudaMemcpyAsync(h->sp.p, &hs, sizeof(hs), cudaMemcpyHostToDevice, h->stream));
     const char *noGraph = getenv("TETSIM_NO_GRAPH");
-    if (noGraph && noGraph[0] == '1') {
+    if (h->trace || (noGraph && noGraph[0] == '1')) {
         int rc = enqueue_substeps(h, count);
         h->totalLaunches += h->enq;
         return rc;
@@ -809,6 +856,7 @@ int tetsim_create(const float *verts, int32_t numVerts, const int32_t *tetIds, i
     if (!h) return fail(TETSIM_E_NOMEM, "out of host memory");
     struct Cleanup { tetsim *h; bool armed = true; ~Cleanup() { if (armed) tetsim_destroy(h); } } cleanup{h};
     h->opt = opt; h->params = prm; h->N = numVerts; h->M = numTets; h->device = dev;
+    { const char *tr = getenv("TETSIM_TRACE"); h->trace = tr && tr[0] == '1'; }
     h->KX = exact_kernels();
     h->K = opt.arithmetic == TETSIM_ARITH_BITEXACT ? exact_kernels() : fast_kernels();
     if (opt.stream) h->stream = (cudaStream_t)opt.stream;
@@ -918,6 +966,7 @@ void tetsim_destroy(tetsim_t *h) {
     DeviceGuard g(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second);
+    if (h->trace) trace_report(h);
     for (void *m : h->peerOpened) cudaIpcCloseMemHandle(m);
     if (h->comm) g_nccl.CommDestroy(h->comm);
     if (h->evFork) cudaEventDestroy(h->evFork);
@@ -947,6 +996,7 @@ int tetsim_synchronize(tetsim_t *h) {
     if (!h) return fail(TETSIM_E_INVALID, "null handle");
     DeviceGuard g(h->device);
     CK(cudaStreamSynchronize(h->stream));
+    if (h->trace) trace_report(h);
     return peer_check(h);
 }
 
