@@ -659,7 +659,7 @@ void launch_build_tiles(cudaStream_t s, int clusterSize, int numRecords, const i
 // Vertex side of the clustered Jacobi: x += (sum of the vertex's tile partials) / valence, optionally
 // fused with post (simulate() :213-239) and with the NEXT substep's predict (:198-202) so a substep
 // inside tetsim_step costs exactly two launches.
-template <int MODE, bool PEER>
+template <int MODE, bool PEER, bool INLINE = false>
 __global__ void k_jacobi_apply(int begin, int end, ApplyArgs a) {
     const unsigned blk = (PEER && (a.pxFlags & kPeerV2ReverseBlocks)) ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
     int i = begin + blk * blockDim.x + threadIdx.x;
@@ -705,6 +705,24 @@ __global__ void k_jacobi_apply(int begin, int end, ApplyArgs a) {
         float4 s = a.acc[i];
         a.acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         sx = s.x; sy = s.y; sz = s.z;
+    } else if (INLINE) {
+        // experiment: the vertex's partial slots come in one 16-byte record, so the dependent chain is
+        // record -> partials (two levels) instead of vpStart -> vpSlot -> partials (three); same summation order
+        const uint4 r = __ldg(a.vpInline + i);
+        if (r.w == 0xfffffffeu) {
+            for (int j = a.vpStart[i]; j < a.vpStart[i + 1]; j++) {
+                float4 s = ldg4(a.part + a.vpSlot[j]);
+                sx += s.x; sy += s.y; sz += s.z;
+            }
+        } else {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 s0 = r.x != 0xffffffffu ? ldg4(a.part + r.x) : z, s1 = r.y != 0xffffffffu ? ldg4(a.part + r.y) : z;
+            const float4 s2 = r.z != 0xffffffffu ? ldg4(a.part + r.z) : z, s3 = r.w != 0xffffffffu ? ldg4(a.part + r.w) : z;
+            sx = 0.0f + s0.x; sy = 0.0f + s0.y; sz = 0.0f + s0.z;
+            if (r.y != 0xffffffffu) { sx += s1.x; sy += s1.y; sz += s1.z; }
+            if (r.z != 0xffffffffu) { sx += s2.x; sy += s2.y; sz += s2.z; }
+            if (r.w != 0xffffffffu) { sx += s3.x; sy += s3.y; sz += s3.z; }
+        }
     } else {
         for (int j = a.vpStart[i]; j < a.vpStart[i + 1]; j++) {
             float4 s = ldg4(a.part + a.vpSlot[j]);
@@ -743,6 +761,12 @@ void launch_jacobi_apply(cudaStream_t s, int begin, int end, int mode, const App
         if (mode == 0) k_jacobi_apply<0, true><<<cdiv(n, TB), TB, 0, s>>>(begin, end, a);
         else if (mode == 1) k_jacobi_apply<1, true><<<cdiv(n, TB), TB, 0, s>>>(begin, end, a);
         else k_jacobi_apply<2, true><<<cdiv(n, TB), TB, 0, s>>>(begin, end, a);
+        return;
+    }
+    if (a.vpInline && !a.acc) {  // experiment, single-GPU deterministic flush only
+        if (mode == 0) k_jacobi_apply<0, false, true><<<cdiv(n, TB), TB, 0, s>>>(begin, end, a);
+        else if (mode == 1) k_jacobi_apply<1, false, true><<<cdiv(n, TB), TB, 0, s>>>(begin, end, a);
+        else k_jacobi_apply<2, false, true><<<cdiv(n, TB), TB, 0, s>>>(begin, end, a);
         return;
     }
     if (mode == 0) k_jacobi_apply<0, false><<<cdiv(n, TB), TB, 0, s>>>(begin, end, a);

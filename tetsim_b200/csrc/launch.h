@@ -77,6 +77,8 @@ void launch_build_tiles(cudaStream_t, int clusterSize, int numRecords, const int
 struct ApplyArgs {
     float4 *x4, *prev4, *vel4;
     const int *vpStart, *vpSlot;    // vertex -> partial-sum slots (CSR into part[])
+    const uint4 *vpInline;          // experiment (TETSIM_APPLY_INLINE=1): up to 4 slots per vertex in ONE 16-byte record
+                                    // (0xffffffff = none; .w = 0xfffffffe = more than 4, use the CSR), or NULL
     const float4 *part;
     float4 *acc;                    // atomic-flush accumulator (read and re-zeroed) or NULL
     const float *invVal;            // 1 / valence

@@ -146,6 +146,7 @@ struct tetsim {
     // Jacobi cluster path
     ClusterPlan plan;
     DevBuf<int> vpStart, vpSlot;
+    DevBuf<uint4> vpInline;               // experiment TETSIM_APPLY_INLINE=1 (ApplyArgs::vpInline)
     DevBuf<unsigned char> tileTets, tileMeta;
     DevBuf<uint32_t> metaOff;
     DevBuf<float4> part, acc, bsum;
@@ -421,6 +422,18 @@ int build_jacobi_cluster(tetsim *h, const std::vector<float> &verts, const std::
     CK(h->vpStart.upload(P.vpStart, s));
     CK(h->vpSlot.upload(P.vpSlot, s));
     CK(h->invVal.upload(P.invValence, s));
+    if (const char *e = getenv("TETSIM_APPLY_INLINE")) {
+        if (e[0] == '1' && h->opt.worldSize == 1 && h->opt.deterministic) {
+            std::vector<uint4> rec((size_t)P.numLocalVerts, make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu));
+            for (int v = 0; v < P.numLocalVerts; v++) {
+                const int b = P.vpStart[v], n = P.vpStart[v + 1] - b;
+                if (n > 4) { rec[v].w = 0xfffffffeu; continue; }
+                unsigned *w = &rec[v].x;
+                for (int k = 0; k < n; k++) w[k] = (unsigned)P.vpSlot[b + k];
+            }
+            CK(h->vpInline.upload(rec, s));
+        }
+    }
     if (h->opt.deterministic) CK(h->part.alloc(P.clVerts.size()));
     else { CK(h->acc.alloc((size_t)P.numLocalVerts)); CK(cudaMemsetAsync(h->acc.p, 0, h->acc.bytes(), s)); }
     if (P.numBoundary > 0) CK(h->bsum.alloc((size_t)P.numBoundary));
@@ -595,6 +608,7 @@ int enqueue_substeps(tetsim *h, int count) {
                     ApplyArgs aa{};
                     aa.x4 = h->x4.p; aa.prev4 = h->prev4.p; aa.vel4 = h->vel4.p;
                     aa.vpStart = h->vpStart.p; aa.vpSlot = h->vpSlot.p; aa.part = h->part.p; aa.acc = h->acc.p;
+                    aa.vpInline = h->vpInline.p;
                     aa.invVal = h->invVal.p; aa.sp = sp; aa.vertId = vid;
                     aa.boundaryBegin = P.numInterior;
                     const bool multi = h->opt.worldSize > 1 && P.numBoundary > 0;
