@@ -8,7 +8,8 @@
  * PARITY UNPINNED: the reference ships no tests, golden vectors or known-answer fixtures for
  * this path, and no JavaScript engine exists in the build image, so the reference itself cannot
  * be executed.  The oracle is pinned only against (i) a second, independently structured numpy
- * restatement (oracle/oracle_np.py) and (ii) analytic properties (tests/test_oracle.py).
+ * restatement (oracle/oracle_np.py), (ii) analytic properties and (iii) a finite-difference XPBD projection of the
+ * published constraint functions (tests/test_oracle.py).
  *
  * Arithmetic rule being restated (JavaScript typed-array semantics):
  *   - every Float32Array read widens f32 -> f64,

@@ -172,3 +172,56 @@ def test_skin_and_normals_oracle(dragon):
     n = oracle.vertex_normals(s.reshape(-1), dragon["vis_tri_ids"]).reshape(-1, 3)
     ln = np.linalg.norm(n, axis=1)
     assert np.all((np.abs(ln - 1.0) < 1e-6) | (ln == 0.0))
+
+
+def test_projection_matches_the_published_constraints_by_finite_differences():
+    """Pins the restated solveElem/applyToElem (src/Softbody.js:91-193) to the PUBLISHED algorithm rather than to its
+    own code shape: Macklin & Mueller 2021 define the deviatoric constraint C_D = ||F||_F and the hydrostatic constraint
+    C_H = det F - 1 - alpha_vol/alpha_dev with F = Ds Dm^-1, projected by XPBD, dlambda = -C / (sum_i w_i |grad_i C|^2 +
+    alpha / (dt^2 V_rest)), dx_i = w_i grad_i C dlambda.  Here the gradients come from central finite differences of
+    those two scalar functions in float64 -- no hand-derived gradient, no matrix layout shared with the oracle -- for
+    random well-shaped tets with random deformations, and the per-tet displacement must agree with the oracle's to
+    float32 rounding."""
+    rng = np.random.default_rng(7)
+    dt, dev_c, vol_c, density = 1.0 / 600.0, 1e-5, 2e-6, 1000.0
+    for trial in range(20):
+        rest = (np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], float) * rng.uniform(0.05, 0.3)
+                + rng.normal(0, 0.01, (4, 3)) + rng.uniform(-1, 1, 3))
+        if np.linalg.det((rest[1:] - rest[0]).T) < 0:
+            rest[[1, 2]] = rest[[2, 1]]
+        rest32 = rest.astype(np.float32)
+        sb = oracle.SoftBodyOracle(rest32.reshape(-1), np.array([0, 1, 2, 3], np.int32), gravity=0.0, density=density,
+                                   devCompliance=dev_c, volCompliance=vol_c)
+        A = np.eye(3) + rng.normal(0, 0.15, (3, 3))                      # a random deformation of the rest shape
+        cur32 = (rest32.astype(float) @ A.T + rng.normal(0, 0.002, (4, 3))).astype(np.float32)
+        sb.pos[:] = cur32.reshape(-1)
+        got = sb.jacobi_accumulate(np.array([0], np.int32), dt).reshape(4, 3).astype(float)
+
+        r = rest32.astype(float)
+        Dm_inv = np.linalg.inv((r[1:] - r[0]).T)
+        V = np.linalg.det((r[1:] - r[0]).T) / 6.0
+        w = np.full(4, 1.0 / (V / 4.0 * density))                        # lumped mass V/4*rho per vertex (:75-78)
+
+        def F_of(x):
+            return (x[1:] - x[0]).T @ Dm_inv
+
+        def project(x, Cfun, alpha):
+            C = Cfun(x)
+            g = np.zeros((4, 3))
+            h = 1e-6
+            for i in range(4):
+                for c in range(3):
+                    xp, xm = x.copy(), x.copy()
+                    xp[i, c] += h
+                    xm[i, c] -= h
+                    g[i, c] = (Cfun(xp) - Cfun(xm)) / (2 * h)
+            dl = -C / ((w * (g * g).sum(1)).sum() + alpha / dt / dt / V)
+            return x + g * (w * dl)[:, None]
+
+        x0 = cur32.astype(float)
+        x1 = project(x0, lambda x: np.sqrt((F_of(x) ** 2).sum()), dev_c)
+        x2 = project(x1, lambda x: np.linalg.det(F_of(x)) - 1.0 - vol_c / dev_c, vol_c)
+        want = x2 - x0
+        scale = np.abs(want).max()
+        assert scale > 1e-6
+        assert np.abs(got - want).max() <= 2e-4 * scale + 2e-7, (trial, np.abs(got - want).max(), scale)
