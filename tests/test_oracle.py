@@ -279,3 +279,25 @@ def test_polar_rotation_extraction_against_svd_polar_decomposition():
             assert err < 5e-4, (trial, stretch, err)
             if not stretch:
                 assert np.abs(po.pos - cur.reshape(-1)).max() < 1e-6   # a rigidly moved tet is already at its goal
+
+
+def test_init_physics_identities(dragon):
+    """initPhysics (src/Softbody.js:60-87) against its defining identities, computed independently in float64:
+    invRestPose_e * Dm_e = I, invRestVolume_e = 1 / (det Dm_e / 6), and the lumped masses add up to density * volume
+    with every vertex receiving a quarter of each incident tet (the column-major layout of App. A is what makes the first
+    identity come out)."""
+    sb = oracle.SoftBodyOracle(dragon["tet_verts"], dragon["tet_ids"])
+    x = dragon["tet_verts"].reshape(-1, 3).astype(np.float64)
+    t = dragon["tet_ids"].reshape(-1, 4)
+    Dm = np.stack([x[t[:, 1]] - x[t[:, 0]], x[t[:, 2]] - x[t[:, 0]], x[t[:, 3]] - x[t[:, 0]]], axis=2)  # columns = edges
+    Q = sb.invRestPose.reshape(-1, 3, 3).transpose(0, 2, 1).astype(np.float64)   # stored column-major: A[9n + 3c + r]
+    I = np.einsum("eij,ejk->eik", Q, Dm)
+    cond = np.linalg.cond(Dm)
+    assert np.max(np.abs(I - np.eye(3)) / cond[:, None, None]) < 2e-6            # f32 storage of an inverse: error ~ eps * cond
+    V = np.linalg.det(Dm) / 6.0
+    assert V.min() > 0
+    np.testing.assert_allclose(sb.invRestVolume, 1.0 / V, rtol=2e-4)               # V itself comes from f32 edge vectors
+    m = np.zeros(len(x))
+    np.add.at(m, t.reshape(-1), np.repeat(V / 4.0 * 1000.0, 4))
+    np.testing.assert_allclose(1.0 / sb.invMass.astype(np.float64), m, rtol=2e-4)
+    assert abs((1.0 / sb.invMass.astype(np.float64)).sum() - 1000.0 * V.sum()) < 1e-4 * 1000.0 * V.sum()
