@@ -98,10 +98,10 @@ typedef struct TetSimOptions {
     int32_t exchange;          /* multi-GPU: 0 = ncclAllReduce of the boundary dx over all ranks (default),
                                   1 = neighbour exchange: grouped ncclSend/ncclRecv with the ranks that share
                                   vertices with this one, sharers' sums added in ascending rank order,
-                                  2 = peer-memory exchange: the kernel that forms this rank's boundary sums stores
-                                  them over NVLink straight into the sharers' receive buffers (cudaIpc mappings,
-                                  tetsim_get_ipc_handle / tetsim_set_peers) and publishes a flag; no NCCL, no
-                                  ncclUniqueId, same rank-ordered sums as 1                                     */
+                                  2 = peer-memory exchange: the tile kernel stores its partial sums of rank-shared
+                                  vertices over NVLink straight into the sharers' receive buffers (cudaIpc mappings,
+                                  tetsim_get_ipc_handle / tetsim_set_peers) as self-validating tagged entries, the
+                                  vertex kernel polls them; no NCCL, no ncclUniqueId, same rank-ordered sums as 1 */
     void *stream;              /* cudaStream_t to enqueue on; NULL = a stream owned by the handle     */
     const void *ncclUniqueId;  /* 128-byte ncclUniqueId from tetsim_nccl_unique_id (rank 0's), or NULL */
 } TetSimOptions;
