@@ -547,6 +547,13 @@ static void launch_tilesN(cudaStream_t s, const TileArgs &a) {
     }
     int grid = lc.sms * lc.n;
     if (grid > a.numTiles - a.tileBegin) grid = a.numTiles - a.tileBegin;
+    // experiment (round 2, multi-GPU ranks with few tiles per CTA): shrink the grid so every CTA walks the same number
+    // of tiles (2442 tiles on 592 CTAs = 4 or 5 each -> 489 CTAs x 5) instead of leaving most CTAs idle in the last round
+    static const bool balance = [] { const char *e = getenv("TETSIM_TILE_BALANCE"); return e && e[0] == '1'; }();
+    if (balance && grid > 0) {
+        const int tiles = a.numTiles - a.tileBegin, rounds = (tiles + grid - 1) / grid;
+        grid = (tiles + rounds - 1) / rounds;
+    }
     k_jacobi_tilesN<T, TPT, S, MINB, PEER><<<grid, T / TPT, smem, s>>>(a);
 }
 
