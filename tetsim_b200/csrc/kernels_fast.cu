@@ -264,6 +264,10 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
 
     const SubstepParams *sp = a.sp;
     const float alphaDev = sp->alphaDev, alphaVol = sp->alphaVol, gammaVol = sp->gammaVol;
+    // kPeerV2PushRecords: the epoch does not change while this kernel runs -- read it (and the record table) once
+    const bool pushByRecord = PEER && (a.pxFlags & kPeerV2PushRecords);
+    const uint4 *pushRec = pushByRecord ? a.px->pushRec : nullptr;
+    const unsigned pushEpoch = pushByRecord ? *reinterpret_cast<volatile unsigned *>(a.px->self + kPeerCtlOff) + 1u : 0u;
 
     auto issue_meta = [&](uint32_t o, uint32_t end, int slot) {  // one thread; block = [16*o, 16*end)
         const uint32_t bytes = (end - o) * 16u;
@@ -415,14 +419,44 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
                                      make_float4(ax, ay, az, 0.0f));
                 else a.part[v0 + j] = make_float4(ax, ay, az, 0.0f);
                 if (PEER) {  // multi-GPU, fused exchange: a rank-shared vertex's tile partial goes straight to the sharers
-                    const PeerArgs &px = *a.px;
                     const int slot = v0 + j;
-                    if (slot < ((a.pxFlags & kPeerV2SlotsByValue) ? a.pxSlots : px.numBoundarySlots)) {
-                        const unsigned i = px.slotIdx[slot];
-                        if (i != 0xffu) {
-                            const int id = reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3])[j];
-                            const unsigned e = *reinterpret_cast<volatile unsigned *>(px.self + kPeerCtlOff) + 1u;  // advanced by the vertex kernel
-                            peer_push_partial(px, id - px.boundaryBegin, (int)i, px.vpStart[id + 1] - px.vpStart[id], e, ax, ay, az);
+                    if (a.pxFlags & kPeerV2PushRecords) {
+                        if (slot < a.pxSlots) {
+                            const uint4 r0 = __ldg(pushRec + 2 * slot), r1 = __ldg(pushRec + 2 * slot + 1);
+                            if (r0.x != 0xffffffffu) {
+                                const unsigned i = r0.x & 0xffu, n1 = (r0.x >> 8) & 0xffu, sharers = r0.x >> 16;
+                                const unsigned tag = (pushEpoch & 0x0fffffffu) * (unsigned)kPeerK + n1;
+                                const unsigned long long p0 = ((unsigned long long)r0.w << 32) | r0.z, p1 = ((unsigned long long)r1.w << 32) | r1.z;
+                                unsigned char *d0 = reinterpret_cast<unsigned char *>(p0) + (size_t)(pushEpoch & 1u) * r1.x * 32;
+                                st_volatile_u4(d0, __float_as_uint(ax), tag, __float_as_uint(ay), tag);
+                                st_volatile_u4(d0 + 16, __float_as_uint(az), tag, 0u, tag);
+                                if (sharers > 1) {
+                                    unsigned char *d1 = reinterpret_cast<unsigned char *>(p1) + (size_t)(pushEpoch & 1u) * r1.y * 32;
+                                    st_volatile_u4(d1, __float_as_uint(ax), tag, __float_as_uint(ay), tag);
+                                    st_volatile_u4(d1 + 16, __float_as_uint(az), tag, 0u, tag);
+                                }
+                                if (sharers > 2) {  // a vertex on a corner of the partition: the remaining sharers from the CSR
+                                    const PeerArgs &px = *a.px;
+                                    const int b = (int)r0.y;
+                                    for (int t = px.pxStart[b] + 2; t < px.pxStart[b + 1]; t++) {
+                                        const int q = px.pxPeer[t];
+                                        unsigned char *dst = px.peerBase[q] + kPeerRecvOff +
+                                                             (((size_t)(pushEpoch & 1u) * px.remoteTotal[q] + px.pxEntry[t]) * kPeerK + i) * 32;
+                                        st_volatile_u4(dst, __float_as_uint(ax), tag, __float_as_uint(ay), tag);
+                                        st_volatile_u4(dst + 16, __float_as_uint(az), tag, 0u, tag);
+                                    }
+                                }
+                            }
+                        }
+                    } else {
+                        const PeerArgs &px = *a.px;
+                        if (slot < ((a.pxFlags & kPeerV2SlotsByValue) ? a.pxSlots : px.numBoundarySlots)) {
+                            const unsigned i = px.slotIdx[slot];
+                            if (i != 0xffu) {
+                                const int id = reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3])[j];
+                                const unsigned e = *reinterpret_cast<volatile unsigned *>(px.self + kPeerCtlOff) + 1u;  // advanced by the vertex kernel
+                                peer_push_partial(px, id - px.boundaryBegin, (int)i, px.vpStart[id + 1] - px.vpStart[id], e, ax, ay, az);
+                            }
                         }
                     }
                 }
@@ -666,8 +700,8 @@ void launch_build_tiles(cudaStream_t s, int clusterSize, int numRecords, const i
 // Vertex side of the clustered Jacobi: x += (sum of the vertex's tile partials) / valence, optionally
 // fused with post (simulate() :213-239) and with the NEXT substep's predict (:198-202) so a substep
 // inside tetsim_step costs exactly two launches.
-template <int MODE, bool PEER, bool INLINE = false>
-__global__ void k_jacobi_apply(int begin, int end, ApplyArgs a) {
+template <int MODE, bool PEER, bool INLINE = false, bool LB8 = false>
+__global__ void __launch_bounds__(256, LB8 ? 8 : 1) k_jacobi_apply(int begin, int end, ApplyArgs a) {
     const unsigned blk = (PEER && (a.pxFlags & kPeerV2ReverseBlocks)) ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
     int i = begin + blk * blockDim.x + threadIdx.x;
     unsigned epoch = 0u;
@@ -764,6 +798,12 @@ void launch_jacobi_apply(cudaStream_t s, int begin, int end, int mode, const App
     int n = end - begin;
     if (n <= 0) return;
     const int TB = 256;
+    if (a.px && (a.pxFlags & kPeerV2Apply32Regs)) {  // experiment: the same kernel capped at 32 registers
+        if (mode == 0) k_jacobi_apply<0, true, false, true><<<cdiv(n, TB), TB, 0, s>>>(begin, end, a);
+        else if (mode == 1) k_jacobi_apply<1, true, false, true><<<cdiv(n, TB), TB, 0, s>>>(begin, end, a);
+        else k_jacobi_apply<2, true, false, true><<<cdiv(n, TB), TB, 0, s>>>(begin, end, a);
+        return;
+    }
     if (a.px) {  // multi-GPU, fused peer exchange: poll + rank-ordered reduce for the rank-shared vertices
         if (mode == 0) k_jacobi_apply<0, true><<<cdiv(n, TB), TB, 0, s>>>(begin, end, a);
         else if (mode == 1) k_jacobi_apply<1, true><<<cdiv(n, TB), TB, 0, s>>>(begin, end, a);

@@ -125,6 +125,11 @@ struct PeerArgs {
     unsigned long long timeoutNs;         // give up waiting after this long (sets ctl[2])
     const unsigned char *slotIdx;         // fused push: [numBoundarySlots] partial index of a boundary-tile slot, 0xff = not shared
     int numBoundarySlots;
+    // kPeerV2PushRecords: everything a push needs in ONE 32-byte record per boundary-tile slot (two parallel 16-byte loads):
+    //   rec[2 s]     = {i | (count - 1) << 8 | sharers << 16 (or ~0: not shared), boundary id, address of sharer 0's entry (lo, hi)}
+    //   rec[2 s + 1] = {parity stride of sharer 0, of sharer 1 (units of 32 B), address of sharer 1's entry (lo, hi)}
+    // entry addresses are those of the parity-0 half; a third and further sharer (partition corners) come from the CSR.
+    const uint4 *pushRec;
 };
 // Fused form (deterministic flush; the default of exchange = 2): the tile kernel itself pushes, with NO synchronisation
 // at all on the sending side.  A thread that has just formed a tile's partial sum of a rank-shared vertex stores it, next
@@ -142,6 +147,8 @@ struct PeerArgs {
 constexpr int kPeerV2SlotsByValue = 1;    // tile kernel: "is this a boundary-tile slot" from a kernel parameter, not through px->
 constexpr int kPeerV2TileAdvances = 2;    // the tile kernel's CTAs (not the vertex kernel's blocks) advance the epoch
 constexpr int kPeerV2ReverseBlocks = 4;   // vertex kernel: blocks holding the rank-shared vertices are scheduled first
+constexpr int kPeerV2PushRecords = 8;     // tile kernel: one 32-byte record per push + epoch read once per CTA (one dependent load level, not four)
+constexpr int kPeerV2Apply32Regs = 16;    // vertex kernel capped at 32 registers (8 blocks per SM like the single-GPU kernel)
 constexpr int kPeerK = 16;                // most tile partials a rank may hold for one shared vertex (checked at create)
 void launch_peer_push(cudaStream_t, const PeerArgs &a);
 void launch_peer_reduce(cudaStream_t, const PeerArgs &a);

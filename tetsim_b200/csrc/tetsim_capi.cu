@@ -189,6 +189,7 @@ struct tetsim {
     DevBuf<unsigned char *> peerBase;       // [peers] mapped exchange allocation of each sharer
     DevBuf<int> pxStart, pxPeer, pxEntry, pxRemoteTotal, pxRemoteSlot;
     DevBuf<unsigned char> pxSlotIdx;        // fused push: partial index of every boundary-tile partial slot
+    DevBuf<uint4> pushRec;                  // kPeerV2PushRecords: two uint4 per boundary-tile partial slot (PeerArgs::pushRec)
     DevBuf<PeerArgs> pxArgs;                // device copy of peer_args(h), read by the tile and vertex kernels
     bool peerFused = false;                 // the tile kernel pushes, the vertex kernel polls + reduces (2 launches/iteration)
     int peerV2 = 0;                         // TETSIM_PEER_V2 experiment mask (kPeerV2*), read at create
@@ -458,7 +459,7 @@ int build_jacobi_cluster(tetsim *h, const std::vector<float> &verts, const std::
         // the fused push sends tile partials, so it needs the deterministic flush (per-tile partial sums).  The choice
         // must be the same on every rank (it fixes the layout of the receive buffers): options + environment only.
         h->peerFused = h->opt.deterministic != 0 && !(unfused && unfused[0] == '1') && jacobi_tiles_has_peer_push(P.T);
-        if (const char *v2 = getenv("TETSIM_PEER_V2")) h->peerV2 = atoi(v2) & 7;
+        if (const char *v2 = getenv("TETSIM_PEER_V2")) h->peerV2 = atoi(v2) & 31;
         if (P.T < 128) h->peerV2 &= ~kPeerV2TileAdvances;  // warp-tile workers have no CTA-level ticket
         if (h->peerFused && P.pxMaxPartials > kPeerK)
             return fail(TETSIM_E_STATE, "a rank-shared vertex has " + std::to_string(P.pxMaxPartials) + " tile partials on this rank (limit " + std::to_string(kPeerK) + "): use a larger clusterSize or exchange = 1");
@@ -560,6 +561,7 @@ PeerArgs peer_args(const tetsim *h) {
     a.self = h->peerBuf.p; a.selfTotal = (int)P.hxSendIdx.size();
     a.srcStart = h->hxSrcStart.p; a.src = h->hxSrc.p;
     a.slotIdx = h->pxSlotIdx.p; a.numBoundarySlots = (int)P.pxSlotIdx.size();
+    a.pushRec = h->pushRec.p;
     unsigned long long ms = 10000ull;
     if (const char *e = getenv("TETSIM_PEER_TIMEOUT_MS")) { long v = atol(e); if (v > 0) ms = (unsigned long long)v; }
     a.timeoutNs = ms * 1000000ull;
@@ -1281,6 +1283,29 @@ int tetsim_set_peers(tetsim_t *h, const void *blobs) {
         }
     }
     CK(cudaMemcpyAsync(h->peerBase.p, base.data(), base.size() * sizeof(unsigned char *), cudaMemcpyHostToDevice, h->stream));
+    if (h->peerFused && (h->peerV2 & kPeerV2PushRecords)) {  // experiment: one self-contained 32-byte record per pushing slot
+        std::vector<uint4> rec(2 * std::max<size_t>(P.pxSlotIdx.size(), 1), make_uint4(0xffffffffu, 0u, 0u, 0u));
+        for (int b = 0; b < P.numBoundary; b++) {
+            const int id = P.numInterior + b, n = P.vpStart[id + 1] - P.vpStart[id];
+            const int t0 = P.pxStart[b], sharers = P.pxStart[b + 1] - t0;
+            if (n == 0 || sharers == 0) continue;
+            for (int i = 0; i < n; i++) {
+                const size_t slot = (size_t)P.vpSlot[P.vpStart[id] + i];
+                uint4 r0 = make_uint4((unsigned)i | (unsigned)(n - 1) << 8 | (unsigned)sharers << 16, (unsigned)b, 0u, 0u), r1 = make_uint4(0u, 0u, 0u, 0u);
+                for (int k = 0; k < 2 && k < sharers; k++) {
+                    const int q = P.pxPeer[t0 + k];
+                    const unsigned long long addr = (unsigned long long)(uintptr_t)(base[q] + kPeerRecvOff) +
+                                                    ((unsigned long long)P.pxEntry[t0 + k] * kPeerK + (unsigned)i) * 32ull;
+                    const unsigned stride = (unsigned)P.pxRemoteTotal[q] * (unsigned)kPeerK;  // parity stride in 32-byte units
+                    if (k == 0) { r0.z = (unsigned)addr; r0.w = (unsigned)(addr >> 32); r1.x = stride; }
+                    else { r1.z = (unsigned)addr; r1.w = (unsigned)(addr >> 32); r1.y = stride; }
+                }
+                rec[2 * slot] = r0;
+                rec[2 * slot + 1] = r1;
+            }
+        }
+        CK(h->pushRec.upload(rec, h->stream));
+    }
     const PeerArgs pa = peer_args(h);
     CK(cudaMemcpyAsync(h->pxArgs.p, &pa, sizeof(pa), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));

@@ -2,7 +2,7 @@
 # N-GPU pass (gpurun --gpus N -- 'NGPU=N bash tools/gpu_pass_multigpu.sh'): correctness of the exchanges through real
 # cudaIpc / NCCL, then bench.py at N for every exchange mode (and every TETSIM_PEER_V2 experiment mask for the peer
 # exchange), then one traced run per mode (TETSIM_TRACE=1: per-launch intervals on every rank).
-#   EXCHANGES="peer halo allreduce"  TILES="512 256"  PEER_V2S="0 2 4 6 7"  TRACE=1  CHECKS="peer"
+#   EXCHANGES="peer halo allreduce"  TILES="512 256"  PEER_V2S="0 2 4 8 16 31"  TRACE=1  CHECKS="peer"
 N=${NGPU:-2}
 mkdir -p gpurun_out
 run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $1 "${@:2}"; }
