@@ -12,9 +12,9 @@ timeout 200 python bench.py > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.er
 TETSIM_APPLY_INLINE=1 timeout 200 python bench.py --no-cpu-baseline > gpurun_out/r2_bench_inline.json 2> gpurun_out/r2_bench_inline.err
 timeout 200 python tools/tile_sweep.py --sizes 512,256 --out gpurun_out/r2_tile_sweep.txt > gpurun_out/r2_sweep.log 2>&1
 timeout 150 ncu --set full --clock-control none --import-source on -k regex:"k_jacobi_tiles|k_jacobi_apply" -s 4 -c 2 -f -o gpurun_out/r2_prof \
-    python tools/profile_driver.py --cluster-size 512 > gpurun_out/r2_prof.log 2>&1
+    python tools/profile_driver.py --cluster-size 512 --steps 2 > gpurun_out/r2_prof.log 2>&1
 TETSIM_APPLY_INLINE=1 timeout 150 ncu --set full --clock-control none --import-source on -k regex:k_jacobi_apply -s 2 -c 1 -f -o gpurun_out/r2_prof_inline \
-    python tools/profile_driver.py --cluster-size 512 > gpurun_out/r2_prof_inline.log 2>&1
+    python tools/profile_driver.py --cluster-size 512 --steps 2 > gpurun_out/r2_prof_inline.log 2>&1
 tail -3 gpurun_out/r2_pytest.log; tail -3 gpurun_out/r2_peer_masks.log
 for f in gpurun_out/r2_bench.json gpurun_out/r2_bench_inline.json; do
   tail -1 $f | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$f', 'value', round(d['value']), 'ms/step', round(d['ms_per_step'],3), 'e2e', round(d['e2e']['value']), 'frac', round(d['roofline']['frac'],3))" || tail -3 ${f%.json}.err
