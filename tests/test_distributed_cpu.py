@@ -1,4 +1,4 @@
-"""World-size-2 tests of the multi-GPU HOST logic on CPU (gloo): the tet partition every rank derives
+"""World-size-2 and -3 tests of the multi-GPU HOST logic on CPU (gloo): the tet partition every rank derives
 independently must be consistent across ranks, and the exchange it implies -- each rank sums the dx of
 its own tets, the shared-boundary sums are all-reduced, every rank applies the reduced value -- must
 reproduce the single-process Jacobi iteration.  The per-tet arithmetic is the oracle's (this is test
@@ -70,6 +70,18 @@ def _worker(rank, world, port, cluster_size, out):
     res = ~np.isnan(merged[:, 0])
     scale = np.abs(full).max()
     assert np.max(np.abs(merged[res] - full[res])) <= 2e-6 * scale
+    # ---- the neighbour / peer-memory exchanges: every sharer adds the ranks' sums in ascending rank order ----
+    mine = torch.from_numpy(acc[l2c[nI:]].copy())          # this rank's sums of the boundary vertices (zeros where it has no tet)
+    every = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(every, mine)
+    ordered = np.zeros((nB, 3), np.float32)
+    for q in range(world):                                 # float32, rank 0 first: the order k_halo_reduce / k_jacobi_apply<PEER> use
+        ordered = ordered + every[q].numpy()
+    mine_bits = torch.from_numpy(ordered.view(np.int32).copy())
+    all_bits = [torch.zeros_like(mine_bits) for _ in range(world)]
+    dist.all_gather(all_bits, mine_bits)
+    assert all(torch.equal(all_bits[0], x) for x in all_bits), "rank-ordered sums must be bit-identical on every rank"
+    assert np.max(np.abs(ordered - full[l2c[nI:]])) <= 2e-6 * scale
     # every vertex is resident somewhere
     r = torch.from_numpy(res.astype(np.int32))
     dist.all_reduce(r)
@@ -78,19 +90,19 @@ def _worker(rank, world, port, cluster_size, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("cluster_size", [64, 256])
-def test_partition_and_exchange_world2(cluster_size):
+@pytest.mark.parametrize("world,cluster_size", [(2, 64), (2, 256), (3, 128)])
+def test_partition_and_exchange(world, cluster_size):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, cluster_size, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, cluster_size, q)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
         p.join(180)
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
-    got = sorted(q.get(timeout=5) for _ in range(2))
-    assert got[0][2] == got[1][2] > 0
+    got = sorted(q.get(timeout=5) for _ in range(world))
+    assert len({g[2] for g in got}) == 1 and got[0][2] > 0
 
 
 @pytest.mark.parametrize("world", [2, 3, 4, 8])
