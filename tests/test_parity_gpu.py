@@ -19,9 +19,10 @@ from util import DT600, DT1200, assert_bit_equal, vec_rel_err
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-4  # north_star: "vertex positions within 1e-4 rel of the reference after 100 substeps"
-# Velocities are (x - prev) / dt (src/Softbody.js:238-239): a position difference at the 1e-4 tolerance is
-# amplified by 1/dt, i.e. 1e-4 * 1200 = 0.12 at dt = 1/1200.  (north_star states no velocity tolerance.)
-VEL_TOL_1200 = TOL * 1200.0
+# Velocities are (x - prev) / dt (src/Softbody.js:238-239), so position rounding is amplified by 1/dt; north_star states
+# no velocity tolerance.  The bar is tied to what was MEASURED for this kernel on Dragon after 100 substeps at dt = 1/1200
+# (profiles/r1_jacobi_accuracy.txt: max |dv| 3.7e-2 m/s at a position error of 2.2e-5, every tile size), with 2x margin.
+VEL_TOL_1200 = 7.5e-2
 
 
 def new_body(m, cls=ts.SoftBody, params=None, **kw):
@@ -517,3 +518,84 @@ def test_config4_full_size_beam_jacobi():
     sb2 = ts.SoftBody(v, t, None, p, solver="jacobi")
     sb2.step(p)
     assert_bit_equal(sb2.pos, x, "tile kernel is deterministic")
+
+
+# ------------------------------------------------------------------------------------------------
+# The CUDA path against the REFERENCE'S OWN TEXT (tests/golden/ref_golden.npz was produced by executing the
+# mechanically transpiled src/Softbody.js, tools/transpile_reference.py + tools/make_ref_golden.py; the oracle is not
+# involved here at all)
+# ------------------------------------------------------------------------------------------------
+from oracle import ref_scenarios  # noqa: E402  (scenario definitions only: dt, params, grab events)
+
+REF_GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_golden.npz"))
+
+
+@pytest.mark.parametrize("sc", ref_scenarios.SCENARIOS, ids=[s["name"] for s in ref_scenarios.SCENARIOS])
+def test_cuda_bitexact_reproduces_the_transpiled_reference(dragon, sc):
+    v = ref_scenarios.shifted(dragon["tet_verts"], sc["shift"])
+    sb = ts.SoftBody(v, dragon["tet_ids"], None, dict(ts.DEFAULT_PHYSICS_PARAMS, **sc["params"]), solver="gs_exact", arithmetic="bitexact")
+    seen = []
+
+    def check(step, d):
+        seen.append(step)
+        n = sc["name"]
+        assert_bit_equal(d["pos"], REF_GOLD["%s_pos_%d" % (n, step)], "%s pos @%d" % (n, step))
+        assert_bit_equal(d["prev"], REF_GOLD["%s_prev_%d" % (n, step)], "%s prevPos @%d" % (n, step))
+        assert_bit_equal(d["vel"], REF_GOLD["%s_vel_%d" % (n, step)], "%s vel @%d" % (n, step))
+        assert d["volError"] == float(REF_GOLD["%s_volError_%d" % (n, step)]), (n, step)
+        assert d["grabId"] == int(REF_GOLD["%s_grabId_%d" % (n, step)]), (n, step)
+
+    class Drive:   # simulate(dt, params) with the scenario's params merged over the defaults, like Main.update does
+        def simulate(self, dt, params):
+            sb.simulate(dt, dict(ts.DEFAULT_PHYSICS_PARAMS, **params))
+        startGrab, moveGrabbed, endGrab = sb.startGrab, sb.moveGrabbed, sb.endGrab
+
+    ref_scenarios.run(sc, Drive(), lambda _: dict(pos=sb.pos, prev=sb.prevPos, vel=sb.vel, volError=sb.volError, grabId=sb.grabId), check)
+    assert tuple(seen) == tuple(sc["save"])
+
+
+def test_cuda_init_skinning_and_polar_init_equal_the_transpiled_reference(dragon):
+    sb = ts.SoftBody(dragon["tet_verts"], dragon["tet_ids"], dragon["tet_edge_ids"], None, dragon["vis_verts"], dragon["vis_tri_ids"],
+                     solver="gs_exact", arithmetic="bitexact")
+    assert_bit_equal(sb.invRestPose, REF_GOLD["invRestPose"], "invRestPose")
+    assert_bit_equal(sb.invRestVolume, REF_GOLD["invRestVolume"], "invRestVolume")
+    assert_bit_equal(sb.invMass, REF_GOLD["invMass"], "invMass")
+    assert_bit_equal(sb.visMesh.positions, REF_GOLD["vis_pos_0"], "updateVisMesh in the constructor")
+    for _ in range(100):
+        sb.simulate(DT600)
+    sb.endFrame()
+    assert_bit_equal(sb.visMesh.positions, REF_GOLD["vis_pos_100"], "updateVisMesh @100")
+    assert_bit_equal(sb.edgeMesh.positions, REF_GOLD["edge_pos_100"], "updateEdgeMesh @100")
+    # SoftBodyGPU.initPhysics (src/SoftbodyGPU.js:487-608): goal corners, quaternions
+    M = dragon["tet_ids"].size // 4
+    g = ts.SoftBodyGPU(dragon["tet_verts"], dragon["tet_ids"], None, None, arithmetic="bitexact")
+    el = g.elems.reshape(M, 4, 3)
+    for k in range(4):
+        assert_bit_equal(el[:, k, :], REF_GOLD["gpu_elems0_%d" % k].reshape(-1, 4)[:M, :3], "elems0[%d]" % k)
+    assert_bit_equal(g.quats.reshape(M, 4), REF_GOLD["gpu_quats0"].reshape(-1, 4)[:M], "quats0")
+
+
+def test_config4_bench_configuration_100_substeps():
+    """BASELINE config 4 exactly as bench.py runs it -- T = 512 tiles, 20-substep CUDA graphs (tetsim_step, post of one
+    substep fused with the predict of the next), dt = 1/1200, iters = 1 -- on a JITTERED 1,038,336-tet beam, 100 substeps
+    against the oracle's Jacobi: north_star's 1e-4 on vertex positions."""
+    cells = (64, 52, 52)
+    v, t = mesh.make_beam(cells, jitter=0.2)
+    assert t.size // 4 == 6 * 64 * 52 * 52 >= 1_000_000
+    p = dict(ts.DEFAULT_PHYSICS_PARAMS, numSubsteps=20, worldBounds=list(mesh.wide_bounds(64.0)))
+    sb = ts.SoftBody(v, t, None, p, solver="jacobi", arithmetic="fast", cluster_size=512, track_vol_error=True)
+    assert sb.info()["clusterSize"] == 512 and sb.info()["launchesPerSubstep"] == 2
+    ref = oracle.SoftBodyOracle(v, t, worldBounds=p["worldBounds"])
+    for frame in range(5):
+        sb.step(p)
+        for _ in range(20):
+            ref.simulate_jacobi(DT1200, 1)
+        err = vec_rel_err(sb.pos, ref.pos)
+        assert err <= TOL, (frame, err)
+    assert vec_rel_err(sb.prevPos, ref.prevPos) <= TOL
+    assert np.max(np.abs(sb.vel - ref.vel)) <= VEL_TOL_1200
+    assert abs(sb.volError - ref.volError) < 1e-4
+    sb2 = ts.SoftBody(v, t, None, p, solver="jacobi", arithmetic="fast", cluster_size=512)
+    for _ in range(5):
+        sb2.step(p)
+    assert_bit_equal(sb2.pos, sb.pos, "run-to-run")

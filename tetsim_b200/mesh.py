@@ -1,7 +1,7 @@
 """Mesh inputs for the solver: the reference's Dragon, tiled copies of a body, the synthetic beam.
 
 The reference's only input is src/Dragon.js (five JS array literals, src/Dragon.js:1,311,1080,1705,11640);
-tools/extract_dragon.py turns it into tests/golden/dragon_mesh.npz, which is what is loaded here.
+tools/extract_dragon.py turns it into tetsim_b200/assets/dragon_mesh.npz (a packaged asset), which is what is loaded here.
 The tiler and the beam generator produce the BASELINE.json scale configs.
 """
 from __future__ import annotations
@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-DRAGON_NPZ = os.path.join(_ROOT, "tests", "golden", "dragon_mesh.npz")
+DRAGON_NPZ = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets", "dragon_mesh.npz")
 
 
 def load_dragon(path: str = DRAGON_NPZ) -> dict:

@@ -7,14 +7,14 @@ float32 for the two Float32Arrays (same rounding a JS `new Float32Array([...])` 
 decimal -> float64 -> float32), ints for the three index arrays.
 
 Run in the build container only (reads /root/reference); the output
-tests/golden/dragon_mesh.npz is committed and is what travels to the GPU box.
+tetsim_b200/assets/dragon_mesh.npz is committed and is what travels to the GPU box.
 """
 import re
 import sys
 import numpy as np
 
 SRC = sys.argv[1] if len(sys.argv) > 1 else "/root/reference/src/Dragon.js"
-OUT = sys.argv[2] if len(sys.argv) > 2 else "tests/golden/dragon_mesh.npz"
+OUT = sys.argv[2] if len(sys.argv) > 2 else "tetsim_b200/assets/dragon_mesh.npz"
 
 text = open(SRC).read()
 

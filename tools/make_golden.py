@@ -21,7 +21,7 @@ import oracle  # noqa: E402
 DT600 = (1.0 * (1.0 / 60.0)) / 10
 DT1200 = (1.0 * (1.0 / 60.0)) / 20
 
-m = np.load(os.path.join(ROOT, "tests", "golden", "dragon_mesh.npz"))
+m = np.load(os.path.join(ROOT, "tetsim_b200", "assets", "dragon_mesh.npz"))
 V, T = m["tet_verts"], m["tet_ids"]
 out = {}
 
