@@ -58,8 +58,11 @@ def parse():
                     help="strong: the same 10M-tet mesh split over N GPUs (BASELINE config 4); weak: beam length x N")
     ap.add_argument("--cpu-substeps", type=int, default=6, help="substeps of the CPU baseline sample (rank 0, N=1)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "allreduce", "halo", "peer"],
-                    help="multi-GPU boundary exchange: ncclAllReduce over all ranks, or grouped ncclSend/ncclRecv with the neighbour ranks; "
-                         "auto = all-reduce at 2 GPUs, neighbour exchange beyond (measured 22 %% faster at 8 GPUs, profiles/r1_scaling.md)")
+                    help="multi-GPU boundary exchange: ncclAllReduce over all ranks, grouped ncclSend/ncclRecv with the neighbour ranks, or the "
+                         "fused peer-memory exchange (the tile kernel stores its boundary partials straight into the sharers' buffers over "
+                         "NVLink); auto = peer (measured fastest, profiles/r2_peer_experiments.txt), falling back to halo without peer access")
+    ap.add_argument("--no-parity", action="store_true", help="skip the N-rank-vs-1-rank check at N > 1")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config rates (BASELINE configs 1, 2, 3, 5) at N = 1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -149,21 +152,115 @@ def cpu_dragon_substeps_per_s(substeps=300):
     return substeps / (time.perf_counter() - t0)
 
 
+def vec_rel(x, ref):
+    x, r = np.asarray(x, np.float64).reshape(-1, 3), np.asarray(ref, np.float64).reshape(-1, 3)
+    return float(np.max(np.linalg.norm(x - r, axis=1) / np.maximum(np.linalg.norm(r, axis=1), 1e-30)))
+
+
+def jacobi_vs_gs(stream, substeps=100, iters_list=(1, 2, 4, 8, 16)):
+    """How far NH-Jacobi(iters) is from the reference's answer: Dragon, 100 substeps at dt = 1/600 (BASELINE config 1),
+    vector-relative position error against the reference-order Gauss-Seidel run by this library in BITEXACT arithmetic
+    (bit-identical to src/Softbody.js, tests/test_parity_gpu.py), and the tet-projection rate divided by iters
+    ("equal-substep" rate).  The reference never runs Jacobi Neo-Hookean (README.md:25)."""
+    import torch
+    import tetsim_b200 as ts
+    from tetsim_b200 import mesh
+    m = mesh.load_dragon()
+    dt = FRAME_DT / 10
+    pp = dict(ts.DEFAULT_PHYSICS_PARAMS, numSubsteps=10)
+    gs = ts.SoftBody(m["tet_verts"], m["tet_ids"], None, pp, solver="gs_exact", arithmetic="bitexact", stream=stream.cuda_stream)
+    for _ in range(substeps // 10):
+        gs.step(pp)
+    ref = gs.pos.copy()
+    gs.close()
+    y0 = m["tet_verts"].reshape(-1, 3)[:, 1]
+    out = {"reference": "NH Gauss-Seidel in tet order, BITEXACT (== src/Softbody.js), Dragon, %d substeps at dt=1/600" % substeps,
+           "free_fall_drop_m": float(np.mean(y0) - np.mean(ref.reshape(-1, 3)[:, 1])), "by_iters": {}}
+    for it in iters_list:
+        jb = ts.SoftBody(m["tet_verts"], m["tet_ids"], None, pp, solver="jacobi", arithmetic="fast", iters=it, stream=stream.cuda_stream)
+        for _ in range(substeps // 10):
+            jb.step(pp)
+        x = jb.pos.copy()
+        # shape error with the rigid translation removed: how different the deformed shape is, in units of the body size
+        a, b = x.reshape(-1, 3).astype(np.float64), ref.reshape(-1, 3).astype(np.float64)
+        shape = float(np.max(np.linalg.norm((a - a.mean(0)) - (b - b.mean(0)), axis=1)) / np.max(np.ptp(b, axis=0)))
+        out["by_iters"][str(it)] = {"vec_rel_err": vec_rel(x, ref), "shape_err_rel_body_size": shape}
+        jb.close()
+    return out
+
+
+def config_rates(stream, device_index, frames=20):
+    """Driver-visible rates of the BASELINE configs the headline does not cover (1, 2, 3(i), 3(ii), 5), one B200, each with
+    its own clock sample: substeps/s and tet-projections/s through tetsim_step (one CUDA-graph launch per frame)."""
+    import torch
+    import tetsim_b200 as ts
+    from tetsim_b200 import mesh
+    m = mesh.load_dragon()
+    out = {}
+
+    def rate(key, what, make, pp, nframes):
+        body = make()
+        for _ in range(3):
+            body.step(pp)
+        body.synchronize()
+        smp = ClockSampler(device_index)
+        smp.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(nframes):
+            body.step(pp)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        info = body.info()
+        sub = nframes * pp["numSubsteps"]
+        out[key] = {"what": what, "substeps_per_s": sub / ms * 1e3, "Mtet_per_s": info["numTets"] * info["iters"] * sub / ms / 1e3,
+                    "tets": info["numTets"], "launches_per_substep": info["launchesPerSubstep"], "ms_timed": ms,
+                    "finite": bool(np.isfinite(body.pos).all()), "clocks": smp.stop()}
+        body.close()
+
+    p10 = dict(ts.DEFAULT_PHYSICS_PARAMS, numSubsteps=10)
+    p20 = dict(ts.DEFAULT_PHYSICS_PARAMS, numSubsteps=20)
+    sk = dict(stream=stream.cuda_stream)
+    V, T = m["tet_verts"], m["tet_ids"]
+    rate("C1_C3i_gs_exact_bitexact", "Dragon, NH Gauss-Seidel in the reference order, the reference's arithmetic (bit-identical to src/Softbody.js)",
+         lambda: ts.SoftBody(V, T, None, p10, solver="gs_exact", arithmetic="bitexact", **sk), p10, frames)
+    rate("C1_C3i_gs_exact_fast", "Dragon, NH Gauss-Seidel in the reference order, f32",
+         lambda: ts.SoftBody(V, T, None, p10, solver="gs_exact", arithmetic="fast", **sk), p10, frames)
+    rate("C3ii_gs_color_fast", "Dragon, NH Gauss-Seidel by greedy graph colouring (32 colours), f32",
+         lambda: ts.SoftBody(V, T, None, p10, solver="gs_color", arithmetic="fast", **sk), p10, frames)
+    rate("C2_polar_fast", "Dragon, polar-decomposition Jacobi (SoftBodyGPU), 20 substeps/frame, f32",
+         lambda: ts.SoftBodyGPU(V, T, None, dict(p20), **sk), p20, frames)
+    rate("C2_polar_bitexact", "Dragon, polar-decomposition Jacobi (SoftBodyGPU), 20 substeps/frame, the shader's arithmetic",
+         lambda: ts.SoftBodyGPU(V, T, None, dict(p20), arithmetic="bitexact", **sk), p20, frames)
+    wb = list(mesh.wide_bounds(64.0))
+    for n in (8, 28):
+        v, t = mesh.tile_bodies(V, T, n, n, y_shift=-0.40)
+        pw = dict(p10, worldBounds=wb)
+        rate("C5_%dx_gs_exact_fast" % (n * n), "%d tiled Dragons + ground, NH Gauss-Seidel in the reference order per body, f32" % (n * n),
+             lambda: ts.SoftBody(v, t, None, pw, solver="gs_exact", arithmetic="fast", **sk), pw, max(3, frames // 2))
+        pj = dict(p20, worldBounds=wb)
+        rate("C5_%dx_jacobi_tiles" % (n * n), "%d tiled Dragons + ground, NH Jacobi tile kernel (unstructured mesh), 20 substeps/frame" % (n * n),
+             lambda: ts.SoftBody(v, t, None, pj, solver="jacobi", arithmetic="fast", cluster_size=512, **sk), pj, frames)
+    out["jacobi_vs_gs"] = jacobi_vs_gs(stream)
+    return out
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.exchange == "auto":
-        args.exchange = "halo" if world > 2 else "allreduce"
+        args.exchange = "peer"
     cells = tuple(int(c) for c in args.cells.split(","))
     if args.scaling == "weak":
         cells = (cells[0] * max(world, 1), cells[1], cells[2])
     dt = FRAME_DT / args.substeps
     from tetsim_b200 import mesh
 
-    workload = "beam %dx%dx%d cells Kuhn-split, NH Jacobi iters=%d, dt=1/%d, %d substeps/step" % (
-        cells[0], cells[1], cells[2], args.iters, round(1.0 / dt), args.substeps)
+    mesh_name = "beam %dx%dx%d cells Kuhn-split" % cells
+    workload = "%s, NH Jacobi iters=%d, dt=1/%d, %d substeps/step" % (mesh_name, args.iters, round(1.0 / dt), args.substeps)
 
     # ------------------------------------------------------------------ reference arm (CPU only)
     if args.impl == "reference":
@@ -185,7 +282,11 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps,
                 "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64-expr/f32-store",
-                "data": "synthetic", "config": {"workload": workload, "tets": M, "verts": verts.size // 3},
+                "data": "synthetic",
+                "config": {"workload": "%s, NH sequential Gauss-Seidel in tet order (the reference's own algorithm, src/Softbody.js:206-208), "
+                                       "dt=1/%d, 1 substep/step" % (mesh_name, round(1.0 / dt)),
+                           "algorithm": "sequential Gauss-Seidel (reference); the GPU arm runs Jacobi on the same mesh -- see configs/jacobi_vs_gs in the GPU arm's line",
+                           "tets": M, "verts": verts.size // 3},
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
                                  "host_cores": os.cpu_count(), "dragon_substeps_per_s": cpu_dragon_substeps_per_s()},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -259,6 +360,40 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # ---- N > 1: the partitioned run against the same mesh on ONE GPU, outside every timed region ----
+    parity = None
+    if world > 1 and not args.no_parity:
+        frames = 2                                        # 40 substeps from the initial state
+        for _ in range(frames):
+            body.step(pp)
+        pos = torch.from_numpy(body.pos.copy()).cuda()    # caller order, NaN where not resident on this rank
+        res = torch.from_numpy(body.resident.astype(np.uint8)).cuda()
+        allpos = [torch.empty_like(pos) for _ in range(world)]
+        allres = [torch.empty_like(res) for _ in range(world)]
+        dist.all_gather(allpos, pos)
+        dist.all_gather(allres, res)
+        if rank == 0:
+            P = torch.stack(allpos).cpu().numpy().reshape(world, N, 3)
+            R = torch.stack(allres).cpu().numpy().astype(bool)
+            merged = np.zeros((N, 3), np.float32)
+            for r in range(world):
+                merged[R[r]] = P[r][R[r]]
+            shared = R.sum(axis=0) > 1
+            identical = all(np.array_equal(P[r][R[r] & shared].view(np.uint32), merged[R[r] & shared].view(np.uint32)) for r in range(world))
+            single = ts.SoftBody(verts, tets, None, pp, solver="jacobi", arithmetic="fast", iters=args.iters, cluster_size=args.cluster_size,
+                                 reorder=not args.no_reorder, deterministic=not args.atomic, device=local_rank, stream=stream.cuda_stream)
+            for _ in range(frames):
+                single.step(pp)
+            ref = single.pos.reshape(N, 3).astype(np.float64)
+            single.close()
+            err = float(np.max(np.linalg.norm(merged - ref, axis=1) / np.linalg.norm(ref, axis=1)))
+            parity = {"err": err, "replicas_bit_identical": bool(identical), "every_vertex_resident": bool(R.any(axis=0).all()),
+                      "shared_vertices": int(shared.sum()), "substeps": frames * args.substeps,
+                      "against": "the same mesh, kernels and options on 1 GPU (vector-relative position error; the only difference "
+                                 "is the summation order of the rank-shared vertices' partial sums)"}
+        del allpos, allres, pos, res
+        barrier()
+
     # ---- device-resident throughput ----
     for _ in range(args.warmup):
         body.step(pp)
@@ -282,51 +417,93 @@ def main():
     k_ms, k_bytes = body.time_kernel(50)
     peak, peak_src = load_peaks()
     achieved = k_bytes / (k_ms * 1e-3) / 1e9
-    traffic = None
+    kernel_key = "k_jacobi_tilesN<%d,2,2,%d>" % (args.cluster_size, 4 if args.cluster_size == 512 else 0)
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("k_jacobi_tiles_dram_bytes_per_launch") if world == 1 else None
+    if world == 1 and os.path.exists(tp) and tuple(cells) == (407, 64, 64):
+        try:   # one ncu --set full capture of this kernel on this mesh (a number taken under ncu is never a bench value)
+            ent = json.load(open(tp))["kernels"].get(kernel_key)
+            if ent:
+                traffic, traffic_src = ent["dram_bytes_per_launch"], ent["source"]
         except Exception:
             traffic = None
     roofline = {"kernel": "k_jacobi_tilesN<%d, 2 tets/thread> (persistent tile kernel, tetsim_b200/csrc/kernels_fast.cu)" % args.cluster_size, "bound": "hbm", "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": k_bytes, "ms_per_launch": k_ms,
                 "share_of_step": k_ms * args.iters * args.substeps / ms_step,
                 "tets_per_s_kernel_alone": info["localTets"] / (k_ms * 1e-3)}
 
-    # ---- end to end through the public API with host buffers ----
+    # ---- end to end through the C ABI with HOST buffers ----
+    # Per step: upload this step's inputs (positions + velocities of the vertices resident on this rank, from pinned host
+    # memory), solve the frame, download the resulting positions.  prevPos is NOT an input of simulate(): it is
+    # overwritten at src/Softbody.js:200 before anything reads it.  Two figures: `serial` waits for each frame's
+    # positions before the next upload starts; `value` (the headline) streams frames double-buffered -- the download of
+    # frame k (tetsim_get_positions_resident_async) overlaps the upload and solve of frame k+1, each step still moving
+    # its own inputs and outputs inside the timed region.
     e2e = None
     if not args.no_e2e:
-        res = body.resident
-        h_pos = torch.from_numpy(np.nan_to_num(body.pos.copy())).pin_memory()
-        h_prev = torch.from_numpy(np.nan_to_num(body.prevPos.copy())).pin_memory()
-        h_vel = torch.from_numpy(np.nan_to_num(body.vel.copy())).pin_memory()
-        h_out = torch.empty(3 * N, dtype=torch.float32).pin_memory()
-        lib, hnd = _capi.lib(), body._h
         import ctypes as C
+        ids = body.resident_ids
+        nloc = ids.size
+        own = ids >= 0
+        pos_r = np.nan_to_num(body.pos_resident)
+        vel_c = np.nan_to_num(body.vel).reshape(-1, 3)
+        vel_r = np.zeros((nloc, 3), np.float32)
+        vel_r[own] = vel_c[ids[own]]
+        h_pos = torch.from_numpy(pos_r).pin_memory()
+        h_vel = torch.from_numpy(vel_r.reshape(-1)).pin_memory()
+        h_out = [torch.empty(3 * nloc, dtype=torch.float32).pin_memory() for _ in range(2)]
+        lib, hnd = _capi.lib(), body._h
         prm = ts.softbody._params_struct(pp)
+        pp_, pv_ = C.c_void_p(h_pos.data_ptr()), C.c_void_p(h_vel.data_ptr())
+        po_ = [C.c_void_p(t.data_ptr()) for t in h_out]
 
-        def e2e_step():
-            _capi.check(lib.tetsim_set_state(hnd, C.c_void_p(h_pos.data_ptr()), C.c_void_p(h_prev.data_ptr()),
-                                             C.c_void_p(h_vel.data_ptr())))
+        def upload_and_step():
+            _capi.check(lib.tetsim_set_state_resident(hnd, pp_, None, pv_))
             _capi.check(lib.tetsim_step(hnd, FRAME_DT, args.substeps, C.byref(prm)))
-            _capi.check(lib.tetsim_get_positions(hnd, C.c_void_p(h_out.data_ptr())))
 
+        def serial_step():
+            upload_and_step()
+            _capi.check(lib.tetsim_get_positions_resident(hnd, po_[0]))
+
+        def streamed(n):
+            upload_and_step()
+            _capi.check(lib.tetsim_get_positions_resident_async(hnd, po_[0]))
+            for k in range(1, n):
+                upload_and_step()
+                _capi.check(lib.tetsim_wait_positions(hnd))          # frame k-1 is in host memory
+                _capi.check(lib.tetsim_get_positions_resident_async(hnd, po_[k & 1]))
+            _capi.check(lib.tetsim_wait_positions(hnd))
+
+        n_e2e = max(3, min(args.steps, 20))
         for _ in range(2):
-            e2e_step()
+            serial_step()
         barrier()
-        n_e2e = max(3, min(args.steps, 10))
         e0.record(stream)
         for _ in range(n_e2e):
-            e2e_step()
+            serial_step()
+        e1.record(stream)
+        barrier()
+        ms_serial = max_over_ranks(e0.elapsed_time(e1)) / n_e2e
+        streamed(3)
+        barrier()
+        e0.record(stream)
+        streamed(n_e2e)
         e1.record(stream)
         barrier()
         ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / n_e2e
+        assert np.isfinite(h_out[(n_e2e - 1) & 1].numpy()[np.repeat(own, 3)]).all()
+        tot = torch.tensor([float(nloc)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tot)
+        nres = int(tot.item())
         e2e = {"value": proj_per_step / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_e2e,
-               "h2d_bytes_per_step": 3 * 3 * N * 4, "d2h_bytes_per_step": 3 * N * 4, "steps": n_e2e,
-               "api": "tetsim_set_state(pos,prev,vel from pinned host) + tetsim_step + tetsim_get_positions(to pinned host)"}
-        del res
+               "h2d_bytes_per_step": 2 * 3 * nres * 4, "d2h_bytes_per_step": 3 * nres * 4, "steps": n_e2e,
+               "mode": "frames streamed double-buffered: the download of frame k overlaps the upload + solve of frame k+1",
+               "serial": {"value": proj_per_step / (ms_serial * 1e-3) / 1e6, "ms_per_step": ms_serial,
+                          "mode": "each frame's positions are in host memory before the next upload starts"},
+               "api": "tetsim_set_state_resident(pos, vel from pinned host; all ranks' resident vertices) + tetsim_step + "
+                      "tetsim_get_positions_resident[_async] (to pinned host)"}
 
     clocks = sampler.stop()   # sampled across the timed steps, the kernel-alone loop and the end-to-end steps
 
@@ -340,6 +517,11 @@ def main():
                          "src/Softbody.js, 1 thread (the sweep is inherently sequential; no JS engine in image)"
                          % (args.cpu_substeps, M, sec)}
 
+    configs = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        body.synchronize()
+        configs = config_rates(stream, local_rank)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -348,11 +530,16 @@ def main():
             "config": {"workload": workload, "tets": M, "verts": N, "iters": args.iters, "substeps_per_step": args.substeps,
                        "cluster_size": info["clusterSize"], "clusters_rank0": info["numClusters"],
                        "boundary_verts": info["boundaryVerts"], "boundary_tiles_rank0": info["boundaryTiles"], "deterministic": not args.atomic,
-                       "parallelism": ("tet-partition x%d (RCB), %s of boundary dx per iteration, overlapped with interior tiles" % (world, {"allreduce": "ncclAllReduce", "halo": "neighbour ncclSend/ncclRecv", "peer": "peer-memory stores (cudaIpc over NVLink, no NCCL)"}[args.exchange])) if world > 1 else "single GPU",
+                       "parallelism": ("tet-partition x%d (RCB), %s of boundary dx per iteration, overlapped with interior tiles" % (world, {"allreduce": "ncclAllReduce", "halo": "neighbour ncclSend/ncclRecv", "peer": "fused peer-memory exchange: the tile kernel stores its boundary partials into the sharers' buffers (cudaIpc over NVLink, no NCCL on the data path)"}[args.exchange])) if world > 1 else "single GPU",
+                       "exchange": args.exchange if world > 1 else None,
                        "l2": "working set per substep (%.0f MB) exceeds the 126 MB L2; no flush needed" % ((56.0 * M + 144.0 * N) / 1e6)},
             "scalar_constraints_per_s_M": 2 * value,
             "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
         }
+        if parity is not None:
+            line["parity"] = parity
+        if configs is not None:
+            line["configs"] = configs
         print(json.dumps(line))
     barrier()   # every rank idle before any rank frees its (possibly peer-mapped) buffers
     body.close()

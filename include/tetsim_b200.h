@@ -161,8 +161,24 @@ int tetsim_get_prev_positions(tetsim_t *h, float *out);
 int tetsim_get_velocities(tetsim_t *h, float *out);
 int tetsim_get_resident(tetsim_t *h, uint8_t *outNumVerts);
 /* Overwrite state (checkpoint / resume; also the per-frame upload of the end-to-end benchmark).
- * Any pointer may be NULL = leave unchanged. */
+ * Any pointer may be NULL = leave unchanged.  The copies are ENQUEUED (a dedicated copy stream into a double-buffered
+ * staging area, then one unpack kernel on the handle's stream): with pinned host memory the call returns at once and
+ * the arrays must stay unchanged until the next tetsim_synchronize / tetsim_get_* on the handle returns. */
 int tetsim_set_state(tetsim_t *h, const float *pos, const float *prevPos, const float *vel);
+/* Asynchronous form of tetsim_get_positions (SoftBodyGPU.readToCPU without the stall, src/SoftbodyGPU.js:649-653):
+ * the positions as of everything enqueued so far are packed and copied to `out` on a second copy stream;
+ * tetsim_wait_positions (or tetsim_synchronize) returns when `out` is complete.  What the caller enqueues in between --
+ * the next frame's tetsim_set_state / tetsim_step -- overlaps the download (PCIe is full duplex). */
+int tetsim_get_positions_async(tetsim_t *h, float *out);
+int tetsim_wait_positions(tetsim_t *h);
+/* Rank-local state access for multi-GPU hosts: the arrays hold ONLY the vertices resident on this rank, in the
+ * handle's own order -- tetsim_get_resident_ids lists the caller's vertex id of each (TetSimInfo.localVerts entries,
+ * -1 = a replica this rank does not maintain: written as NaN, ignored on upload).  Each rank moves 1/worldSize of the
+ * state instead of all of it.  Valid on single-GPU handles too (localVerts = numVerts, the solver's internal order). */
+int tetsim_get_resident_ids(tetsim_t *h, int32_t *outLocalVerts);
+int tetsim_set_state_resident(tetsim_t *h, const float *pos, const float *prevPos, const float *vel);
+int tetsim_get_positions_resident(tetsim_t *h, float *out);
+int tetsim_get_positions_resident_async(tetsim_t *h, float *out);
 /* .invRestPose (9 per tet, column-major) .invRestVolume .invMass of initPhysics, src/Softbody.js:60-87.
  * Any pointer may be NULL. */
 int tetsim_get_rest(tetsim_t *h, float *invRestPose, float *invRestVolume, float *invMass);
@@ -176,6 +192,12 @@ int tetsim_get_polar_state(tetsim_t *h, float *rest12, float *quat4);
  * startGrab picks the nearest vertex on the device (first strict minimum of the f64 squared
  * distance, like the reference loop) and returns its index through outGrabId (may be NULL). */
 int tetsim_start_grab(tetsim_t *h, const double p[3], int32_t *outGrabId);
+/* The two halves of startGrab for multi-GPU hosts (tetsim_start_grab fails with TETSIM_E_STATE there: a rank sees only
+ * its own vertices).  tetsim_nearest_vertex searches the vertices this rank maintains and returns the caller's id and
+ * the f64 squared distance (id -1 / +inf when none); the host takes the minimum over ranks (ties: smallest id) and
+ * passes the winner to tetsim_set_grab on EVERY rank, so replicas of a shared vertex are pinned consistently. */
+int tetsim_nearest_vertex(tetsim_t *h, const double p[3], int32_t *outId, double *outD2);
+int tetsim_set_grab(tetsim_t *h, int32_t grabId, const double p[3]);
 int tetsim_move_grabbed(tetsim_t *h, const double p[3]);
 int tetsim_end_grab(tetsim_t *h);
 

@@ -25,15 +25,9 @@ def test_partitioned_jacobi_matches_single_gpu(world, exchange):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
 
 
-# TETSIM_TEST_PEER_V2="1 2 4 8 16 31" additionally runs the fused cases under those experiment masks (TETSIM_PEER_V2,
-# launch.h kPeerV2*); by default only the measured protocol (mask 0) is exercised.
-_V2_MASKS = [0] + [int(v) for v in os.environ.get("TETSIM_TEST_PEER_V2", "").split() if int(v) != 0]
-
-
-@pytest.mark.parametrize("v2", _V2_MASKS)
 @pytest.mark.parametrize("world,deterministic,fused", [(2, True, True), (3, True, True), (4, True, True), (2, True, False),
                                                        (2, False, False)])
-def test_peer_exchange_single_process(world, deterministic, fused, v2, monkeypatch):
+def test_peer_exchange_single_process(world, deterministic, fused, monkeypatch):
     """The peer-memory exchange protocol (push into the sharers' buffers + epoch flags, wait + rank-ordered reduce)
     driven on ONE GPU: `world` handles of this process, each owning one tet partition, are each other's peers (the
     blob carries the owner's pointer, so no cudaIpc mapping is involved).  Merged positions must agree with the
@@ -46,9 +40,6 @@ def test_peer_exchange_single_process(world, deterministic, fused, v2, monkeypat
     # fused: the tile kernel pushes and the vertex kernel waits + reduces (2 launches per iteration, the default with the
     # deterministic flush); unfused: boundary tiles / push / interior tiles / wait + reduce / vertex kernel
     monkeypatch.setenv("TETSIM_PEER_UNFUSED", "0" if fused else "1")
-    if v2 and not fused:
-        pytest.skip("experiment masks only touch the fused form")
-    monkeypatch.setenv("TETSIM_PEER_V2", str(v2))
     v, t = mesh.make_beam((48, 10, 10), h=0.02, y0=0.004, jitter=0.15)   # reaches the floor within the 60 substeps
     N = v.size // 3
     pp = dict(ts.DEFAULT_PHYSICS_PARAMS, numSubsteps=20, worldBounds=list(mesh.wide_bounds(16.0)))

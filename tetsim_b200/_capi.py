@@ -30,6 +30,8 @@ SYMBOLS = [
     "tetsim_get_polar_state", "tetsim_start_grab", "tetsim_move_grabbed", "tetsim_end_grab", "tetsim_skin",
     "tetsim_get_info", "tetsim_time_kernel", "tetsim_nccl_unique_id", "tetsim_get_ipc_handle", "tetsim_set_peers",
     "tetsim_level_schedule", "tetsim_greedy_colors", "tetsim_plan_partition", "tetsim_plan_halo",
+    "tetsim_get_positions_async", "tetsim_wait_positions", "tetsim_get_resident_ids", "tetsim_set_state_resident",
+    "tetsim_get_positions_resident", "tetsim_get_positions_resident_async", "tetsim_nearest_vertex", "tetsim_set_grab",
 ]
 
 
@@ -116,6 +118,13 @@ def lib() -> C.CDLL:
     for name in ("tetsim_get_positions", "tetsim_get_prev_positions", "tetsim_get_velocities"):
         getattr(L, name).argtypes = [vp, vp]
     L.tetsim_get_resident.argtypes = [vp, vp]
+    for name in ("tetsim_get_positions_async", "tetsim_get_positions_resident", "tetsim_get_positions_resident_async",
+                 "tetsim_get_resident_ids"):
+        getattr(L, name).argtypes = [vp, vp]
+    L.tetsim_wait_positions.argtypes = [vp]
+    L.tetsim_set_state_resident.argtypes = [vp, vp, vp, vp]
+    L.tetsim_nearest_vertex.argtypes = [vp, dblp, i32p, dblp]
+    L.tetsim_set_grab.argtypes = [vp, C.c_int32, dblp]
     L.tetsim_set_state.argtypes = [vp, vp, vp, vp]
     L.tetsim_get_rest.argtypes = [vp, vp, vp, vp]
     L.tetsim_get_vol_error.argtypes = [vp, dblp]

@@ -142,17 +142,6 @@ __device__ __forceinline__ uint4 ld_volatile_u4(const void *p) {
     asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
-// sender: one tile partial (px, py, pz) of boundary vertex b, partial index i of n, into every sharer's buffer
-__device__ __forceinline__ void peer_push_partial(const PeerArgs &a, int b, int i, int n, unsigned e, float px, float py, float pz) {
-    const unsigned tag = (e & 0x0fffffffu) * (unsigned)kPeerK + (unsigned)(n - 1);  // 28-bit epoch, count - 1
-    for (int j = a.pxStart[b]; j < a.pxStart[b + 1]; j++) {
-        const int q = a.pxPeer[j];
-        unsigned char *dst = a.peerBase[q] + kPeerRecvOff +
-                             (((size_t)(e & 1u) * a.remoteTotal[q] + a.pxEntry[j]) * kPeerK + i) * 32;
-        st_volatile_u4(dst, __float_as_uint(px), tag, __float_as_uint(py), tag);
-        st_volatile_u4(dst + 16, __float_as_uint(pz), tag, 0u, tag);
-    }
-}
 // receiver: the partials one sharer delivered for receive entry E, added in the sharer's order.  Spins until the
 // entries carry this epoch's tag; after a timeout the sticky error flag is set and whatever is there is used.
 __device__ __forceinline__ float4 peer_poll_entry(const PeerArgs &a, unsigned *ctl, int E, unsigned e) {
@@ -264,10 +253,9 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
 
     const SubstepParams *sp = a.sp;
     const float alphaDev = sp->alphaDev, alphaVol = sp->alphaVol, gammaVol = sp->gammaVol;
-    // kPeerV2PushRecords: the epoch does not change while this kernel runs -- read it (and the record table) once
-    const bool pushByRecord = PEER && (a.pxFlags & kPeerV2PushRecords);
-    const uint4 *pushRec = pushByRecord ? a.px->pushRec : nullptr;
-    const unsigned pushEpoch = pushByRecord ? *reinterpret_cast<volatile unsigned *>(a.px->self + kPeerCtlOff) + 1u : 0u;
+    // fused peer push: the epoch does not change while this kernel runs (its last CTA advances it) -- read it once
+    const uint4 *pushRec = PEER ? a.px->pushRec : nullptr;
+    const unsigned pushEpoch = PEER ? *reinterpret_cast<volatile unsigned *>(a.px->self + kPeerCtlOff) + 1u : 0u;
 
     auto issue_meta = [&](uint32_t o, uint32_t end, int slot) {  // one thread; block = [16*o, 16*end)
         const uint32_t bytes = (end - o) * 16u;
@@ -420,50 +408,43 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
                 else a.part[v0 + j] = make_float4(ax, ay, az, 0.0f);
                 if (PEER) {  // multi-GPU, fused exchange: a rank-shared vertex's tile partial goes straight to the sharers
                     const int slot = v0 + j;
-                    if (a.pxFlags & kPeerV2PushRecords) {
-                        if (slot < a.pxSlots) {
-                            const uint4 r0 = __ldg(pushRec + 2 * slot), r1 = __ldg(pushRec + 2 * slot + 1);
-                            if (r0.x != 0xffffffffu) {
-                                const unsigned i = r0.x & 0xffu, n1 = (r0.x >> 8) & 0xffu, sharers = r0.x >> 16;
-                                const unsigned tag = (pushEpoch & 0x0fffffffu) * (unsigned)kPeerK + n1;
-                                const unsigned long long p0 = ((unsigned long long)r0.w << 32) | r0.z, p1 = ((unsigned long long)r1.w << 32) | r1.z;
-                                unsigned char *d0 = reinterpret_cast<unsigned char *>(p0) + (size_t)(pushEpoch & 1u) * r1.x * 32;
-                                st_volatile_u4(d0, __float_as_uint(ax), tag, __float_as_uint(ay), tag);
-                                st_volatile_u4(d0 + 16, __float_as_uint(az), tag, 0u, tag);
-                                if (sharers > 1) {
-                                    unsigned char *d1 = reinterpret_cast<unsigned char *>(p1) + (size_t)(pushEpoch & 1u) * r1.y * 32;
-                                    st_volatile_u4(d1, __float_as_uint(ax), tag, __float_as_uint(ay), tag);
-                                    st_volatile_u4(d1 + 16, __float_as_uint(az), tag, 0u, tag);
-                                }
-                                if (sharers > 2) {  // a vertex on a corner of the partition: the remaining sharers from the CSR
-                                    const PeerArgs &px = *a.px;
-                                    const int b = (int)r0.y;
-                                    for (int t = px.pxStart[b] + 2; t < px.pxStart[b + 1]; t++) {
-                                        const int q = px.pxPeer[t];
-                                        unsigned char *dst = px.peerBase[q] + kPeerRecvOff +
-                                                             (((size_t)(pushEpoch & 1u) * px.remoteTotal[q] + px.pxEntry[t]) * kPeerK + i) * 32;
-                                        st_volatile_u4(dst, __float_as_uint(ax), tag, __float_as_uint(ay), tag);
-                                        st_volatile_u4(dst + 16, __float_as_uint(az), tag, 0u, tag);
-                                    }
-                                }
+                    if (slot < a.pxSlots) {  // boundary tiles come first, so do their partial slots
+                        // ONE 32-byte record per pushing slot (two parallel 16-byte loads, addresses precomputed at
+                        // tetsim_set_peers): a dependent chain slot -> CSR -> peer table -> base cost ~3 us in the first
+                        // tile of every CTA that owns boundary tiles (measured, profiles/r2_peer_experiments.txt)
+                        const uint4 r0 = __ldg(pushRec + 2 * slot), r1 = __ldg(pushRec + 2 * slot + 1);
+                        if (r0.x != 0xffffffffu) {
+                            const unsigned i = r0.x & 0xffu, n1 = (r0.x >> 8) & 0xffu, sharers = r0.x >> 16;
+                            const unsigned tag = (pushEpoch & 0x0fffffffu) * (unsigned)kPeerK + n1;
+                            const unsigned long long p0 = ((unsigned long long)r0.w << 32) | r0.z, p1 = ((unsigned long long)r1.w << 32) | r1.z;
+                            unsigned char *d0 = reinterpret_cast<unsigned char *>(p0) + (size_t)(pushEpoch & 1u) * r1.x * 32;
+                            st_volatile_u4(d0, __float_as_uint(ax), tag, __float_as_uint(ay), tag);
+                            st_volatile_u4(d0 + 16, __float_as_uint(az), tag, 0u, tag);
+                            if (sharers > 1) {
+                                unsigned char *d1 = reinterpret_cast<unsigned char *>(p1) + (size_t)(pushEpoch & 1u) * r1.y * 32;
+                                st_volatile_u4(d1, __float_as_uint(ax), tag, __float_as_uint(ay), tag);
+                                st_volatile_u4(d1 + 16, __float_as_uint(az), tag, 0u, tag);
                             }
-                        }
-                    } else {
-                        const PeerArgs &px = *a.px;
-                        if (slot < ((a.pxFlags & kPeerV2SlotsByValue) ? a.pxSlots : px.numBoundarySlots)) {
-                            const unsigned i = px.slotIdx[slot];
-                            if (i != 0xffu) {
-                                const int id = reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3])[j];
-                                const unsigned e = *reinterpret_cast<volatile unsigned *>(px.self + kPeerCtlOff) + 1u;  // advanced by the vertex kernel
-                                peer_push_partial(px, id - px.boundaryBegin, (int)i, px.vpStart[id + 1] - px.vpStart[id], e, ax, ay, az);
+                            if (sharers > 2) {  // a vertex on a corner of the partition: the remaining sharers from the CSR
+                                const PeerArgs &px = *a.px;
+                                const int b = (int)r0.y;
+                                for (int t = px.pxStart[b] + 2; t < px.pxStart[b + 1]; t++) {
+                                    const int q = px.pxPeer[t];
+                                    unsigned char *dst = px.peerBase[q] + kPeerRecvOff +
+                                                         (((size_t)(pushEpoch & 1u) * px.remoteTotal[q] + px.pxEntry[t]) * kPeerK + i) * 32;
+                                    st_volatile_u4(dst, __float_as_uint(ax), tag, __float_as_uint(ay), tag);
+                                    st_volatile_u4(dst + 16, __float_as_uint(az), tag, 0u, tag);
+                                }
                             }
                         }
                     }
                 }
             }
     }
-    if (PEER && !WARP_SCOPE && (a.pxFlags & kPeerV2TileAdvances)) {
-        // every push of this CTA is issued (and has read the epoch): take a ticket, the last CTA advances the epoch
+    if (PEER && !WARP_SCOPE) {
+        // every push of this CTA is issued (and used the epoch read above): take a ticket, the last CTA advances the
+        // epoch.  (The vertex kernel used to do this with one same-address atomic per block -- 3,400 per launch at two
+        // ranks; moving it here was worth 9 % of the substep, profiles/r2_peer_experiments.txt.)
         __syncthreads();
         if (tid == 0) {
             unsigned *ctl = reinterpret_cast<unsigned *>(a.px->self + kPeerCtlOff);
@@ -581,13 +562,6 @@ static void launch_tilesN(cudaStream_t s, const TileArgs &a) {
     }
     int grid = lc.sms * lc.n;
     if (grid > a.numTiles - a.tileBegin) grid = a.numTiles - a.tileBegin;
-    // experiment (round 2, multi-GPU ranks with few tiles per CTA): shrink the grid so every CTA walks the same number
-    // of tiles (2442 tiles on 592 CTAs = 4 or 5 each -> 489 CTAs x 5) instead of leaving most CTAs idle in the last round
-    static const bool balance = [] { const char *e = getenv("TETSIM_TILE_BALANCE"); return e && e[0] == '1'; }();
-    if (balance && grid > 0) {
-        const int tiles = a.numTiles - a.tileBegin, rounds = (tiles + grid - 1) / grid;
-        grid = (tiles + rounds - 1) / rounds;
-    }
     k_jacobi_tilesN<T, TPT, S, MINB, PEER><<<grid, T / TPT, smem, s>>>(a);
 }
 
@@ -700,24 +674,14 @@ void launch_build_tiles(cudaStream_t s, int clusterSize, int numRecords, const i
 // Vertex side of the clustered Jacobi: x += (sum of the vertex's tile partials) / valence, optionally
 // fused with post (simulate() :213-239) and with the NEXT substep's predict (:198-202) so a substep
 // inside tetsim_step costs exactly two launches.
-template <int MODE, bool PEER, bool INLINE = false, bool LB8 = false>
-__global__ void __launch_bounds__(256, LB8 ? 8 : 1) k_jacobi_apply(int begin, int end, ApplyArgs a) {
-    const unsigned blk = (PEER && (a.pxFlags & kPeerV2ReverseBlocks)) ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+template <int MODE, bool PEER>
+__global__ void __launch_bounds__(256) k_jacobi_apply(int begin, int end, ApplyArgs a) {
+    // fused peer exchange: the rank-shared vertices are the LAST of the handle's numbering, and they may have to wait for
+    // a sharer's entries -- their blocks are scheduled first so that the wait overlaps the interior vertices' work
+    const unsigned blk = PEER ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
     int i = begin + blk * blockDim.x + threadIdx.x;
     unsigned epoch = 0u;
-    if (PEER) {  // fused peer exchange
-        unsigned *ctl = reinterpret_cast<unsigned *>(a.px->self + kPeerCtlOff);
-        if (a.pxFlags & kPeerV2TileAdvances) {
-            epoch = *reinterpret_cast<volatile unsigned *>(ctl);  // already advanced by the tile kernel's last CTA
-        } else {  // this launch consumes epoch ctl[0] + 1; the last block to pass here advances it
-            epoch = *reinterpret_cast<volatile unsigned *>(ctl) + 1u;
-            __syncthreads();  // every thread of the block has read the epoch before the block's ticket
-            if (threadIdx.x == 0 && atomicAdd(ctl + 1, 1u) == gridDim.x - 1) {
-                ctl[1] = 0u;
-                *reinterpret_cast<volatile unsigned *>(ctl) = epoch;
-            }
-        }
-    }
+    if (PEER) epoch = *reinterpret_cast<volatile unsigned *>(a.px->self + kPeerCtlOff);  // advanced by the tile kernel's last CTA
     if (i >= end) return;
     float sx = 0.0f, sy = 0.0f, sz = 0.0f;
     if (PEER && i >= a.boundaryBegin) {
@@ -746,24 +710,6 @@ __global__ void __launch_bounds__(256, LB8 ? 8 : 1) k_jacobi_apply(int begin, in
         float4 s = a.acc[i];
         a.acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         sx = s.x; sy = s.y; sz = s.z;
-    } else if (INLINE) {
-        // experiment: the vertex's partial slots come in one 16-byte record, so the dependent chain is
-        // record -> partials (two levels) instead of vpStart -> vpSlot -> partials (three); same summation order
-        const uint4 r = __ldg(a.vpInline + i);
-        if (r.w == 0xfffffffeu) {
-            for (int j = a.vpStart[i]; j < a.vpStart[i + 1]; j++) {
-                float4 s = ldg4(a.part + a.vpSlot[j]);
-                sx += s.x; sy += s.y; sz += s.z;
-            }
-        } else {
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 s0 = r.x != 0xffffffffu ? ldg4(a.part + r.x) : z, s1 = r.y != 0xffffffffu ? ldg4(a.part + r.y) : z;
-            const float4 s2 = r.z != 0xffffffffu ? ldg4(a.part + r.z) : z, s3 = r.w != 0xffffffffu ? ldg4(a.part + r.w) : z;
-            sx = 0.0f + s0.x; sy = 0.0f + s0.y; sz = 0.0f + s0.z;
-            if (r.y != 0xffffffffu) { sx += s1.x; sy += s1.y; sz += s1.z; }
-            if (r.z != 0xffffffffu) { sx += s2.x; sy += s2.y; sz += s2.z; }
-            if (r.w != 0xffffffffu) { sx += s3.x; sy += s3.y; sz += s3.z; }
-        }
     } else {
         for (int j = a.vpStart[i]; j < a.vpStart[i + 1]; j++) {
             float4 s = ldg4(a.part + a.vpSlot[j]);
@@ -798,22 +744,10 @@ void launch_jacobi_apply(cudaStream_t s, int begin, int end, int mode, const App
     int n = end - begin;
     if (n <= 0) return;
     const int TB = 256;
-    if (a.px && (a.pxFlags & kPeerV2Apply32Regs)) {  // experiment: the same kernel capped at 32 registers
-        if (mode == 0) k_jacobi_apply<0, true, false, true><<<cdiv(n, TB), TB, 0, s>>>(begin, end, a);
-        else if (mode == 1) k_jacobi_apply<1, true, false, true><<<cdiv(n, TB), TB, 0, s>>>(begin, end, a);
-        else k_jacobi_apply<2, true, false, true><<<cdiv(n, TB), TB, 0, s>>>(begin, end, a);
-        return;
-    }
     if (a.px) {  // multi-GPU, fused peer exchange: poll + rank-ordered reduce for the rank-shared vertices
         if (mode == 0) k_jacobi_apply<0, true><<<cdiv(n, TB), TB, 0, s>>>(begin, end, a);
         else if (mode == 1) k_jacobi_apply<1, true><<<cdiv(n, TB), TB, 0, s>>>(begin, end, a);
         else k_jacobi_apply<2, true><<<cdiv(n, TB), TB, 0, s>>>(begin, end, a);
-        return;
-    }
-    if (a.vpInline && !a.acc) {  // experiment, single-GPU deterministic flush only
-        if (mode == 0) k_jacobi_apply<0, false, true><<<cdiv(n, TB), TB, 0, s>>>(begin, end, a);
-        else if (mode == 1) k_jacobi_apply<1, false, true><<<cdiv(n, TB), TB, 0, s>>>(begin, end, a);
-        else k_jacobi_apply<2, false, true><<<cdiv(n, TB), TB, 0, s>>>(begin, end, a);
         return;
     }
     if (mode == 0) k_jacobi_apply<0, false><<<cdiv(n, TB), TB, 0, s>>>(begin, end, a);
@@ -938,6 +872,22 @@ __global__ void k_unpack3(int N, const float *__restrict__ src, const int *__res
 void launch_unpack3(cudaStream_t s, int N, const float *src3, const int *perm, float4 *dst, int keepW) {
     if (N > 0) k_unpack3<<<cdiv(N, 256), 256, 0, s>>>(N, src3, perm, dst, keepW);
 }
+// tetsim_set_state: the arrays the caller passed (mask bit 0 pos, 1 prevPos, 2 vel) sit in ONE staging buffer, array k at
+// stage + k * stride; one launch unpacks them all into the 16-byte records (pos keeps its invMass lane).
+__global__ void k_unpack_state(int N, size_t stride, const float *__restrict__ stage, const int *__restrict__ perm,
+                               float4 *__restrict__ x4, float4 *__restrict__ prev4, float4 *__restrict__ vel4, int mask) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    if (perm && perm[i] < 0) return;  // replica this rank does not maintain
+    const size_t o = 3 * (size_t)(perm ? perm[i] : i);
+    if (mask & 1) { const float *p = stage + o; x4[i] = make_float4(p[0], p[1], p[2], x4[i].w); }
+    if (mask & 2) { const float *p = stage + stride + o; prev4[i] = make_float4(p[0], p[1], p[2], 0.0f); }
+    if (mask & 4) { const float *p = stage + 2 * stride + o; vel4[i] = make_float4(p[0], p[1], p[2], 0.0f); }
+}
+void launch_unpack_state(cudaStream_t s, int N, size_t stride, const float *stage, const int *perm, float4 *x4,
+                         float4 *prev4, float4 *vel4, int mask) {
+    if (N > 0 && mask) k_unpack_state<<<cdiv(N, 256), 256, 0, s>>>(N, stride, stage, perm, x4, prev4, vel4, mask);
+}
 
 // volError = (sequential f64 sum of the per-tet terms in tet order) / M  (src/Softbody.js:206-209)
 __global__ void k_sum_sequential(int M, const double *__restrict__ terms, double *__restrict__ out) {
@@ -956,10 +906,11 @@ __device__ __forceinline__ double grab_d2(float4 x, const double *p) {
     double a0 = __dsub_rn(p[0], (double)x.x), a1 = __dsub_rn(p[1], (double)x.y), a2 = __dsub_rn(p[2], (double)x.z);
     return __dadd_rn(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)), __dmul_rn(a2, a2));
 }
-__global__ void k_nearest_pass1(int N, const float4 *__restrict__ x4, const double *__restrict__ p,
-                                unsigned long long *__restrict__ best) {
+__global__ void k_nearest_pass1(int N, const float4 *__restrict__ x4, const int *__restrict__ vertId,
+                                const double *__restrict__ p, unsigned long long *__restrict__ best) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
+    if (vertId && vertId[i] < 0) return;  // replica this rank does not maintain
     double d2 = grab_d2(x4[i], p);
     if (d2 < 1.7976931348623157e308) atomicMin(best, (unsigned long long)__double_as_longlong(d2));
 }
@@ -968,6 +919,7 @@ __global__ void k_nearest_pass2(int N, const float4 *__restrict__ x4, const int 
                                 int *__restrict__ outId) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
+    if (vertId && vertId[i] < 0) return;
     double d2 = grab_d2(x4[i], p);
     if (d2 < 1.7976931348623157e308 && (unsigned long long)__double_as_longlong(d2) == *best)
         atomicMin(outId, vertId ? vertId[i] : i);
@@ -977,7 +929,7 @@ void launch_nearest_vertex(cudaStream_t s, int N, const float4 *x4, const int *v
     cudaMemsetAsync(scratch, 0xff, sizeof(unsigned long long), s);
     cudaMemsetAsync(outId, 0x7f, sizeof(int), s);  // 0x7f7f7f7f: larger than any vertex id
     if (N <= 0) return;
-    k_nearest_pass1<<<cdiv(N, 256), 256, 0, s>>>(N, x4, p3, scratch);
+    k_nearest_pass1<<<cdiv(N, 256), 256, 0, s>>>(N, x4, vertId, p3, scratch);
     k_nearest_pass2<<<cdiv(N, 256), 256, 0, s>>>(N, x4, vertId, p3, scratch, outId);
 }
 

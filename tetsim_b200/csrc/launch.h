@@ -65,7 +65,7 @@ struct TileArgs {
     int staggerNs;                  // initial delay per resident-CTA slot (breaks phase lockstep of co-resident CTAs)
     int debugSkip;                  // measurement only (tetsim_time_kernel + TETSIM_TILE_DEBUG): 1 no vertex phase, 2 no math, 4 no gather
     const PeerArgs *px;             // DEVICE copy of the peer-exchange arguments: fused push of the boundary sums, or NULL
-    int pxSlots, pxFlags;           // fused push experiments (TETSIM_PEER_V2 bit mask, see kPeerV2*): slot bound by value
+    int pxSlots;                    // fused push: partial slots [0, pxSlots) belong to boundary tiles (by value: no load on the way)
 };
 void launch_jacobi_tiles(cudaStream_t, int clusterSize, const TileArgs &a);
 bool jacobi_tiles_has_peer_push(int clusterSize);  // can this tile size (and the TETSIM_TILE_* overrides in force) push?
@@ -77,14 +77,11 @@ void launch_build_tiles(cudaStream_t, int clusterSize, int numRecords, const int
 struct ApplyArgs {
     float4 *x4, *prev4, *vel4;
     const int *vpStart, *vpSlot;    // vertex -> partial-sum slots (CSR into part[])
-    const uint4 *vpInline;          // experiment (TETSIM_APPLY_INLINE=1): up to 4 slots per vertex in ONE 16-byte record
-                                    // (0xffffffff = none; .w = 0xfffffffe = more than 4, use the CSR), or NULL
     const float4 *part;
     float4 *acc;                    // atomic-flush accumulator (read and re-zeroed) or NULL
     const float *invVal;            // 1 / valence
     const float4 *bsum;             // all-reduced boundary sums for vertices >= boundaryBegin, or NULL
     const PeerArgs *px;             // DEVICE copy: wait for the sharers' flags and reduce in rank order here (fused), or NULL
-    int pxFlags;                    // TETSIM_PEER_V2 bit mask (kPeerV2*)
     int boundaryBegin;
     const SubstepParams *sp;
     const int *vertId;              // handle-local -> caller's vertex id (for the grab test)
@@ -123,9 +120,7 @@ struct PeerArgs {
     int selfTotal;                        // parity stride of my receive buffer
     const int *srcStart, *src;            // reduce sources (ClusterPlan hxSrcStart / hxSrc)
     unsigned long long timeoutNs;         // give up waiting after this long (sets ctl[2])
-    const unsigned char *slotIdx;         // fused push: [numBoundarySlots] partial index of a boundary-tile slot, 0xff = not shared
-    int numBoundarySlots;
-    // kPeerV2PushRecords: everything a push needs in ONE 32-byte record per boundary-tile slot (two parallel 16-byte loads):
+    // fused push: everything a push needs in ONE 32-byte record per boundary-tile partial slot (two parallel 16-byte loads):
     //   rec[2 s]     = {i | (count - 1) << 8 | sharers << 16 (or ~0: not shared), boundary id, address of sharer 0's entry (lo, hi)}
     //   rec[2 s + 1] = {parity stride of sharer 0, of sharer 1 (units of 32 B), address of sharer 1's entry (lo, hi)}
     // entry addresses are those of the parity-0 half; a third and further sharer (partition corners) come from the CSR.
@@ -138,17 +133,13 @@ struct PeerArgs {
 // (every 8-byte half carries the tag, the granularity NVLink stores are not torn at -- the scheme of NCCL's LL
 // protocol), slot (entry * kPeerK + partial index) of the parity half of the buffer.  Boundary tiles run first, so the
 // partials cross NVLink while the interior tiles are still being solved, inside ONE launch and without fences, flags
-// or tickets.  The vertex kernel (k_jacobi_apply) polls the entries of its rank-shared vertices until their tags show
-// the current epoch, adds each sharer's partials in that sharer's own order and the sharers' sums in ascending rank
-// order (so every sharer computes the identical value), and the last vertex block advances the epoch: 2 launches per
-// iteration, as on a single GPU.
-// Round-2 experiments on the fused form, off by default (TETSIM_PEER_V2 = bit mask), one per suspected source of the
-// ~20 us/substep it still costs at 2 GPUs:
-constexpr int kPeerV2SlotsByValue = 1;    // tile kernel: "is this a boundary-tile slot" from a kernel parameter, not through px->
-constexpr int kPeerV2TileAdvances = 2;    // the tile kernel's CTAs (not the vertex kernel's blocks) advance the epoch
-constexpr int kPeerV2ReverseBlocks = 4;   // vertex kernel: blocks holding the rank-shared vertices are scheduled first
-constexpr int kPeerV2PushRecords = 8;     // tile kernel: one 32-byte record per push + epoch read once per CTA (one dependent load level, not four)
-constexpr int kPeerV2Apply32Regs = 16;    // vertex kernel capped at 32 registers (8 blocks per SM like the single-GPU kernel)
+// or tickets.
+// The last CTA of the tile kernel advances the epoch (ticket in ctl[1]); the vertex kernel reads it, schedules the blocks
+// holding the rank-shared vertices FIRST, polls their entries, adds each sharer's partials in that sharer's own order and
+// the sharers' sums in ascending rank order (so every sharer computes the identical value): 2 launches per iteration, as
+// on a single GPU.  Measured at 2 ranks on the 10M-tet beam (profiles/r2_peer_experiments.txt): epoch advanced by the
+// vertex kernel's 3,400 blocks 85.9 G tet/s -> by the tile kernel's 592 CTAs 94.0; boundary blocks first 90.1; both +
+// one-record pushes 99.1 (NCCL all-reduce 95.1, NCCL neighbour exchange 87.3).
 constexpr int kPeerK = 16;                // most tile partials a rank may hold for one shared vertex (checked at create)
 void launch_peer_push(cudaStream_t, const PeerArgs &a);
 void launch_peer_reduce(cudaStream_t, const PeerArgs &a);
@@ -156,6 +147,9 @@ void launch_peer_reduce(cudaStream_t, const PeerArgs &a);
 // ---- utility kernels (kernels_fast.cu) ----
 void launch_pack3(cudaStream_t, int N, const float4 *src, const int *perm, float *dst3);       // dst[perm[i]] = src[i].xyz
 void launch_unpack3(cudaStream_t, int N, const float *src3, const int *perm, float4 *dst, int keepW);
+// array k (0 pos, 1 prevPos, 2 vel; mask bit k = present) at stage + k * stride -> the 16-byte state records, one launch
+void launch_unpack_state(cudaStream_t, int N, size_t stride, const float *stage, const int *perm, float4 *x4,
+                         float4 *prev4, float4 *vel4, int mask);
 void launch_sum_sequential(cudaStream_t, int M, const double *terms, double *out);             // out = (sum in index order) / M
 void launch_nearest_vertex(cudaStream_t, int N, const float4 *x4, const int *vertId, const double *p3, int *outId,
                            unsigned long long *scratch);

@@ -146,7 +146,6 @@ struct tetsim {
     // Jacobi cluster path
     ClusterPlan plan;
     DevBuf<int> vpStart, vpSlot;
-    DevBuf<uint4> vpInline;               // experiment TETSIM_APPLY_INLINE=1 (ApplyArgs::vpInline)
     DevBuf<unsigned char> tileTets, tileMeta;
     DevBuf<uint32_t> metaOff;
     DevBuf<float4> part, acc, bsum;
@@ -157,7 +156,15 @@ struct tetsim {
     DevBuf<int> tStart, tEnt;
     // per-launch parameters, staging, grab
     DevBuf<SubstepParams> sp;
-    DevBuf<float> stage3;
+    // host <-> device state transfer.  Two copy streams (one per DMA direction) beside the compute stream and two staging
+    // buffers per direction: an upload never waits for the previous download (PCIe is full duplex), the three arrays of
+    // one tetsim_set_state go out back to back and ONE kernel unpacks them, and a download started with
+    // tetsim_get_positions_async overlaps whatever the caller enqueues next.
+    cudaStream_t h2dStream = nullptr, d2hStream = nullptr;
+    DevBuf<float> stageIn[2], stageOut[2];
+    cudaEvent_t evIn[2] = {nullptr, nullptr}, evInFree[2] = {nullptr, nullptr}, evPacked[2] = {nullptr, nullptr}, evOut[2] = {nullptr, nullptr};
+    unsigned inSeq = 0, outSeq = 0;
+    int pendingOut = -1;                    // staging slot of the download started last (tetsim_wait_positions)
     DevBuf<double> grabP;
     DevBuf<int> grabOut;
     DevBuf<unsigned long long> grabScratch;
@@ -188,11 +195,9 @@ struct tetsim {
     std::vector<void *> peerOpened;         // bases returned by cudaIpcOpenMemHandle (closed at destroy)
     DevBuf<unsigned char *> peerBase;       // [peers] mapped exchange allocation of each sharer
     DevBuf<int> pxStart, pxPeer, pxEntry, pxRemoteTotal, pxRemoteSlot;
-    DevBuf<unsigned char> pxSlotIdx;        // fused push: partial index of every boundary-tile partial slot
-    DevBuf<uint4> pushRec;                  // kPeerV2PushRecords: two uint4 per boundary-tile partial slot (PeerArgs::pushRec)
+    DevBuf<uint4> pushRec;                  // fused push: two uint4 per boundary-tile partial slot (PeerArgs::pushRec)
     DevBuf<PeerArgs> pxArgs;                // device copy of peer_args(h), read by the tile and vertex kernels
     bool peerFused = false;                 // the tile kernel pushes, the vertex kernel polls + reduces (2 launches/iteration)
-    int peerV2 = 0;                         // TETSIM_PEER_V2 experiment mask (kPeerV2*), read at create
     // TETSIM_TRACE=1: in-situ per-launch timing of the clustered Jacobi substep (events between launches, no graph);
     // the way to see where a multi-GPU substep spends its time, where ncu cannot be used
     bool trace = false;
@@ -206,7 +211,7 @@ struct tetsim {
                          volTerm.bytes() + dx.bytes() + vpStart.bytes() + vpSlot.bytes() + tileTets.bytes() +
                          tileMeta.bytes() + metaOff.bytes() + part.bytes() + acc.bytes() +
                          bsum.bytes() + invVal.bytes() + rest.bytes() + quat.bytes() + tStart.bytes() + tEnt.bytes() +
-                         stage3.bytes() + peerBuf.bytes() + pxSlotIdx.bytes() + visV.bytes() + visTri.bytes() + vtStart.bytes() + vtEnt.bytes() +
+                         stageIn[0].bytes() + stageIn[1].bytes() + stageOut[0].bytes() + stageOut[1].bytes() + peerBuf.bytes() + pushRec.bytes() + visV.bytes() + visTri.bytes() + vtStart.bytes() + vtEnt.bytes() +
                          visPos.bytes() + visNrm.bytes());
     }
 };
@@ -423,21 +428,9 @@ int build_jacobi_cluster(tetsim *h, const std::vector<float> &verts, const std::
     CK(h->vpStart.upload(P.vpStart, s));
     CK(h->vpSlot.upload(P.vpSlot, s));
     CK(h->invVal.upload(P.invValence, s));
-    if (const char *e = getenv("TETSIM_APPLY_INLINE")) {
-        if (e[0] == '1' && h->opt.worldSize == 1 && h->opt.deterministic) {
-            std::vector<uint4> rec((size_t)P.numLocalVerts, make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu));
-            for (int v = 0; v < P.numLocalVerts; v++) {
-                const int b = P.vpStart[v], n = P.vpStart[v + 1] - b;
-                if (n > 4) { rec[v].w = 0xfffffffeu; continue; }
-                unsigned *w = &rec[v].x;
-                for (int k = 0; k < n; k++) w[k] = (unsigned)P.vpSlot[b + k];
-            }
-            CK(h->vpInline.upload(rec, s));
-        }
-    }
     if (h->opt.deterministic) CK(h->part.alloc(P.clVerts.size()));
     else { CK(h->acc.alloc((size_t)P.numLocalVerts)); CK(cudaMemsetAsync(h->acc.p, 0, h->acc.bytes(), s)); }
-    if (P.numBoundary > 0) CK(h->bsum.alloc((size_t)P.numBoundary));
+    if (P.numBoundary > 0) { CK(h->bsum.alloc((size_t)P.numBoundary)); CK(cudaMemsetAsync(h->bsum.p, 0, h->bsum.bytes(), s)); }
     if (h->trackVol) { CK(h->volTerm.alloc(1)); CK(cudaMemsetAsync(h->volTerm.p, 0, sizeof(double), s)); }
     h->h_vertId = P.localToCaller;
     h->halo = h->opt.worldSize > 1 && h->opt.exchange == 1 && P.haloOk;
@@ -459,8 +452,6 @@ int build_jacobi_cluster(tetsim *h, const std::vector<float> &verts, const std::
         // the fused push sends tile partials, so it needs the deterministic flush (per-tile partial sums).  The choice
         // must be the same on every rank (it fixes the layout of the receive buffers): options + environment only.
         h->peerFused = h->opt.deterministic != 0 && !(unfused && unfused[0] == '1') && jacobi_tiles_has_peer_push(P.T);
-        if (const char *v2 = getenv("TETSIM_PEER_V2")) h->peerV2 = atoi(v2) & 31;
-        if (P.T < 128) h->peerV2 &= ~kPeerV2TileAdvances;  // warp-tile workers have no CTA-level ticket
         if (h->peerFused && P.pxMaxPartials > kPeerK)
             return fail(TETSIM_E_STATE, "a rank-shared vertex has " + std::to_string(P.pxMaxPartials) + " tile partials on this rank (limit " + std::to_string(kPeerK) + "): use a larger clusterSize or exchange = 1");
         const size_t entryBytes = h->peerFused ? (size_t)kPeerK * 32 : sizeof(float4);
@@ -474,11 +465,6 @@ int build_jacobi_cluster(tetsim *h, const std::vector<float> &verts, const std::
         CK(h->pxRemoteTotal.upload(P.pxRemoteTotal, s));
         CK(h->pxRemoteSlot.upload(P.pxRemoteSlot, s));
         CK(h->peerBase.alloc(std::max<size_t>(P.hxPeers.size(), 1)));
-        {
-            std::vector<unsigned char> si(P.pxSlotIdx.begin(), P.pxSlotIdx.end());
-            if (si.empty()) si.push_back(0xff);
-            CK(h->pxSlotIdx.upload(si, s));
-        }
         CK(h->pxArgs.alloc(1));
         for (int b = 0; b < P.numBoundary; b++)
             if (!P.boundaryActive[b]) h->h_vertId[(size_t)P.numInterior + b] = -1;
@@ -560,7 +546,6 @@ PeerArgs peer_args(const tetsim *h) {
     a.peerBase = h->peerBase.p; a.remoteTotal = h->pxRemoteTotal.p; a.remoteSlot = h->pxRemoteSlot.p;
     a.self = h->peerBuf.p; a.selfTotal = (int)P.hxSendIdx.size();
     a.srcStart = h->hxSrcStart.p; a.src = h->hxSrc.p;
-    a.slotIdx = h->pxSlotIdx.p; a.numBoundarySlots = (int)P.pxSlotIdx.size();
     a.pushRec = h->pushRec.p;
     unsigned long long ms = 10000ull;
     if (const char *e = getenv("TETSIM_PEER_TIMEOUT_MS")) { long v = atol(e); if (v > 0) ms = (unsigned long long)v; }
@@ -610,7 +595,6 @@ int enqueue_substeps(tetsim *h, int count) {
                     ApplyArgs aa{};
                     aa.x4 = h->x4.p; aa.prev4 = h->prev4.p; aa.vel4 = h->vel4.p;
                     aa.vpStart = h->vpStart.p; aa.vpSlot = h->vpSlot.p; aa.part = h->part.p; aa.acc = h->acc.p;
-                    aa.vpInline = h->vpInline.p;
                     aa.invVal = h->invVal.p; aa.sp = sp; aa.vertId = vid;
                     aa.boundaryBegin = P.numInterior;
                     const bool multi = h->opt.worldSize > 1 && P.numBoundary > 0;
@@ -628,11 +612,9 @@ int enqueue_substeps(tetsim *h, int count) {
                             TileArgs cf = ca;
                             cf.px = h->pxArgs.p;
                             cf.pxSlots = (int)P.pxSlotIdx.size();
-                            cf.pxFlags = h->peerV2;
                             launch_jacobi_tiles(s, P.T, cf);
                             TR("tiles + peer push");
                             aa.px = h->pxArgs.p;
-                            aa.pxFlags = h->peerV2;
                             h->enq += 2;
                         } else if (h->peer) {
                             // boundary tiles -> push this rank's boundary sums into the sharers' buffers (+ flag)
@@ -761,14 +743,72 @@ int peer_check(tetsim *h) {
     return TETSIM_OK;
 }
 
-int fetch3(tetsim *h, const float4 *src, float *out) {
+// ---- state transfer (see the comment on tetsim::h2dStream) ----
+int xfer_init(tetsim *h) {
+    if (h->h2dStream) return TETSIM_OK;
+    CK(cudaStreamCreateWithFlags(&h->h2dStream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->d2hStream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; b++) {
+        CK(cudaEventCreateWithFlags(&h->evIn[b], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->evInFree[b], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->evPacked[b], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->evOut[b], cudaEventDisableTiming));
+    }
+    return TETSIM_OK;
+}
+
+// resident = the arrays are in the handle's own vertex order (tetsim_get_resident_ids), nInt entries; else caller order, N.
+int upload_state(tetsim *h, const float *pos, const float *prevPos, const float *vel, bool resident) {
+    if (!h) return fail(TETSIM_E_INVALID, "null handle");
+    DeviceGuard g(h->device);
+    if (int rc = xfer_init(h)) return rc;
+    const float *src[3] = {pos, prevPos, vel};
+    const size_t n3 = 3 * (size_t)(resident ? h->nInt : h->N);
+    int mask = 0;
+    for (int k = 0; k < 3; k++) mask |= src[k] ? 1 << k : 0;
+    if (!mask || n3 == 0) return TETSIM_OK;
+    const int b = (int)(h->inSeq++ & 1u);
+    if (h->stageIn[b].n < 3 * n3) CK(h->stageIn[b].alloc(3 * n3));
+    CK(cudaStreamWaitEvent(h->h2dStream, h->evInFree[b], 0));   // the unpack that last read this staging buffer is done
+    for (int k = 0; k < 3; k++)
+        if (src[k]) CK(cudaMemcpyAsync(h->stageIn[b].p + k * n3, src[k], n3 * sizeof(float), cudaMemcpyHostToDevice, h->h2dStream));
+    CK(cudaEventRecord(h->evIn[b], h->h2dStream));
+    CK(cudaStreamWaitEvent(h->stream, h->evIn[b], 0));
+    launch_unpack_state(h->stream, h->nInt, n3, h->stageIn[b].p, resident ? nullptr : h->vertId.p, h->x4.p, h->prev4.p, h->vel4.p, mask);
+    CK(cudaEventRecord(h->evInFree[b], h->stream));
+    CK(cudaGetLastError());
+    return TETSIM_OK;
+}
+
+int download_begin(tetsim *h, const float4 *src, float *out, bool resident) {
     if (!h || !out) return fail(TETSIM_E_INVALID, "null argument");
     DeviceGuard g(h->device);
-    if (h->nInt != h->N) CK(cudaMemsetAsync(h->stage3.p, 0xff, h->stage3.bytes(), h->stream));  // non-resident -> NaN
-    launch_pack3(h->stream, h->nInt, src, h->vertId.p, h->stage3.p);
-    CK(cudaMemcpyAsync(out, h->stage3.p, h->stage3.bytes(), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    if (int rc = xfer_init(h)) return rc;
+    const size_t n3 = 3 * (size_t)(resident ? h->nInt : h->N);
+    const int b = (int)(h->outSeq++ & 1u);
+    if (h->stageOut[b].n < std::max<size_t>(n3, 1)) CK(h->stageOut[b].alloc(std::max<size_t>(n3, 1)));
+    CK(cudaStreamWaitEvent(h->stream, h->evOut[b], 0));         // the copy that last read this staging buffer is done
+    if (!resident && h->nInt != h->N) CK(cudaMemsetAsync(h->stageOut[b].p, 0xff, n3 * sizeof(float), h->stream));  // non-resident -> NaN
+    launch_pack3(h->stream, h->nInt, src, resident ? nullptr : h->vertId.p, h->stageOut[b].p);
+    CK(cudaEventRecord(h->evPacked[b], h->stream));
+    CK(cudaStreamWaitEvent(h->d2hStream, h->evPacked[b], 0));
+    if (n3) CK(cudaMemcpyAsync(out, h->stageOut[b].p, n3 * sizeof(float), cudaMemcpyDeviceToHost, h->d2hStream));
+    CK(cudaEventRecord(h->evOut[b], h->d2hStream));
+    h->pendingOut = b;
+    CK(cudaGetLastError());
+    return TETSIM_OK;
+}
+
+int download_wait(tetsim *h) {
+    if (!h) return fail(TETSIM_E_INVALID, "null handle");
+    DeviceGuard g(h->device);
+    if (h->pendingOut >= 0) { CK(cudaEventSynchronize(h->evOut[h->pendingOut])); h->pendingOut = -1; }
     return peer_check(h);
+}
+
+int fetch3(tetsim *h, const float4 *src, float *out, bool resident = false) {
+    if (int rc = download_begin(h, src, out, resident)) return rc;
+    return download_wait(h);
 }
 }  // namespace
 
@@ -933,7 +973,13 @@ int tetsim_create(const float *verts, int32_t numVerts, const int32_t *tetIds, i
         const bool identity = h->h_vertId.empty();
         h->nInt = identity ? numVerts : (int)h->h_vertId.size();
         std::vector<float4> hxi((size_t)h->nInt);
-        for (int i = 0; i < h->nInt; i++) hxi[i] = hx[identity ? i : h->h_vertId[i]];
+        // replicas of rank-shared vertices this rank's tets never touch (h_vertId < 0, worldSize >= 3 with the neighbour
+        // and peer exchanges) are not maintained: NaN records that no tile reads; pack/unpack/nearest skip them through vertId
+        const float qnan = std::nanf("");
+        for (int i = 0; i < h->nInt; i++) {
+            const int c = identity ? i : h->h_vertId[i];
+            hxi[i] = c >= 0 ? hx[c] : make_float4(qnan, qnan, qnan, 0.0f);
+        }
         CK(h->x4.upload(hxi, s));
         CK(h->prev4.upload(hxi, s));
         CK(h->vel4.alloc((size_t)h->nInt));
@@ -968,7 +1014,6 @@ int tetsim_create(const float *verts, int32_t numVerts, const int32_t *tetIds, i
         if (rc != TETSIM_OK) return rc;
     }
     CK(h->sp.alloc(1));
-    CK(h->stage3.alloc(3 * (size_t)std::max(numVerts, 1)));
     CK(h->volOut.alloc(1));
     CK(h->grabP.alloc(3)); CK(h->grabOut.alloc(1)); CK(h->grabScratch.alloc(1));
     CK(cudaStreamSynchronize(s));
@@ -981,6 +1026,10 @@ void tetsim_destroy(tetsim_t *h) {
     if (!h) return;
     DeviceGuard g(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->h2dStream) { cudaStreamSynchronize(h->h2dStream); cudaStreamDestroy(h->h2dStream); }
+    if (h->d2hStream) { cudaStreamSynchronize(h->d2hStream); cudaStreamDestroy(h->d2hStream); }
+    for (int b = 0; b < 2; b++)
+        for (cudaEvent_t e : {h->evIn[b], h->evInFree[b], h->evPacked[b], h->evOut[b]}) if (e) cudaEventDestroy(e);
     for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second);
     if (h->trace) trace_report(h);
     for (void *m : h->peerOpened) cudaIpcCloseMemHandle(m);
@@ -992,7 +1041,7 @@ void tetsim_destroy(tetsim_t *h) {
     for (auto *b : f4) b->release();
     DevBuf<int> *i1[] = {&h->vertId, &h->cStart, &h->cEnt, &h->order, &h->levelStart, &h->vpStart, &h->vpSlot, &h->tStart, &h->tEnt, &h->grabOut, &h->visTri, &h->vtStart, &h->vtEnt};
     for (auto *b : i1) b->release();
-    DevBuf<float> *f1[] = {&h->Q9, &h->irv, &h->invMass, &h->invVal, &h->stage3, &h->visPos, &h->visNrm};
+    DevBuf<float> *f1[] = {&h->Q9, &h->irv, &h->invMass, &h->invVal, &h->stageIn[0], &h->stageIn[1], &h->stageOut[0], &h->stageOut[1], &h->visPos, &h->visNrm};
     for (auto *b : f1) b->release();
     h->ids.release(); h->I.release(); h->bodies.release(); h->volTerm.release(); h->volOut.release();
     h->tileTets.release(); h->tileMeta.release(); h->metaOff.release();
@@ -1012,6 +1061,8 @@ int tetsim_synchronize(tetsim_t *h) {
     if (!h) return fail(TETSIM_E_INVALID, "null handle");
     DeviceGuard g(h->device);
     CK(cudaStreamSynchronize(h->stream));
+    if (h->d2hStream) CK(cudaStreamSynchronize(h->d2hStream));
+    h->pendingOut = -1;
     if (h->trace) trace_report(h);
     return peer_check(h);
 }
@@ -1028,17 +1079,18 @@ int tetsim_get_resident(tetsim_t *h, uint8_t *out) {
     return TETSIM_OK;
 }
 
-int tetsim_set_state(tetsim_t *h, const float *pos, const float *prevPos, const float *vel) {
-    if (!h) return fail(TETSIM_E_INVALID, "null handle");
-    DeviceGuard g(h->device);
-    const float *src[3] = {pos, prevPos, vel};
-    float4 *dst[3] = {h->x4.p, h->prev4.p, h->vel4.p};
-    for (int k = 0; k < 3; k++) {
-        if (!src[k]) continue;
-        CK(cudaMemcpyAsync(h->stage3.p, src[k], (size_t)3 * h->N * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-        launch_unpack3(h->stream, h->nInt, h->stage3.p, h->vertId.p, dst[k], k == 0 ? 1 : 0);
-    }
-    CK(cudaGetLastError());
+int tetsim_set_state(tetsim_t *h, const float *pos, const float *prevPos, const float *vel) { return upload_state(h, pos, prevPos, vel, false); }
+int tetsim_set_state_resident(tetsim_t *h, const float *pos, const float *prevPos, const float *vel) { return upload_state(h, pos, prevPos, vel, true); }
+
+int tetsim_get_positions_async(tetsim_t *h, float *out) { return h ? download_begin(h, h->x4.p, out, false) : fail(TETSIM_E_INVALID, "null handle"); }
+int tetsim_get_positions_resident(tetsim_t *h, float *out) { return h ? fetch3(h, h->x4.p, out, true) : fail(TETSIM_E_INVALID, "null handle"); }
+int tetsim_get_positions_resident_async(tetsim_t *h, float *out) { return h ? download_begin(h, h->x4.p, out, true) : fail(TETSIM_E_INVALID, "null handle"); }
+int tetsim_wait_positions(tetsim_t *h) { return download_wait(h); }
+
+int tetsim_get_resident_ids(tetsim_t *h, int32_t *out) {
+    if (!h || !out) return fail(TETSIM_E_INVALID, "null argument");
+    if (h->h_vertId.empty()) { for (int i = 0; i < h->nInt; i++) out[i] = i; }
+    else std::copy(h->h_vertId.begin(), h->h_vertId.end(), out);
     return TETSIM_OK;
 }
 
@@ -1083,15 +1135,40 @@ int tetsim_get_polar_state(tetsim_t *h, float *rest12, float *quat4) {
     return TETSIM_OK;
 }
 
-int tetsim_start_grab(tetsim_t *h, const double p[3], int32_t *outGrabId) {
-    if (!h || !p) return fail(TETSIM_E_INVALID, "null argument");
+// Nearest resident vertex (first strict minimum of the f64 squared distance, src/Softbody.js:279-291) without touching
+// the grab state.  On a multi-GPU handle every rank searches the vertices it maintains; the caller reduces (d2, id) over
+// the ranks (smallest d2, ties to the smallest id) and hands the winner to every rank with tetsim_set_grab.
+int tetsim_nearest_vertex(tetsim_t *h, const double p[3], int32_t *outId, double *outD2) {
+    if (!h || !p || !outId) return fail(TETSIM_E_INVALID, "null argument");
     DeviceGuard g(h->device);
     CK(cudaMemcpyAsync(h->grabP.p, p, 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     launch_nearest_vertex(h->stream, h->nInt, h->x4.p, h->vertId.p, h->grabP.p, h->grabOut.p, h->grabScratch.p);
     int id = -1;
+    unsigned long long bits = 0;
     CK(cudaMemcpyAsync(&id, h->grabOut.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&bits, h->grabScratch.p, sizeof(bits), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (id < 0 || id >= h->N) id = -1;  // no finite distance: grabId stays -1 like the reference loop
+    *outId = id;
+    if (outD2) { double d2; memcpy(&d2, &bits, sizeof(d2)); *outD2 = id >= 0 ? d2 : INFINITY; }
+    return TETSIM_OK;
+}
+
+int tetsim_set_grab(tetsim_t *h, int32_t grabId, const double p[3]) {
+    if (!h || !p) return fail(TETSIM_E_INVALID, "null argument");
+    if (grabId < -1 || grabId >= h->N) return fail(TETSIM_E_INVALID, "grabId outside [-1, numVerts)");
+    h->grabId = grabId;
+    memcpy(h->grabPos, p, sizeof(h->grabPos));
+    return TETSIM_OK;
+}
+
+int tetsim_start_grab(tetsim_t *h, const double p[3], int32_t *outGrabId) {
+    if (!h || !p) return fail(TETSIM_E_INVALID, "null argument");
+    if (h->opt.worldSize > 1)
+        return fail(TETSIM_E_STATE, "startGrab on a multi-GPU handle: every rank sees only its own vertices -- call tetsim_nearest_vertex on every rank, "
+                                    "reduce (d2, id) over the ranks and pass the winner to tetsim_set_grab on every rank");
+    int32_t id = -1;
+    if (int rc = tetsim_nearest_vertex(h, p, &id, nullptr)) return rc;
     h->grabId = id;
     memcpy(h->grabPos, p, sizeof(h->grabPos));
     if (outGrabId) *outGrabId = id;
@@ -1283,7 +1360,7 @@ int tetsim_set_peers(tetsim_t *h, const void *blobs) {
         }
     }
     CK(cudaMemcpyAsync(h->peerBase.p, base.data(), base.size() * sizeof(unsigned char *), cudaMemcpyHostToDevice, h->stream));
-    if (h->peerFused && (h->peerV2 & kPeerV2PushRecords)) {  // experiment: one self-contained 32-byte record per pushing slot
+    if (h->peerFused) {  // one self-contained 32-byte record per pushing slot (PeerArgs::pushRec)
         std::vector<uint4> rec(2 * std::max<size_t>(P.pxSlotIdx.size(), 1), make_uint4(0xffffffffu, 0u, 0u, 0u));
         for (int b = 0; b < P.numBoundary; b++) {
             const int id = P.numInterior + b, n = P.vpStart[id + 1] - P.vpStart[id];

@@ -198,6 +198,43 @@ class _Body:
         check(_capi.lib().tetsim_set_state(self._h, *[ptr(a) for a in arrs]))
         self.synchronize()
 
+    # ---- rank-local state access (multi-GPU hosts): arrays in the handle's own vertex order ----
+    @property
+    def resident_ids(self):
+        """Caller vertex id of every vertex this handle holds (-1: a replica this rank does not maintain)."""
+        out = np.empty(self.info()["localVerts"], np.int32)
+        check(_capi.lib().tetsim_get_resident_ids(self._h, ptr(out)))
+        return out
+
+    def set_state_resident(self, pos=None, prevPos=None, vel=None):
+        n = 3 * self.info()["localVerts"]
+        arrs = [None if a is None else np.ascontiguousarray(a, np.float32).reshape(-1) for a in (pos, prevPos, vel)]
+        for a in arrs:
+            if a is not None and a.size != n:
+                raise ValueError("resident state arrays must hold 3 floats per resident vertex")
+        self._cache.clear()
+        check(_capi.lib().tetsim_set_state_resident(self._h, *[ptr(a) for a in arrs]))
+        self.synchronize()
+
+    @property
+    def pos_resident(self):
+        out = np.empty(3 * self.info()["localVerts"], np.float32)
+        check(_capi.lib().tetsim_get_positions_resident(self._h, ptr(out)))
+        return out
+
+    def nearest_vertex(self, pos):
+        """(caller vertex id, f64 squared distance) of the nearest vertex this rank maintains; (-1, inf) if none."""
+        p = self._xyz(pos)
+        gid, d2 = C.c_int32(-1), C.c_double(0.0)
+        check(_capi.lib().tetsim_nearest_vertex(self._h, p.ctypes.data_as(C.POINTER(C.c_double)), C.byref(gid), C.byref(d2)))
+        return gid.value, d2.value
+
+    def set_grab(self, grab_id, pos):
+        p = self._xyz(pos)
+        check(_capi.lib().tetsim_set_grab(self._h, int(grab_id), p.ctypes.data_as(C.POINTER(C.c_double))))
+        self.grabId = int(grab_id)
+        self.grabPos[:] = p
+
     def info(self) -> dict:
         i = _capi.TetSimInfo()
         check(_capi.lib().tetsim_get_info(self._h, C.byref(i)))
