@@ -197,11 +197,11 @@ struct TileSmem {
     static constexpr int TET_BYTES = T * 48;
     // byte offsets inside the worker's shared-memory region (computed, never indexed: stays in registers)
     int sxBytes, metaStride, sdx, sx0, meta0, bars, total;
-    __host__ __device__ TileSmem(int metaStride_, int maxTileVertsPad) {
+    __host__ __device__ TileSmem(int metaStride_, int maxTileVertsPad, int maxTileEntries) {
         sxBytes = maxTileVertsPad * 16;
         metaStride = metaStride_;
         sdx = 0;
-        sx0 = sdx + (4 * T + 1) * 16;  // + one spare entry for padding records
+        sx0 = sdx + ((maxTileEntries + 1) * 16 + 127) / 128 * 128;  // + one spare entry for padding records
         meta0 = sx0 + S * sxBytes;
         bars = meta0 + (S + 1) * metaStride;
         total = (bars + (S + 1) * 8 + 127) & ~127;
@@ -238,7 +238,7 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
     constexpr int T = NT * TPT;
     const int dbg = DBG ? a.debugSkip : 0;  // ablation switches exist only in the DBG instantiation (tetsim_time_kernel)
     const bool trackVol = a.volAcc != nullptr;
-    const TileSmem<T, S> L(a.metaStride, a.maxTileVertsPad);
+    const TileSmem<T, S> L(a.metaStride, a.maxTileVertsPad, a.maxTileEntries);
     uint64_t *metaFull = reinterpret_cast<uint64_t *>(ws + L.bars);  // [S + 1]
     unsigned char *const sdx = ws + L.sdx;
     const uint32_t wsa = smem_u32(ws);           // shared-window address of the worker's region
@@ -299,18 +299,18 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
         else cp_async_commit();
     }
 
-    // (Software-pipelining these loads one tile ahead -- issuing them right after the previous tile's math -- was
-    // measured twice in round 1 and is slower: 0.195 vs 0.188 ms with one tet per thread, 0.153 vs 0.141 ms with two.)
-    int k = 0;
-    for (int c = first; c < a.numTiles; c += stride, k++) {
-        const int cur = k % S, mcur = k % (S + 1);
-        // this tile's records: issue the loads first, they land while we wait and prefetch below
-        const unsigned char *tb = a.tets + (size_t)c * TileSmem<T, S>::TET_BYTES;
-        float4 rA[TPT], rB[TPT], rC[TPT];
+    // The tile's records (3 x LDG.128 per tet), issued at the top of the tile's iteration: they land while the CTA waits for
+    // its gathers and the barrier.  (Issuing them one phase earlier -- for the NEXT tile, right before this tile's corner
+    // sums, into the same registers -- was measured three times, rounds 1 and 2, and is 3 % slower each time.)
+    // Issuing the next tile's GATHER in their shadow (right after the first barrier, by all threads) is worse still: +8 %.
+    // Staggering the start of co-resident CTAs changes nothing.  (profiles/r2_tile_experiments.txt)
+    float4 rA[TPT], rB[TPT], rC[TPT];
+    auto load_records = [&](int tile) {
+        const unsigned char *tb = a.tets + (size_t)tile * TileSmem<T, S>::TET_BYTES;
 #pragma unroll
         for (int u = 0; u < TPT; u++) {
             const int t = tid + NT * u;
-            if (dbg & 8) {  // measurement only: synthetic record, no HBM stream
+            if (DBG && (dbg & 8)) {  // measurement only: synthetic record, no HBM stream
                 const float f = 1.0f + 1e-3f * (float)(t & 7);
                 rA[u] = make_float4(f, 0.01f, 0.02f, f); rB[u] = make_float4(0.03f, f, 6.0f, 1.0f);
                 rC[u] = make_float4(__uint_as_float(((t * 16) & 0x3ff) | (((t * 16 + 16) & 0x3ff) << 16)),
@@ -323,6 +323,11 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
             rB[u] = ldg_stream4(tb + T * 16 + t * 16);
             rC[u] = ldg_stream4(tb + T * 32 + t * 16);
         }
+    };
+    int k = 0;
+    for (int c = first; c < a.numTiles; c += stride, k++) {
+        const int cur = k % S, mcur = k % (S + 1);
+        load_records(c);
         cp_async_wait_pending<S - 2>();
         sync();  // this tile's gathers (all threads') landed; previous tile's corner sums are finished
 
@@ -388,20 +393,27 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
         sync();
         prefetch_next();
 
-        // ---- per-tile-vertex sum of corner dx, ascending (tet, corner) order ----
+        // ---- per-tile-vertex sum of corner dx (grouped rows, mesh_prep.cpp): thread j owns tile vertex j, its entries sit
+        // 144 bytes apart from a per-group base -> LDS.128 with immediate offsets, four in flight at a time ----
         const unsigned char *m = ws + L.meta(mcur);
         const int v0 = reinterpret_cast<const int *>(m)[0];
         const int nl = reinterpret_cast<const int *>(m)[1];
-        const uint16_t *scol = reinterpret_cast<const uint16_t *>(m + 16);
+        const uint16_t *gbase = reinterpret_cast<const uint16_t *>(m + 16);
         if (!(dbg & 1))
             for (int j = tid; j < nl; j += NT) {
                 const int val = m[a.metaValOff + j];
-                const unsigned char *base = sdx + j * 16;
+                const unsigned char *p = sdx + gbase[j >> 3] + ((j & 7) << 4);
                 float ax = 0.0f, ay = 0.0f, az = 0.0f;
-#pragma unroll 4
-                for (int i = 0; i < val; i++) {
-                    const float4 d = *reinterpret_cast<const float4 *>(base + scol[i]);
-                    ax += d.x; ay += d.y; az += d.z;
+                int i = 0;
+#pragma unroll 1
+                for (; i + 2 <= val; i += 2, p += 2 * 144) {  // (four per trip spills at the 64-register cap)
+                    const float4 d0 = *reinterpret_cast<const float4 *>(p), d1 = *reinterpret_cast<const float4 *>(p + 144);
+                    ax += d0.x; ay += d0.y; az += d0.z;
+                    ax += d1.x; ay += d1.y; az += d1.z;
+                }
+                if (i < val) {
+                    const float4 d0 = *reinterpret_cast<const float4 *>(p);
+                    ax += d0.x; ay += d0.y; az += d0.z;
                 }
                 if (a.acc) atomicAdd(a.acc + reinterpret_cast<const int *>(m + reinterpret_cast<const int *>(m)[3])[j],
                                      make_float4(ax, ay, az, 0.0f));
@@ -463,12 +475,6 @@ template <int T, int S, int MINB, bool DBG = false>
 __global__ void __launch_bounds__(T, MINB) k_jacobi_tiles(TileArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     if (a.tileBegin + (int)blockIdx.x >= a.numTiles) return;
-    if (a.staggerNs > 0) {  // co-resident CTAs are identical and would otherwise run their phases in lockstep
-        int sms;
-        asm("mov.u32 %0, %%nsmid;" : "=r"(sms));
-        const unsigned slot = blockIdx.x / (unsigned)sms;
-        if (slot) __nanosleep(slot * (unsigned)a.staggerNs);
-    }
     tile_worker<T, 1, S, false, DBG>(a, smem, threadIdx.x, a.tileBegin + blockIdx.x, gridDim.x);
 }
 
@@ -491,12 +497,12 @@ __global__ void __launch_bounds__(TPL == 1 ? 832 : 448, 1) k_jacobi_warptiles(Ti
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int first = a.tileBegin + blockIdx.x * wpb + wid;
     if (first >= a.numTiles) return;
-    const TileSmem<32 * TPL, S> L(a.metaStride, a.maxTileVertsPad);
+    const TileSmem<32 * TPL, S> L(a.metaStride, a.maxTileVertsPad, a.maxTileEntries);
     tile_worker<32, TPL, S, true>(a, smem + (size_t)wid * L.total, lane, first, gridDim.x * wpb);
 }
 
 template <int T, int S>
-static size_t tile_smem_bytes(const TileArgs &a) { return (size_t)TileSmem<T, S>(a.metaStride, a.maxTileVertsPad).total; }
+static size_t tile_smem_bytes(const TileArgs &a) { return (size_t)TileSmem<T, S>(a.metaStride, a.maxTileVertsPad, a.maxTileEntries).total; }
 
 // Kernel shape per tile size.  Defaults are the round-1 sweep winners on the 10M-tet beam (profiles/r1_tile_sweep.txt):
 // two tets per thread (independent dependency chains, half the per-tile barrier/prefetch overhead per tet, corner sums

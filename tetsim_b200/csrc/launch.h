@@ -58,11 +58,11 @@ struct TileArgs {
     const uint32_t *metaOff;        // [numTiles + 1]
     int tileBegin, numTiles;        // this launch walks tiles [tileBegin, numTiles)
     int metaStride, metaValOff, colStride, maxTileVertsPad;  // metaStride = largest block
+    int maxTileEntries;             // sixteen-byte entries of the largest tile's corner buffer (ClusterPlan::maxTileEntries)
     float4 *part;                   // per-tile partial dx sums (deterministic flush)
     float4 *acc;                    // global accumulator (atomic flush), or NULL
     double *volAcc;                 // sum over tets of det F - 1, or NULL
     const SubstepParams *sp;
-    int staggerNs;                  // initial delay per resident-CTA slot (breaks phase lockstep of co-resident CTAs)
     int debugSkip;                  // measurement only (tetsim_time_kernel + TETSIM_TILE_DEBUG): 1 no vertex phase, 2 no math, 4 no gather
     const PeerArgs *px;             // DEVICE copy of the peer-exchange arguments: fused push of the boundary sums, or NULL
     int pxSlots;                    // fused push: partial slots [0, pxSlots) belong to boundary tiles (by value: no load on the way)

@@ -430,6 +430,8 @@ bool build_cluster_plan(int numVerts, int numTets, const int *tetIds, const std:
     std::vector<int> stamp((size_t)P.numLocalVerts, -1), tileIdx((size_t)P.numLocalVerts, 0);
     std::vector<int> tileVerts, tileVal, perm, rank_of;
     std::vector<std::vector<uint16_t>> colOffs((size_t)P.numClusters);
+    constexpr int kGroup = 8, kRowStride = 9;
+    int maxTileEntries = 0;
     std::vector<uint8_t> allVal;
     std::vector<int> cornerStart, cornerFill, cornerList, cornerDiag, loadG, loadS, sorted;
     std::vector<char> posTaken, diagFree;
@@ -455,19 +457,26 @@ bool build_cluster_plan(int numVerts, int numTets, const int *tetIds, const std:
         const int tv = nl ? tileVal[perm[0]] : 0;
         if (tv > 255) { err = "a vertex has more than 255 tet corners inside one tile"; return false; }
         maxTileVal = std::max(maxTileVal, tv);
-        // jagged diagonals: diagonal i holds one corner of every vertex with valence > i; vertices are
-        // valence-sorted, so those are a prefix and entry (i, j) sits at colOff[i] + j
-        std::vector<uint16_t> &co = colOffs[c];
-        co.assign((size_t)tv + 1, 0);
+        // grouped rows: the valence-sorted tile vertices are cut into groups of kGroup = 8; group g owns a block of
+        // (largest valence in g) rows of kRowStride = 9 sixteen-byte entries, entry (i, j) = i-th corner of tile vertex j at
+        // gbase[j / 8] + 9 i + j % 8.  The thread that sums vertex j then reads base + 144 i: immediate offsets, no
+        // per-entry index load (the jagged diagonals of round 1 cost a LDS.U16 + two LEA per entry), and a quarter-warp
+        // reads 128 contiguous bytes (conflict-free).  The odd row stride keeps the row choice a degree of freedom for
+        // the bank placement of the scatter: entry (i, j) lies in bank group (i + j) mod 8.
+        std::vector<uint16_t> &co = colOffs[c];  // gbase per group, in entries
+        const int ngroups = (nl + kGroup - 1) / kGroup;
+        co.assign((size_t)ngroups + 1, 0);
         {
-            int off = 0, cnt = nl;
-            for (int i = 0; i < tv; i++) {
-                co[i] = (uint16_t)off;
-                while (cnt > 0 && tileVal[perm[cnt - 1]] <= i) cnt--;
-                off += cnt;
+            int off = 0;
+            for (int g = 0; g < ngroups; g++) {
+                co[g] = (uint16_t)off;
+                off += tileVal[perm[g * kGroup]] * kRowStride;  // perm is descending: the group's first vertex has its largest valence
             }
-            co[tv] = (uint16_t)off;
+            co[ngroups] = (uint16_t)off;
+            if (off > 4000) { err = "tile too large for 16-bit byte offsets"; return false; }
+            maxTileEntries = std::max(maxTileEntries, off);
         }
+        auto entryOf = [&](int i, int j) { return (int)co[j / kGroup] + kRowStride * i + j % kGroup; };
         // ---- shared-memory bank placement (round-1 ncu: 37 % of this kernel's shared-memory wavefronts
         // were bank-conflict replays of the 16-byte gathers and scatters) ----
         // A 128-bit warp access is served a quarter-warp (8 lanes) at a time and is conflict-free when
@@ -540,12 +549,12 @@ bool build_cluster_plan(int numVerts, int numTets, const int *tetIds, const std:
                 int best = -1, bestLoad = 0;
                 for (int i = 0; i < val; i++) {
                     if (!diagFree[i]) continue;
-                    const int ld = loadS[(size_t)sid * 8 + ((co[i] + j) & 7)];
+                    const int ld = loadS[(size_t)sid * 8 + (entryOf(i, j) & 7)];
                     if (best < 0 || ld < bestLoad) { best = i; bestLoad = ld; if (ld == 0) break; }
                 }
                 diagFree[best] = 0;
                 cornerDiag[cn] = best;
-                loadS[(size_t)sid * 8 + ((co[best] + j) & 7)]++;
+                loadS[(size_t)sid * 8 + (entryOf(best, j) & 7)]++;
             }
         }
         for (int tl = 0; tl < ntile; tl++) {
@@ -554,7 +563,7 @@ bool build_cluster_plan(int numVerts, int numTets, const int *tetIds, const std:
             for (int k = 0; k < 4; k++) {
                 const int j = rank_of[tileIdx[local[t[k]]]];
                 sl[k] = 16u * (uint32_t)j;
-                ds[k] = 16u * ((uint32_t)co[cornerDiag[4 * tl + k]] + (uint32_t)j);
+                ds[k] = 16u * (uint32_t)entryOf(cornerDiag[4 * tl + k], j);
             }
             size_t r = (size_t)c * T + tl;
             P.recordAux[4 * r + 0] = sl[0] | sl[1] << 16;
@@ -563,16 +572,17 @@ bool build_cluster_plan(int numVerts, int numTets, const int *tetIds, const std:
             P.recordAux[4 * r + 3] = ds[2] | ds[3] << 16;
         }
     }
-    // padding records of the last tile: read tile vertex 0, park their (zero) dx in the spare entry 4T
+    // padding records of the last tile: read tile vertex 0, park their (zero) dx in the spare entry after the largest tile
+    P.maxTileEntries = maxTileEntries;
     for (size_t r = 0; r < nRec; r++)
         if (P.recordTet[r] < 0) {
-            const uint32_t spare = 16u * 4u * (uint32_t)T;
+            const uint32_t spare = 16u * (uint32_t)maxTileEntries;
             P.recordAux[4 * r + 2] = spare | spare << 16;
             P.recordAux[4 * r + 3] = spare | spare << 16;
         }
     if (P.maxTileVerts < 1) P.maxTileVerts = 1;
-    if (16 * P.maxTileVerts > 65535 || 16 * 4 * T > 65535) { err = "tile too large for 16-bit byte offsets"; return false; }
-    P.colStride = ((maxTileVal + 1 + 7) / 8) * 8;
+    if (16 * P.maxTileVerts > 65535 || 16 * (maxTileEntries + 1) > 65535) { err = "tile too large for 16-bit byte offsets"; return false; }
+    P.colStride = (((P.maxTileVerts + kGroup - 1) / kGroup + 1 + 7) / 8) * 8;  // entries of the per-tile group-base table
     P.maxTileVertsPad = ((P.maxTileVerts + 15) / 16) * 16;
     P.metaValOff = 16 + 2 * P.colStride;
     P.metaStride = P.metaValOff + 5 * P.maxTileVertsPad;  // largest block (shared-memory slot size)
@@ -587,7 +597,7 @@ bool build_cluster_plan(int numVerts, int numTets, const int *tetIds, const std:
         unsigned char *m = P.tileMeta.data() + (size_t)P.metaOff[c] * 16;
         const int v0 = P.clVertStart[c], nl = P.clVertStart[c + 1] - v0;
         const int nlPad = ((nl + 15) / 16) * 16;
-        int hdr[4] = {v0, nl, (int)colOffs[c].size() - 1, P.metaValOff + nlPad /* byte offset of ids */};
+        int hdr[4] = {v0, nl, (int)colOffs[c].size() - 1 /* groups */, P.metaValOff + nlPad /* byte offset of ids */};
         memcpy(m, hdr, 16);
         uint16_t *co = reinterpret_cast<uint16_t *>(m + 16);
         for (size_t i = 0; i < colOffs[c].size(); i++) co[i] = (uint16_t)(16u * colOffs[c][i]);

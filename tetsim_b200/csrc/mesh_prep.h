@@ -72,13 +72,13 @@ struct ClusterPlan {
     std::vector<int> recordTet;         // [numClusters * T] caller tet index, -1 = padding
     // per record: {slot0|slot1<<16, slot2|slot3<<16, dest0|dest1<<16, dest2|dest3<<16}.  slot = byte offset
     // (16 * tile vertex index) of a corner's position in the staged vertex tile; dest = byte offset
-    // (16 * entry) of the corner's dx in the staged jagged-diagonal sum buffer.
+    // (16 * entry) of the corner's dx in the staged corner buffer (grouped rows).
     std::vector<uint32_t> recordAux;    // [numClusters * T * 4]
     std::vector<int> clVertStart;       // [numClusters + 1]
     std::vector<int> clVerts;           // local vertex ids per tile, descending tile valence
     // One metadata block per tile (variable size, 16-byte granular), fetched with a single bulk async copy:
     //   [0,16)   int32 {first partial-sum slot, tile vertex count nl, max tile valence, byte offset of ids}
-    //   [16, ..) uint16 colOff[colStride]   byte offset (16 * entry) of jagged diagonal i
+    //   [16, ..) uint16 gbase[colStride]    byte offset (16 * entry) of the row block of vertex group g (8 vertices per group)
     //   then     uint8  val[nlPad]          tile valence of tile vertex j (descending), nlPad = roundup16(nl)
     //   then     int32  ids[nlPad]          handle-local vertex id of tile vertex j
     std::vector<unsigned char> tileMeta;
@@ -86,6 +86,7 @@ struct ClusterPlan {
     int metaStride = 0;                 // largest block, bytes
     int metaValOff = 0;
     int colStride = 0;
+    int maxTileEntries = 0;             // sixteen-byte entries of the largest tile's corner buffer (grouped rows, see mesh_prep.cpp)
     int maxTileVerts = 0, maxTileVertsPad = 0;
     std::vector<int> vpStart, vpSlot;   // local vertex -> indices into the partial-sum array
     std::vector<float> invValence;      // [numLocalVerts] 1 / GLOBAL valence

@@ -498,10 +498,8 @@ TileArgs tile_args(const tetsim *h) {
     TileArgs a{};
     a.x4 = h->x4.p; a.tets = h->tileTets.p; a.meta = h->tileMeta.p; a.tileBegin = 0; a.numTiles = P.numClusters;
     a.metaOff = h->metaOff.p; a.metaStride = P.metaStride; a.metaValOff = P.metaValOff;
-    a.colStride = P.colStride; a.maxTileVertsPad = P.maxTileVertsPad;
+    a.colStride = P.colStride; a.maxTileVertsPad = P.maxTileVertsPad; a.maxTileEntries = P.maxTileEntries;
     a.part = h->part.p; a.acc = nullptr; a.volAcc = nullptr; a.sp = h->sp.p;
-    a.staggerNs = 0;
-    if (const char *e = getenv("TETSIM_TILE_STAGGER_NS")) a.staggerNs = atoi(e);
     return a;
 }
 
