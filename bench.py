@@ -246,6 +246,65 @@ def config_rates(stream, device_index, frames=20):
     return out
 
 
+def c5_sharded(stream, rank, world, local_rank, dist, n=28, frames=10):
+    """BASELINE config 5 on N GPUs: n*n tiled Dragons + ground, Neo-Hookean Gauss-Seidel in the reference order per body,
+    bodies sharded across the ranks (tetsim_b200.mesh.shard_bodies: independent bodies, NO exchange).  Rate = all bodies'
+    tets x substeps / max-over-ranks time.  At N > 1 rank 0 also runs the whole scene on its own GPU and the merged
+    shard results must be BIT-identical to it (GS per body is deterministic and bodies do not interact)."""
+    import torch
+    import tetsim_b200 as ts
+    from tetsim_b200 import mesh
+    m = mesh.load_dragon()
+    v, t = mesh.tile_bodies(m["tet_verts"], m["tet_ids"], n, n, y_shift=-0.40)
+    pp = dict(ts.DEFAULT_PHYSICS_PARAMS, numSubsteps=10, worldBounds=list(mesh.wide_bounds(64.0)))
+    sv, st, vid, _ = mesh.shard_bodies(v, t, rank, world)
+    body = ts.SoftBody(sv, st, None, pp, solver="gs_exact", arithmetic="fast", device=local_rank, stream=stream.cuda_stream)
+    for _ in range(2):
+        body.step(pp)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    smp = ClockSampler(local_rank)
+    smp.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(frames):
+        body.step(pp)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    clocks = smp.stop()
+    sub = frames * pp["numSubsteps"]
+    M = t.size // 4
+    out = {"what": "%d tiled Dragons + ground, NH Gauss-Seidel in the reference order per body (f32), bodies sharded over %d GPU(s), no exchange" % (n * n, world),
+           "bodies": n * n, "tets": M, "substeps_per_s": sub / ms * 1e3, "Mtet_per_s": M * sub / ms / 1e3, "ms_timed": ms,
+           "bodies_rank0": int(body.info()["numComponents"]), "clocks": clocks}
+    if world > 1:
+        full = torch.full((v.size,), float("nan"), dtype=torch.float32)
+        full.view(-1, 3)[torch.from_numpy(vid.astype(np.int64))] = torch.from_numpy(body.pos.copy()).view(-1, 3)
+        g = full.cuda()
+        parts = [torch.empty_like(g) for _ in range(world)]
+        dist.all_gather(parts, g)
+        if rank == 0:
+            P = torch.stack(parts).cpu().numpy()
+            owned = np.isfinite(P)
+            merged = np.where(owned, P, 0.0).sum(axis=0).astype(np.float32)
+            single = ts.SoftBody(v, t, None, pp, solver="gs_exact", arithmetic="fast", device=local_rank, stream=stream.cuda_stream)
+            for _ in range(2 + frames):
+                single.step(pp)
+            ref = single.pos.copy()
+            single.close()
+            out["parity"] = {"each_vertex_on_exactly_one_rank": bool((owned.sum(axis=0) == 1).all()),
+                             "bit_identical_to_1_gpu": bool(np.array_equal(merged.view(np.uint32), ref.view(np.uint32))),
+                             "substeps": (2 + frames) * pp["numSubsteps"]}
+        dist.barrier()
+    body.close()
+    return out
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -518,9 +577,12 @@ def main():
                          % (args.cpu_substeps, M, sec)}
 
     configs = None
-    if rank == 0 and world == 1 and not args.no_configs:
+    if not args.no_configs:
         body.synchronize()
-        configs = config_rates(stream, local_rank)
+        c5 = c5_sharded(stream, rank, world, local_rank, dist if world > 1 else None)   # every rank takes part
+        if rank == 0:
+            configs = config_rates(stream, local_rank) if world == 1 else {}
+            configs["C5_784x_gs_exact_fast_sharded"] = c5
 
     if rank == 0:
         line = {

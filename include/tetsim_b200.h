@@ -237,6 +237,12 @@ int tetsim_level_schedule(const int32_t *tetIds, int32_t numTets, int32_t numVer
 /* Greedy colouring in tet order (smallest colour unused by any tet sharing a vertex). */
 int tetsim_greedy_colors(const int32_t *tetIds, int32_t numTets, int32_t numVerts, int32_t *color);
 
+/* Connected components of the mesh over shared vertices = the independent bodies of the scene (the reference's
+ * physicsScene.softBodies[], src/main.js:51,80-84, concatenated into one mesh): vertComp[numVerts] receives the body of
+ * every vertex, bodies numbered by their first vertex; returns the number of bodies.  Bodies never interact (the reference
+ * has no body-body collision), so a scene shards across GPUs by bodies with no exchange at all: tetsim_b200.mesh.shard_bodies. */
+int tetsim_connected_components(const int32_t *tetIds, int32_t numTets, int32_t numVerts, int32_t *vertComp);
+
 /* The tet partition a multi-GPU Jacobi handle of (rank, worldSize) would use, without touching a
  * GPU: tets are (optionally Morton-) ordered, cut into tiles of clusterSize and each rank takes a
  * contiguous run of tiles.  counts[0..3] = {localTets, interiorVerts, boundaryVerts, tiles};

@@ -127,3 +127,60 @@ def test_peer_exchange_layouts_agree_across_ranks(world):
             assert p["remoteSlot"][i] == j, "which of the sharer's flags is mine"
             pairs += 1
     assert pairs >= 2 * (world - 1)
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE config 5 on N GPUs: independent bodies sharded across ranks, no exchange (tetsim_b200.mesh.shard_bodies)
+# ------------------------------------------------------------------------------------------------
+def _shard_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    from tetsim_b200 import mesh
+    m = mesh.load_dragon()
+    v, t = mesh.tile_bodies(m["tet_verts"], m["tet_ids"], 3, 2, y_shift=-0.40)     # 6 bodies
+    N, M, nb = v.size // 3, t.size // 4, 6
+    sv, st, vid, tix = mesh.shard_bodies(v, t, rank, world)
+    # every vertex and tet on exactly one rank; bodies whole; the reference's sweep order kept inside every body
+    own_v = torch.zeros(N, dtype=torch.int32); own_v[torch.from_numpy(vid.astype(np.int64))] = 1
+    own_t = torch.zeros(M, dtype=torch.int32); own_t[torch.from_numpy(tix.astype(np.int64))] = 1
+    dist.all_reduce(own_v); dist.all_reduce(own_t)
+    assert int(own_v.min()) == 1 and int(own_v.max()) == 1 and int(own_t.min()) == 1 and int(own_t.max()) == 1
+    assert np.all(np.diff(tix) > 0) and np.all(np.diff(vid) > 0)
+    assert (sv.size // 3) % 1234 == 0 and (st.size // 4) % 3840 == 0
+    counts = torch.tensor([st.size // 4 // 3840], dtype=torch.int64)
+    allc = [torch.zeros_like(counts) for _ in range(world)]
+    dist.all_gather(allc, counts)
+    assert sum(int(c) for c in allc) == nb and max(int(c) for c in allc) - min(int(c) for c in allc) <= 1
+    assert np.array_equal(sv.reshape(-1, 3), v.reshape(-1, 3)[vid])
+    assert np.array_equal(vid[st.reshape(-1, 4)], t.reshape(-1, 4)[tix])
+    # a shard simulated alone == those bodies inside the whole scene, bit for bit (per-copy check on the SAME translated copy)
+    wb = mesh.wide_bounds(64.0)
+    whole = oracle.SoftBodyOracle(v, t, worldBounds=wb)
+    part = oracle.SoftBodyOracle(sv, st, worldBounds=wb)
+    for _ in range(6):
+        whole.simulate(1.0 / 600.0)
+        part.simulate(1.0 / 600.0)
+    assert np.array_equal(part.pos.reshape(-1, 3).view(np.uint32), whole.pos.reshape(-1, 3)[vid].view(np.uint32))
+    merged = torch.zeros(3 * N, dtype=torch.float32)
+    merged.view(-1, 3)[torch.from_numpy(vid.astype(np.int64))] = torch.from_numpy(part.pos.copy()).view(-1, 3)
+    dist.all_reduce(merged)       # disjoint supports: a sum with zeros is exact
+    assert np.array_equal(merged.numpy().view(np.uint32), whole.pos.view(np.uint32))
+    out.put(rank)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_body_sharding_no_exchange(world):
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shard_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert sorted(out.get(timeout=5) for _ in range(world)) == list(range(world))

@@ -32,6 +32,7 @@ SYMBOLS = [
     "tetsim_level_schedule", "tetsim_greedy_colors", "tetsim_plan_partition", "tetsim_plan_halo",
     "tetsim_get_positions_async", "tetsim_wait_positions", "tetsim_get_resident_ids", "tetsim_set_state_resident",
     "tetsim_get_positions_resident", "tetsim_get_positions_resident_async", "tetsim_nearest_vertex", "tetsim_set_grab",
+    "tetsim_connected_components",
 ]
 
 
@@ -140,6 +141,7 @@ def lib() -> C.CDLL:
     L.tetsim_set_peers.argtypes = [vp, vp]
     L.tetsim_level_schedule.argtypes = [i32p, C.c_int32, C.c_int32, i32p]
     L.tetsim_greedy_colors.argtypes = [i32p, C.c_int32, C.c_int32, i32p]
+    L.tetsim_connected_components.argtypes = [i32p, C.c_int32, C.c_int32, i32p]
     L.tetsim_plan_partition.argtypes = [f32p, C.c_int32, i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         i32p, i32p, i32p]
     L.tetsim_plan_halo.argtypes = [f32p, C.c_int32, i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
@@ -192,6 +194,15 @@ def greedy_colors(tet_ids, num_verts: int):
     n = check(lib().tetsim_greedy_colors(ids.ctypes.data_as(C.POINTER(C.c_int32)), ids.size // 4, num_verts,
                                          color.ctypes.data_as(C.POINTER(C.c_int32))))
     return color, n
+
+
+def connected_components(tet_ids, num_verts: int):
+    """(body of every vertex, number of bodies): connected components over shared vertices (host only, no GPU)."""
+    ids = np.ascontiguousarray(tet_ids, np.int32).reshape(-1)
+    comp = np.zeros(max(num_verts, 1), np.int32)
+    n = check(lib().tetsim_connected_components(ids.ctypes.data_as(C.POINTER(C.c_int32)), ids.size // 4, num_verts,
+                                                comp.ctypes.data_as(C.POINTER(C.c_int32))))
+    return comp[:num_verts], n
 
 
 def plan_partition(verts, tet_ids, cluster_size: int, reorder: bool, rank: int, world_size: int) -> dict:

@@ -1398,6 +1398,16 @@ int tetsim_greedy_colors(const int32_t *tetIds, int32_t numTets, int32_t numVert
     return n < 0 ? fail(TETSIM_E_INVALID, "more than 256 colours") : n;
 }
 
+int tetsim_connected_components(const int32_t *tetIds, int32_t numTets, int32_t numVerts, int32_t *vertComp) {
+    if ((!tetIds && numTets > 0) || !vertComp || numTets < 0 || numVerts < 0) return fail(TETSIM_E_INVALID, "null or negative argument");
+    for (int64_t c = 0; c < 4 * (int64_t)numTets; c++)
+        if (tetIds[c] < 0 || tetIds[c] >= numVerts) return fail(TETSIM_E_INVALID, "vertex id out of range");
+    std::vector<int> comp;
+    const int n = connected_components(numVerts, numTets, tetIds, comp);
+    std::copy(comp.begin(), comp.end(), vertComp);
+    return n;
+}
+
 int tetsim_plan_partition(const float *verts, int32_t numVerts, const int32_t *tetIds, int32_t numTets,
                           int32_t clusterSize, int32_t reorder, int32_t rank, int32_t worldSize, int32_t counts[4],
                           int32_t *localToCaller, int32_t *localTets) {

@@ -74,3 +74,24 @@ def make_beam(cells=(407, 64, 64), h: float = 0.01, y0: float = 1.0, jitter: flo
 def wide_bounds(extent: float = 64.0):
     """worldBounds wide enough for tiled scenes (the parameter is honoured per call, src/Softbody.js:215)."""
     return (-extent, -1.0, -extent, extent, 10.0, extent)
+
+
+def shard_bodies(verts, tet_ids, rank: int, world_size: int):
+    """The bodies (connected components) of a scene that rank `rank` of `world_size` simulates (BASELINE config 5 on N GPUs).
+
+    Bodies never interact -- the reference has no body-body collision, its scene is a list of independent soft bodies
+    (src/main.js:51,80-84) -- so the scene shards by bodies with NO exchange: body b goes to rank b * world_size // numBodies
+    (contiguous runs, equal counts +-1).  Returns (verts, tet_ids, vert_ids, tet_index): the rank's sub-mesh with vertices
+    renumbered 0..n-1 in ascending caller order, the caller's vertex id of each, and the caller's tet index of each local tet
+    (ascending, so every body keeps the reference's sweep order).  Positions are the caller's float32 values untouched, so
+    each body's result is bit-identical to the one it has in the unsharded scene."""
+    from . import _capi
+    v = np.asarray(verts, np.float32).reshape(-1, 3)
+    t = np.asarray(tet_ids, np.int32).reshape(-1, 4)
+    comp, nb = _capi.connected_components(t, len(v))
+    owner = (comp.astype(np.int64) * world_size) // max(nb, 1)
+    vert_ids = np.flatnonzero(owner == rank).astype(np.int32)
+    tet_index = np.flatnonzero(owner[t[:, 0]] == rank).astype(np.int32)
+    remap = np.full(len(v), -1, np.int32)
+    remap[vert_ids] = np.arange(len(vert_ids), dtype=np.int32)
+    return v[vert_ids].reshape(-1).copy(), remap[t[tet_index]].reshape(-1).astype(np.int32), vert_ids, tet_index
