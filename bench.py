@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--cells", default="407,64,64", help="beam cells x,y,z (default = 10,002,432 tets)")
     ap.add_argument("--substeps", type=int, default=20, help="substeps per step (frame)")
     ap.add_argument("--iters", type=int, default=1)
-    ap.add_argument("--cluster-size", type=int, default=512, help="tets per tile (512 measured fastest on one GPU, profiles/r1_tile_sweep.txt)")
+    ap.add_argument("--cluster-size", type=int, default=0, help="tets per tile (default 512 for the NH tile kernel -- measured fastest, profiles/r2_tile_experiments.txt -- and 256 for the polar tile kernel)")
     ap.add_argument("--no-reorder", action="store_true")
     ap.add_argument("--atomic", action="store_true", help="deterministic=0: REDG flush instead of per-tile partials")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
@@ -63,6 +63,9 @@ def parse():
                          "NVLink); auto = peer (measured fastest, profiles/r2_peer_experiments.txt), falling back to halo without peer access")
     ap.add_argument("--no-parity", action="store_true", help="skip the N-rank-vs-1-rank check at N > 1")
     ap.add_argument("--no-configs", action="store_true", help="skip the per-config rates (BASELINE configs 1, 2, 3, 5) at N = 1")
+    ap.add_argument("--workload", default="beam", choices=["beam", "polar"],
+                    help="beam: BASELINE config 4 (NH Jacobi tile kernel, the headline); polar: the SoftBodyGPU polar-decomposition "
+                         "Jacobi (BASELINE config 2's algorithm) on the same 10M-tet beam, tiled kernels, roofline 148 B/tet + 32 B/vertex")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -126,10 +129,11 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_reference_run(verts, tets, substeps, dt):
-    """The reference's CPU algorithm (sequential Gauss-Seidel, src/Softbody.js:195-240) via the C restatement."""
+def cpu_reference_run(verts, tets, substeps, dt, polar=False):
+    """The reference's CPU algorithm (sequential Gauss-Seidel, src/Softbody.js:195-240) via the C restatement; for the polar
+    workload the C restatement of the WebGL passes (src/SoftbodyGPU.js:59-376)."""
     import oracle
-    ref = oracle.SoftBodyOracle(verts, tets)
+    ref = oracle.PolarOracle(verts, tets) if polar else oracle.SoftBodyOracle(verts, tets)
     t0 = time.perf_counter()
     for _ in range(substeps):
         ref.simulate(dt)
@@ -312,6 +316,11 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.exchange == "auto":
         args.exchange = "peer"
+    polar = args.workload == "polar"
+    if not args.cluster_size:
+        args.cluster_size = 256 if polar else 512
+    if polar:
+        args.no_configs = True
     cells = tuple(int(c) for c in args.cells.split(","))
     if args.scaling == "weak":
         cells = (cells[0] * max(world, 1), cells[1], cells[2])
@@ -320,6 +329,9 @@ def main():
 
     mesh_name = "beam %dx%dx%d cells Kuhn-split" % cells
     workload = "%s, NH Jacobi iters=%d, dt=1/%d, %d substeps/step" % (mesh_name, args.iters, round(1.0 / dt), args.substeps)
+    if polar:
+        workload = "%s, polar-decomposition shape-matching Jacobi (SoftBodyGPU, src/SoftbodyGPU.js:59-376), dt=1/%d, %d substeps/step" % (
+            mesh_name, round(1.0 / dt), args.substeps)
 
     # ------------------------------------------------------------------ reference arm (CPU only)
     if args.impl == "reference":
@@ -328,7 +340,7 @@ def main():
         verts, tets = mesh.make_beam(cells)
         M = tets.size // 4
         import oracle
-        ref = oracle.SoftBodyOracle(verts, tets)
+        ref = oracle.PolarOracle(verts, tets) if polar else oracle.SoftBodyOracle(verts, tets)
         per_step = 1  # bounded sample: 1 substep of the full mesh per bench step
         for _ in range(args.warmup):
             ref.simulate(dt)
@@ -342,9 +354,12 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps,
                 "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64-expr/f32-store",
                 "data": "synthetic",
-                "config": {"workload": "%s, NH sequential Gauss-Seidel in tet order (the reference's own algorithm, src/Softbody.js:206-208), "
-                                       "dt=1/%d, 1 substep/step" % (mesh_name, round(1.0 / dt)),
-                           "algorithm": "sequential Gauss-Seidel (reference); the GPU arm runs Jacobi on the same mesh -- see configs/jacobi_vs_gs in the GPU arm's line",
+                "config": {"workload": ("%s, polar-decomposition Jacobi (the 7 passes of src/SoftbodyGPU.js restated in C, f32), dt=1/%d, 1 substep/step"
+                                        if polar else
+                                        "%s, NH sequential Gauss-Seidel in tet order (the reference's own algorithm, src/Softbody.js:206-208), "
+                                        "dt=1/%d, 1 substep/step") % (mesh_name, round(1.0 / dt)),
+                           "algorithm": ("polar-decomposition Jacobi, same algorithm as the GPU arm" if polar else
+                                         "sequential Gauss-Seidel (reference); the GPU arm runs Jacobi on the same mesh -- see configs/jacobi_vs_gs in the GPU arm's line"),
                            "tets": M, "verts": verts.size // 3},
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
                                  "host_cores": os.cpu_count(), "dragon_substeps_per_s": cpu_dragon_substeps_per_s()},
@@ -382,6 +397,10 @@ def main():
     torch.cuda.set_stream(stream)
 
     def make_body(nccl_id):
+        if polar:
+            assert world == 1, "the polar workload is single-GPU (multi-GPU tet partitioning exists for the NH Jacobi solver only)"
+            return ts.SoftBodyGPU(verts, tets, None, pp, arithmetic="fast", cluster_size=args.cluster_size, reorder=not args.no_reorder,
+                                  device=local_rank, stream=stream.cuda_stream)
         return ts.SoftBody(verts, tets, None, pp, solver="jacobi", arithmetic="fast", iters=args.iters,
                            cluster_size=args.cluster_size, reorder=not args.no_reorder, deterministic=not args.atomic,
                            device=local_rank, stream=stream.cuda_stream, rank=rank, world_size=world,
@@ -473,10 +492,13 @@ def main():
     value = proj_per_step / (ms_step * 1e-3) / 1e6
 
     # ---- dominant kernel alone (roofline) ----
-    k_ms, k_bytes = body.time_kernel(50)
+    try:
+        k_ms, k_bytes = body.time_kernel(10 if polar else 50)
+    except ts.TetSimError:      # a handle without a tile kernel (TETSIM_POLAR_CSR=1 comparison runs)
+        k_ms, k_bytes = float("nan"), 0
     peak, peak_src = load_peaks()
     achieved = k_bytes / (k_ms * 1e-3) / 1e9
-    kernel_key = "k_jacobi_tilesN<%d,2,2,%d>" % (args.cluster_size, 4 if args.cluster_size == 512 else 0)
+    kernel_key = "k_polar_tiles<%d>" % args.cluster_size if polar else "k_jacobi_tilesN<%d,2,2,%d>" % (args.cluster_size, 4 if args.cluster_size == 512 else 0)
     traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if world == 1 and os.path.exists(tp) and tuple(cells) == (407, 64, 64):
@@ -486,7 +508,8 @@ def main():
                 traffic, traffic_src = ent["dram_bytes_per_launch"], ent["source"]
         except Exception:
             traffic = None
-    roofline = {"kernel": "k_jacobi_tilesN<%d, 2 tets/thread> (persistent tile kernel, tetsim_b200/csrc/kernels_fast.cu)" % args.cluster_size, "bound": "hbm", "achieved": achieved,
+    roofline = {"kernel": ("k_polar_tiles<%d> (tiled polar shape matching, tetsim_b200/csrc/kernels_fast.cu)" if polar else
+                           "k_jacobi_tilesN<%d, 2 tets/thread> (persistent tile kernel, tetsim_b200/csrc/kernels_fast.cu)") % args.cluster_size, "bound": "hbm", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": k_bytes, "ms_per_launch": k_ms,
                 "share_of_step": k_ms * args.iters * args.substeps / ms_step,
@@ -569,7 +592,7 @@ def main():
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, sec = cpu_reference_run(verts, tets, args.cpu_substeps, dt)
+        v, sec = cpu_reference_run(verts, tets, args.cpu_substeps, dt, polar)
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "host_cores": os.cpu_count(),
                "dragon_substeps_per_s": cpu_dragon_substeps_per_s(),
                "sample": "%d substeps of the full %d-tet mesh (%.1f s), sequential Gauss-Seidel C restatement of "

@@ -370,6 +370,59 @@ def test_polar_fast_within_tolerance(dragon):
     assert errs[50] <= 1e-4 and errs[100] <= 1e-3, errs
 
 
+@pytest.mark.parametrize("bug", [True, False])
+def test_polar_tiled_kernels(dragon, bug, monkeypatch):
+    """FAST arithmetic runs the TILED polar kernels (k_polar_tiles + k_polar_vertex_tiles, post fused with the next
+    substep's integrate inside tetsim_step); TETSIM_POLAR_CSR=1 keeps the reference's gather structure.  Both must stay
+    within the tolerance of the polar oracle, agree with each other, and expose the same elems / quats state."""
+    p = dict(ts.DEFAULT_PHYSICS_PARAMS, numSubsteps=20)
+    tiled = new_body(dragon, cls=ts.SoftBodyGPU, params=dict(p), arithmetic="fast", reference_table_bug=bug, cluster_size=128)
+    assert tiled.info()["launchesPerSubstep"] == 2 and tiled.info()["numClusters"] >= 30
+    monkeypatch.setenv("TETSIM_POLAR_CSR", "1")
+    csr = new_body(dragon, cls=ts.SoftBodyGPU, params=dict(p), arithmetic="fast", reference_table_bug=bug)
+    assert csr.info()["launchesPerSubstep"] == 3
+    ref = oracle.PolarOracle(dragon["tet_verts"], dragon["tet_ids"], reference_table_bug=bug)
+    for frame in range(3):
+        tiled.step(p)                      # one graph of 20 substeps, fused vertex kernel
+        for _ in range(20):
+            csr.simulate(DT1200, p)
+            ref.simulate(DT1200)
+        if frame == 1:
+            assert vec_rel_err(tiled.pos, ref.pos) <= 1e-4 and vec_rel_err(csr.pos, ref.pos) <= 1e-4
+    assert vec_rel_err(tiled.pos, csr.pos) <= 2e-4
+    assert vec_rel_err(tiled.pos, ref.pos) <= 1e-3
+    assert np.max(np.abs(tiled.quats - ref.quat)) <= 1e-3 and np.max(np.abs(tiled.elems - ref.rest)) <= 1e-3
+    assert np.max(np.abs(tiled.vel - ref.vel)) <= 0.5 and np.isfinite(tiled.vel).all()
+    # the table quirk (src/SoftbodyGPU.js:568) moves exactly the particle it affects: tetIds[0], whose corner 0 of tet 0 is dropped
+    if bug:
+        monkeypatch.delenv("TETSIM_POLAR_CSR")
+        a = new_body(dragon, cls=ts.SoftBodyGPU, params=dict(p), arithmetic="fast", reference_table_bug=True, cluster_size=128)
+        b = new_body(dragon, cls=ts.SoftBodyGPU, params=dict(p), arithmetic="fast", reference_table_bug=False, cluster_size=128)
+        a.simulate(DT1200, p)
+        b.simulate(DT1200, p)
+        moved = np.flatnonzero(np.any(a.pos.reshape(-1, 3) != b.pos.reshape(-1, 3), axis=1))
+        assert moved.tolist() == [int(dragon["tet_ids"][0])]
+
+
+def test_polar_tiled_beam_with_floor():
+    v, t = mesh.make_beam((24, 6, 6), h=0.05, y0=0.004, jitter=0.2)   # gravity enters a substep late in this variant: 60 substeps drop 12 mm
+    p = dict(ts.DEFAULT_PHYSICS_PARAMS, numSubsteps=20)
+    ref = oracle.PolarOracle(v, t)
+    sb = ts.SoftBodyGPU(v, t, None, dict(p), arithmetic="fast", cluster_size=256)
+    for _ in range(3):
+        sb.step(p)
+        for _ in range(20):
+            ref.simulate(DT1200)
+    assert np.any(ref.pos.reshape(-1, 3)[:, 1] == 0.0)
+    assert vec_rel_err(sb.pos.reshape(-1, 3) + [0, 1, 0], ref.pos.reshape(-1, 3) + [0, 1, 0]) <= 1e-4
+    ms, nbytes = sb.time_kernel(3)
+    assert ms > 0 and nbytes == 148 * (t.size // 4) + 32 * (v.size // 3)
+    x = sb.pos.copy()
+    sb.time_kernel(2)                      # timing must leave the state untouched
+    assert_bit_equal(sb.pos, x, "state after time_kernel")
+    assert_bit_equal(sb.elems, sb.elems, "elems readable")
+
+
 def test_polar_long_run_with_contact(dragon):
     m = _low_dragon(dragon, -0.40)
     ref = oracle.PolarOracle(m["tet_verts"], m["tet_ids"])

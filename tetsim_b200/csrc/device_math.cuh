@@ -25,6 +25,11 @@ struct SubstepParams {
     double grab[3];
     int grabId;
     int pad_;
+    // derived, reference (f64) flavour: the per-launch constants of applyToElem / solveElem / the velocity update, formed ONCE
+    // with the same IEEE operations in the same order as the reference forms them per tet / per call (so the result is the
+    // same double): compliance / dt / dt (src/Softbody.js:187), volCompliance / devCompliance (:161), 1.0 / dt (:239).
+    // Each f64 division on the device is a ~25-instruction dependent sequence on every tet's critical path otherwise.
+    double alphaDevD, alphaVolD, volOverDevD, invDtD;
     // derived, f32 flavour
     float dtF, gDt, invDt, fric, alphaDev, alphaVol, gammaVol, gravityF, frictionF;
     float loF[3], hiF[3], grabF[3];
@@ -76,8 +81,8 @@ __device__ __forceinline__ void ex_matmul3(float *dst, const float *A, const flo
         ex_axpy3(dst + 3 * k, A + 6, b2);
     }
 }
-__device__ __forceinline__ void ex_apply(ExactScratch &s, float *y, const float *w4, double C, double compliance,
-                                         double dt, double irv) {  // applyToElem :168-193
+__device__ __forceinline__ void ex_apply(ExactScratch &s, float *y, const float *w4, double C, double complianceOverDt2,
+                                         double irv) {  // applyToElem :168-193; complianceOverDt2 = compliance / dt / dt
     if (C == 0.0) return;
     float *g = s.g;
     g[0] = 0.0f; g[1] = 0.0f; g[2] = 0.0f;
@@ -88,14 +93,14 @@ __device__ __forceinline__ void ex_apply(ExactScratch &s, float *y, const float 
 #pragma unroll
     for (int i = 0; i < 4; i++) w += ex_len2(g + 3 * i) * (double)w4[i];
     if (w == 0.0) return;
-    double alpha = compliance / dt / dt * irv;
+    double alpha = complianceOverDt2 * irv;
     double dlambda = -C / (w + alpha);
 #pragma unroll
     for (int i = 0; i < 4; i++) ex_axpy3(y + 3 * i, g + 3 * i, dlambda * (double)w4[i]);
 }
 // Returns vol - 1 (the volError term, :163).
-__device__ __forceinline__ double nh_solve_exact(float *y, const float *w4, const float *Q, float irv, double dt,
-                                                 double devC, double volC) {
+__device__ __forceinline__ double nh_solve_exact(float *y, const float *w4, const float *Q, float irv, double alphaDevD,
+                                                 double alphaVolD, double volOverDevD) {
     ExactScratch s;
     ex_diff3(s.P + 0, y + 3, y);
     ex_diff3(s.P + 3, y + 6, y);
@@ -111,7 +116,7 @@ __device__ __forceinline__ double nh_solve_exact(float *y, const float *w4, cons
         ex_axpy3(g, s.F + 3, r_s_inv * (double)Q[3 + (k - 1)]);
         ex_axpy3(g, s.F + 6, r_s_inv * (double)Q[6 + (k - 1)]);
     }
-    ex_apply(s, y, w4, r_s, devC, dt, (double)irv);
+    ex_apply(s, y, w4, r_s, alphaDevD, (double)irv);
 
     ex_diff3(s.P + 0, y + 3, y);
     ex_diff3(s.P + 3, y + 6, y);
@@ -129,8 +134,8 @@ __device__ __forceinline__ double nh_solve_exact(float *y, const float *w4, cons
         ex_axpy3(g, s.dF + 6, (double)Q[6 + (k - 1)]);
     }
     double vol = ex_det3(s.F);
-    double C = vol - 1.0 - volC / devC;
-    ex_apply(s, y, w4, C, volC, dt, (double)irv);
+    double C = vol - 1.0 - volOverDevD;
+    ex_apply(s, y, w4, C, alphaVolD, (double)irv);
     return vol - 1.0;
 }
 
@@ -344,8 +349,34 @@ __device__ __forceinline__ Q4 pl_extract_rotation(const V3 A[3], Q4 q) {  // ext
     }
     return q;
 }
+// FAST flavour of extractRotation for the tiled kernel: the three rotated basis vectors are the columns of R(q), formed
+// directly from the quaternion's products (same polynomial as three Rotate() calls, a quarter of the instructions), one
+// reciprocal per iteration, and the loop leaves as soon as the increment is at the float32 noise floor: the reference's own
+// exit `w < 1e-9` (:131) is unreachable in float32 once |A| ~ edge^2 (the residual rotation of a converged iterate is
+// ~1e-7), so its last five or six of nine iterations only stir rounding noise.  kPolarEps is the measured trade-off:
+// tests/test_parity_gpu.py keeps the result within the polar tolerance of the oracle (which always runs the shader's loop).
+constexpr float kPolarEps = 1.0e-7f;
+__device__ __forceinline__ Q4 pl_extract_rotation_fast(const V3 A[3], Q4 q) {
+    for (int iter = 0; iter < 9; iter++) {
+        const float xx = q.x * q.x, yy = q.y * q.y, zz = q.z * q.z, xy = q.x * q.y, xz = q.x * q.z, yz = q.y * q.z;
+        const float wx = q.w * q.x, wy = q.w * q.y, wz = q.w * q.z;
+        const V3 X = {1.0f - 2.0f * (yy + zz), 2.0f * (xy + wz), 2.0f * (xz - wy)};
+        const V3 Y = {2.0f * (xy - wz), 1.0f - 2.0f * (xx + zz), 2.0f * (yz + wx)};
+        const V3 Z = {2.0f * (xz + wy), 2.0f * (yz - wx), 1.0f - 2.0f * (xx + yy)};
+        const V3 num = pl_add(pl_add(pl_cross(X, A[0]), pl_cross(Y, A[1])), pl_cross(Z, A[2]));
+        const float den = pl_dot(X, A[0]) + pl_dot(Y, A[1]) + pl_dot(Z, A[2]) + 0.000000001f;
+        const V3 omega = pl_mul(num, __fdividef(1.0f, fabsf(den)));
+        const float w2 = pl_dot(omega, omega);
+        if (w2 < kPolarEps * kPolarEps) break;
+        const float rw = rsqrtf(w2), w = w2 * rw, half = w * 0.5f;
+        const float s = __sinf(half) * rw, c = __sinf(half + 1.57f);   // the shader's cosine, :108
+        const Q4 dq = {omega.x * s, omega.y * s, omega.z * s, c};
+        q = pl_qmul(dq, q);
+    }
+    return q;
+}
 // K3 + K4 for one tet: cur[4] current corner positions, last[4] in/out goal corners, quat in/out.
-template <bool EXACT>
+template <bool EXACT, bool TILED = false>
 __device__ __forceinline__ void polar_solve(const V3 cur[4], V3 last[4], Q4 &quat) {
     V3 cc = pl_mul(pl_add(pl_add(pl_add(cur[0], cur[1]), cur[2]), cur[3]), 0.25f);
     V3 lc = pl_mul(pl_add(pl_add(pl_add(last[0], last[1]), last[2]), last[3]), 0.25f);
@@ -358,7 +389,7 @@ __device__ __forceinline__ void polar_solve(const V3 cur[4], V3 last[4], Q4 &qua
         A[2] = pl_add(A[2], pl_mul(c, l.z));
     }
     Q4 ident = {0.0f, 0.0f, 0.0f, 1.0f};
-    Q4 rot = pl_extract_rotation<EXACT>(A, ident);
+    Q4 rot = (!EXACT && TILED) ? pl_extract_rotation_fast(A, ident) : pl_extract_rotation<EXACT>(A, ident);
     Q4 qOld = quat;
     Q4 qNew = pl_normalize<EXACT>(pl_qmul(rot, qOld));  // :181
     quat = qNew;

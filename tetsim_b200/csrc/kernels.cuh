@@ -127,7 +127,7 @@ __device__ __forceinline__ void post_vertex(int i, float4 &x, const float4 prev,
             x.z = f32((double)x.z + (double)Fz * k);
         }
         if (i == sp->grabId) { x.x = f32(sp->grab[0]); x.y = f32(sp->grab[1]); x.z = f32(sp->grab[2]); }
-        double inv = 1.0 / dt;
+        double inv = sp->invDtD;
         v.x = f32(((double)x.x - (double)prev.x) * inv);
         v.y = f32(((double)x.y - (double)prev.y) * inv);
         v.z = f32(((double)x.z - (double)prev.z) * inv);
@@ -173,7 +173,7 @@ __device__ __forceinline__ double gs_solve_one(float4 *x4, int4 id, float4 A, fl
     if (EXACT) {
         float y[12] = {p0.x, p0.y, p0.z, p1.x, p1.y, p1.z, p2.x, p2.y, p2.z, p3.x, p3.y, p3.z};
         const float w4[4] = {p0.w, p1.w, p2.w, p3.w};
-        volm1 = nh_solve_exact(y, w4, Q, C.y, sp->dt, sp->devCompliance, sp->volCompliance);
+        volm1 = nh_solve_exact(y, w4, Q, C.y, sp->alphaDevD, sp->alphaVolD, sp->volOverDevD);
         p0.x = y[0]; p0.y = y[1]; p0.z = y[2];
         p1.x = y[3]; p1.y = y[4]; p1.z = y[5];
         p2.x = y[6]; p2.y = y[7]; p2.z = y[8];
@@ -308,7 +308,7 @@ __global__ void k_jacobi_tet(int M, const float4 *__restrict__ x4, const int4 *_
     if (EXACT) {
         float y[12] = {p0.x, p0.y, p0.z, p1.x, p1.y, p1.z, p2.x, p2.y, p2.z, p3.x, p3.y, p3.z};
         const float w4[4] = {p0.w, p1.w, p2.w, p3.w};
-        vm1 = nh_solve_exact(y, w4, Q, c.y, sp->dt, sp->devCompliance, sp->volCompliance);
+        vm1 = nh_solve_exact(y, w4, Q, c.y, sp->alphaDevD, sp->alphaVolD, sp->volOverDevD);
         d0 = make_float4(f32((double)y[0] - (double)p0.x), f32((double)y[1] - (double)p0.y), f32((double)y[2] - (double)p0.z), 0.f);
         d1 = make_float4(f32((double)y[3] - (double)p1.x), f32((double)y[4] - (double)p1.y), f32((double)y[5] - (double)p1.z), 0.f);
         d2 = make_float4(f32((double)y[6] - (double)p2.x), f32((double)y[7] - (double)p2.y), f32((double)y[8] - (double)p2.z), 0.f);

@@ -853,6 +853,169 @@ void launch_peer_reduce(cudaStream_t s, const PeerArgs &a) {
 }
 
 // =================================================================================================
+// Tiled polar-decomposition shape matching (SoftBodyGPU, src/SoftbodyGPU.js:59-376) -- the throughput form of BASELINE
+// config 2.  Same tiling as the Neo-Hookean tile kernel (ClusterPlan: Hilbert-ordered tiles, vertex tile staged in shared
+// memory, grouped-row corner buffer); per tet it streams what the reference keeps in its `elems` / `quats` render targets:
+//   tile block, T * 96 B, plane-major:  R0 R1 R2 (goal corners, 12 floats, read AND written back -- the reference rotates
+//   its rest tet incrementally, :253-262), Qt (quaternion, read + written), C (4 vertex slots + 4 corner destinations),
+//   E (x = rest volume V, negative = "drop corner 0", the reference's table quirk :568; 0 = unused record slot).
+// K3 + K4 run per tet in registers (polar_solve), every corner's goal * V and V go to the corner buffer (STS.128, .w = V --
+// the reference's vec4(goal, V), :259-262), per-tile-vertex sums leave as one float4 partial (sum goal V, sum V).  K5's
+// per-particle gather over <= 36 scattered texels becomes a sum of ~2.4 tile partials in k_polar_vertex_tiles, so the
+// 64 B / tet `elems` state is never re-read through a pointer chase.  Algorithmic bytes:
+// 148 B / tet + 32 B / vertex per substep.
+// =================================================================================================
+template <int T>
+__global__ void __launch_bounds__(T) k_polar_tiles(PolarTileArgs a) {
+    extern __shared__ __align__(128) unsigned char psm[];
+    const int tile = blockIdx.x, tid = threadIdx.x;
+    float4 *sx = reinterpret_cast<float4 *>(psm);                                   // [maxTileVertsPad]
+    unsigned char *sdx = psm + (size_t)a.maxTileVertsPad * 16;                      // [(maxTileEntries + 1) * 16]
+    unsigned char *sm = sdx + (((size_t)a.maxTileEntries + 1) * 16 + 127) / 128 * 128;  // metadata block
+    const uint4 *mg = reinterpret_cast<const uint4 *>(a.meta + (size_t)a.metaOff[tile] * 16);
+    const int mlen = (int)(a.metaOff[tile + 1] - a.metaOff[tile]);
+    for (int i = tid; i < mlen; i += T) reinterpret_cast<uint4 *>(sm)[i] = __ldg(mg + i);
+    // this tet's record (coalesced LDG.128 per plane), in flight while the vertex tile is gathered
+    unsigned char *tb = a.tets + (size_t)tile * T * 96;
+    const float4 r0 = ldg_stream4(tb + tid * 16), r1 = ldg_stream4(tb + T * 16 + tid * 16), r2 = ldg_stream4(tb + T * 32 + tid * 16);
+    const float4 qt = ldg_stream4(tb + T * 48 + tid * 16), cc = ldg_stream4(tb + T * 64 + tid * 16), ee = ldg_stream4(tb + T * 80 + tid * 16);
+    __syncthreads();
+    const int v0 = reinterpret_cast<const int *>(sm)[0], nl = reinterpret_cast<const int *>(sm)[1];
+    const int *ids = reinterpret_cast<const int *>(sm + reinterpret_cast<const int *>(sm)[3]);
+    for (int j = tid; j < nl; j += T) sx[j] = a.x4[ids[j]];
+    __syncthreads();
+    if (ee.x != 0.0f) {
+        const unsigned s01 = __float_as_uint(cc.x), s23 = __float_as_uint(cc.y), d01 = __float_as_uint(cc.z), d23 = __float_as_uint(cc.w);
+        const unsigned char *sxb = reinterpret_cast<const unsigned char *>(sx);
+        const float4 p0 = *reinterpret_cast<const float4 *>(sxb + (s01 & 0xffffu)), p1 = *reinterpret_cast<const float4 *>(sxb + (s01 >> 16));
+        const float4 p2 = *reinterpret_cast<const float4 *>(sxb + (s23 & 0xffffu)), p3 = *reinterpret_cast<const float4 *>(sxb + (s23 >> 16));
+        const V3 cur[4] = {{p0.x, p0.y, p0.z}, {p1.x, p1.y, p1.z}, {p2.x, p2.y, p2.z}, {p3.x, p3.y, p3.z}};
+        V3 last[4] = {{r0.x, r0.y, r0.z}, {r0.w, r1.x, r1.y}, {r1.z, r1.w, r2.x}, {r2.y, r2.z, r2.w}};
+        Q4 q = {qt.x, qt.y, qt.z, qt.w};
+        polar_solve<false, true>(cur, last, q);
+        reinterpret_cast<float4 *>(tb)[tid] = make_float4(last[0].x, last[0].y, last[0].z, last[1].x);
+        reinterpret_cast<float4 *>(tb + T * 16)[tid] = make_float4(last[1].y, last[1].z, last[2].x, last[2].y);
+        reinterpret_cast<float4 *>(tb + T * 32)[tid] = make_float4(last[2].z, last[3].x, last[3].y, last[3].z);
+        reinterpret_cast<float4 *>(tb + T * 48)[tid] = make_float4(q.x, q.y, q.z, q.w);
+        const float V = fabsf(ee.x), V0 = ee.x < 0.0f ? 0.0f : V;   // corner 0 of tet 0 is dropped from its particle's average (:568)
+        *reinterpret_cast<float4 *>(sdx + (d01 & 0xffffu)) = make_float4(last[0].x * V0, last[0].y * V0, last[0].z * V0, V0);
+        *reinterpret_cast<float4 *>(sdx + (d01 >> 16)) = make_float4(last[1].x * V, last[1].y * V, last[1].z * V, V);
+        *reinterpret_cast<float4 *>(sdx + (d23 & 0xffffu)) = make_float4(last[2].x * V, last[2].y * V, last[2].z * V, V);
+        *reinterpret_cast<float4 *>(sdx + (d23 >> 16)) = make_float4(last[3].x * V, last[3].y * V, last[3].z * V, V);
+    }
+    __syncthreads();
+    const uint16_t *gbase = reinterpret_cast<const uint16_t *>(sm + 16);
+    for (int j = tid; j < nl; j += T) {
+        const int val = sm[a.metaValOff + j];
+        const unsigned char *p = sdx + gbase[j >> 3] + ((j & 7) << 4);
+        float ax = 0.0f, ay = 0.0f, az = 0.0f, aw = 0.0f;
+        for (int i = 0; i < val; i++, p += 144) {
+            const float4 d = *reinterpret_cast<const float4 *>(p);
+            ax += d.x; ay += d.y; az += d.z; aw += d.w;
+        }
+        a.part[v0 + j] = make_float4(ax, ay, az, aw);
+    }
+}
+
+size_t polar_tiles_smem(const PolarTileArgs &a) {
+    return (size_t)a.maxTileVertsPad * 16 + (((size_t)a.maxTileEntries + 1) * 16 + 127) / 128 * 128 + (size_t)a.metaStride;
+}
+void launch_polar_tiles(cudaStream_t s, int clusterSize, const PolarTileArgs &a) {
+    if (a.numTiles <= 0) return;
+    const size_t smem = polar_tiles_smem(a);
+#define PT_CASE(T_)                                                                                                   \
+    case T_: {                                                                                                        \
+        static size_t set[64];                                                                                        \
+        const int dev = current_device();                                                                             \
+        if (set[dev] != smem) { cudaFuncSetAttribute(k_polar_tiles<T_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set[dev] = smem; } \
+        k_polar_tiles<T_><<<a.numTiles, T_, smem, s>>>(a);                                                            \
+        break;                                                                                                        \
+    }
+    switch (clusterSize) { PT_CASE(128) PT_CASE(256) PT_CASE(512) default: break; }
+#undef PT_CASE
+}
+
+// K5 (average of the tile partials) + K6 (grab, bounds, floor + friction) + K7 (velocity, late gravity) per particle,
+// src/SoftbodyGPU.js:272-376; mode 2 also runs K1 + K2 of the NEXT substep (prev = pos; pos += vel * dt), the velocity
+// then never leaves the registers.
+template <int MODE>
+__global__ void k_polar_vertex_tiles(int N, float4 *__restrict__ x4, float4 *__restrict__ prev4, float4 *__restrict__ vel4,
+                                     const int *__restrict__ vpStart, const int *__restrict__ vpSlot,
+                                     const float4 *__restrict__ part, const int *__restrict__ vertId,
+                                     const SubstepParams *__restrict__ sp) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float sx = 0.0f, sy = 0.0f, sz = 0.0f, sw = 0.0f;
+    for (int j = vpStart[i]; j < vpStart[i + 1]; j++) {
+        const float4 s = ldg4(part + vpSlot[j]);
+        sx += s.x; sy += s.y; sz += s.z; sw += s.w;
+    }
+    float4 x = x4[i];
+    const float4 p = prev4[i];
+    const float inv = 1.0f / sw;   // a particle no tet references gets 0 / 0 = NaN, like the shader's unused texels
+    x.x = sx * inv; x.y = sy * inv; x.z = sz * inv;
+    if ((vertId ? vertId[i] : i) == sp->grabId) { x.x = sp->grabF[0]; x.y = sp->grabF[1]; x.z = sp->grabF[2]; }
+    x.x = fminf(fmaxf(x.x, sp->loF[0]), sp->hiF[0]);
+    x.y = fminf(fmaxf(x.y, sp->loF[1]), sp->hiF[1]);
+    x.z = fminf(fmaxf(x.z, sp->loF[2]), sp->hiF[2]);
+    if (x.y < 0.0f) {
+        x.y = 0.0f;
+        const float fr = fminf(1.0f, sp->dtF * sp->frictionF);
+        x.x = fmaf(p.x - x.x, fr, x.x);
+        x.z = fmaf(p.z - x.z, fr, x.z);
+    }
+    const float dt = sp->dtF, idt = sp->invDt;
+    float4 v = make_float4((x.x - p.x) * idt, fmaf(sp->gravityF, dt, (x.y - p.y) * idt), (x.z - p.z) * idt, 0.0f);
+    if (MODE == 2) {
+        prev4[i] = x;
+        x.x = fmaf(v.x, dt, x.x); x.y = fmaf(v.y, dt, x.y); x.z = fmaf(v.z, dt, x.z);
+    } else {
+        vel4[i] = v;
+    }
+    x4[i] = x;
+}
+void launch_polar_vertex_tiles(cudaStream_t s, int N, int mode, float4 *x4, float4 *prev4, float4 *vel4, const int *vpStart,
+                               const int *vpSlot, const float4 *part, const int *vertId, const SubstepParams *sp) {
+    if (N <= 0) return;
+    if (mode == 2) k_polar_vertex_tiles<2><<<cdiv(N, 256), 256, 0, s>>>(N, x4, prev4, vel4, vpStart, vpSlot, part, vertId, sp);
+    else k_polar_vertex_tiles<1><<<cdiv(N, 256), 256, 0, s>>>(N, x4, prev4, vel4, vpStart, vpSlot, part, vertId, sp);
+}
+
+// Tile blocks of the polar solver from the caller-order rest data: record r = tet order[r] (or an unused slot).
+template <int T>
+__global__ void k_build_polar_tiles(int numRecords, const int *__restrict__ order, const float4 *__restrict__ x4, const int4 *__restrict__ ids,
+                                    const float *__restrict__ irv, const uint4 *__restrict__ aux, int dropTet0Corner0,
+                                    unsigned char *__restrict__ tets) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= numRecords) return;
+    const int tile = r / T, t = r % T;
+    unsigned char *tb = tets + (size_t)tile * T * 96;
+    const int e = order[r];
+    float4 R0 = make_float4(0.f, 0.f, 0.f, 0.f), R1 = R0, R2 = R0, Q = make_float4(0.f, 0.f, 0.f, 1.f), E = R0;
+    if (e >= 0) {
+        const int4 id = ids[e];
+        const float4 a0 = x4[id.x], a1 = x4[id.y], a2 = x4[id.z], a3 = x4[id.w];
+        R0 = make_float4(a0.x, a0.y, a0.z, a1.x); R1 = make_float4(a1.y, a1.z, a2.x, a2.y); R2 = make_float4(a2.z, a3.x, a3.y, a3.z);
+        const float V = __fdiv_rn(1.0f, irv[e]);   // the shader's 1.0 / invRestVolume, :220
+        E.x = (dropTet0Corner0 && e == 0) ? -V : V;
+    }
+    reinterpret_cast<float4 *>(tb)[t] = R0;
+    reinterpret_cast<float4 *>(tb + T * 16)[t] = R1;
+    reinterpret_cast<float4 *>(tb + T * 32)[t] = R2;
+    reinterpret_cast<float4 *>(tb + T * 48)[t] = Q;
+    reinterpret_cast<uint4 *>(tb + T * 64)[t] = aux[r];
+    reinterpret_cast<float4 *>(tb + T * 80)[t] = E;
+}
+void launch_build_polar_tiles(cudaStream_t s, int clusterSize, int numRecords, const int *order, const float4 *x4, const int4 *ids,
+                              const float *irv, const uint4 *aux, int dropTet0Corner0, unsigned char *tets) {
+    if (numRecords <= 0) return;
+    const int g = cdiv(numRecords, 256);
+    if (clusterSize == 128) k_build_polar_tiles<128><<<g, 256, 0, s>>>(numRecords, order, x4, ids, irv, aux, dropTet0Corner0, tets);
+    else if (clusterSize == 256) k_build_polar_tiles<256><<<g, 256, 0, s>>>(numRecords, order, x4, ids, irv, aux, dropTet0Corner0, tets);
+    else k_build_polar_tiles<512><<<g, 256, 0, s>>>(numRecords, order, x4, ids, irv, aux, dropTet0Corner0, tets);
+}
+
+// =================================================================================================
 // Utility kernels
 // =================================================================================================
 __global__ void k_pack3(int N, const float4 *__restrict__ src, const int *__restrict__ perm, float *__restrict__ dst) {

@@ -144,6 +144,23 @@ constexpr int kPeerK = 16;                // most tile partials a rank may hold 
 void launch_peer_push(cudaStream_t, const PeerArgs &a);
 void launch_peer_reduce(cudaStream_t, const PeerArgs &a);
 
+// ---- FAST-only throughput path of the polar solver: tiled shape matching (kernels_fast.cu) ----
+struct PolarTileArgs {
+    const float4 *x4;
+    unsigned char *tets;            // [numTiles * T * 96] R0 R1 R2 Qt C E planes per tile (read and written)
+    const unsigned char *meta;      // the ClusterPlan's per-tile metadata blocks
+    const uint32_t *metaOff;
+    int numTiles, metaStride, metaValOff, maxTileVertsPad, maxTileEntries;
+    float4 *part;                   // per tile vertex: (sum goal * V, sum V)
+};
+void launch_polar_tiles(cudaStream_t, int clusterSize, const PolarTileArgs &a);
+size_t polar_tiles_smem(const PolarTileArgs &a);
+// mode 1: K5 + K6 + K7; mode 2: + K1 + K2 of the next substep
+void launch_polar_vertex_tiles(cudaStream_t, int N, int mode, float4 *x4, float4 *prev4, float4 *vel4, const int *vpStart,
+                               const int *vpSlot, const float4 *part, const int *vertId, const SubstepParams *sp);
+void launch_build_polar_tiles(cudaStream_t, int clusterSize, int numRecords, const int *order, const float4 *x4, const int4 *ids,
+                              const float *irv, const uint4 *aux, int dropTet0Corner0, unsigned char *tets);
+
 // ---- utility kernels (kernels_fast.cu) ----
 void launch_pack3(cudaStream_t, int N, const float4 *src, const int *perm, float *dst3);       // dst[perm[i]] = src[i].xyz
 void launch_unpack3(cudaStream_t, int N, const float *src3, const int *perm, float4 *dst, int keepW);

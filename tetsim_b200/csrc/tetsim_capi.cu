@@ -152,6 +152,7 @@ struct tetsim {
     DevBuf<float> invVal;
     bool clustered = false;
     // polar
+    bool polarTiled = false;               // FAST arithmetic: the tiled kernels (k_polar_tiles); else the reference's CSR gather order
     DevBuf<float4> rest, quat;
     DevBuf<int> tStart, tEnt;
     // per-launch parameters, staging, grab
@@ -258,6 +259,10 @@ void fill_substep_params(SubstepParams &s, double dt, const TetSimParams &p, int
     s.devCompliance = p.devCompliance; s.volCompliance = p.volCompliance;
     for (int c = 0; c < 3; c++) { s.lo[c] = p.worldBounds[c]; s.hi[c] = p.worldBounds[3 + c]; s.grab[c] = grab[c]; }
     s.grabId = grabId;
+    s.alphaDevD = p.devCompliance / dt / dt;   // ((compliance / dt) / dt), the reference's grouping
+    s.alphaVolD = p.volCompliance / dt / dt;
+    s.volOverDevD = p.volCompliance / p.devCompliance;
+    s.invDtD = 1.0 / dt;
     s.dtF = (float)dt;
     s.gDt = (float)(p.gravity * dt);
     s.invDt = (float)(1.0 / dt);
@@ -478,8 +483,43 @@ int build_jacobi_cluster(tetsim *h, const std::vector<float> &verts, const std::
     return TETSIM_OK;
 }
 
+// Tiled polar solver: the tiling (and with it the internal vertex numbering) is decided before the state is uploaded.
+int plan_polar_tiles(tetsim *h, const std::vector<float> &verts, const std::vector<int> &tetIds) {
+    std::vector<int> rankStart;
+    std::vector<int> order = solver_order(h->N, h->M, verts.data(), tetIds.data(), h->opt.reorder != 0, 1, rankStart);
+    std::string err;
+    const int T = h->opt.clusterSize < 128 ? 128 : h->opt.clusterSize;
+    if (!build_cluster_plan(h->N, h->M, tetIds.data(), order, rankStart, T, 0, 1, h->plan, err)) return fail(TETSIM_E_INVALID, err);
+    h->h_vertId = h->plan.localToCaller;
+    bool identity = (int)h->h_vertId.size() == h->N;
+    for (int i = 0; identity && i < h->N; i++) identity = h->h_vertId[i] == i;
+    if (identity) h->h_vertId.clear();
+    return TETSIM_OK;
+}
+
 int build_polar(tetsim *h, const std::vector<int> &tetIds) {
     cudaStream_t s = h->stream;
+    if (h->polarTiled) {
+        const ClusterPlan &P = h->plan;
+        const size_t nRec = (size_t)P.numClusters * P.T;
+        CK(h->order.upload(P.recordTet, s));
+        DevBuf<uint4> aux;
+        CK(aux.alloc(nRec));
+        if (nRec) CK(cudaMemcpyAsync(aux.p, P.recordAux.data(), nRec * sizeof(uint4), cudaMemcpyHostToDevice, s));
+        CK(h->tileTets.alloc(nRec * 96));
+        launch_build_polar_tiles(s, P.T, (int)nRec, h->order.p, h->x4.p, h->ids.p, h->irv.p, aux.p, h->opt.referenceTableBug != 0, h->tileTets.p);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(s));
+        aux.release();
+        CK(h->tileMeta.upload(P.tileMeta, s));
+        CK(h->metaOff.upload(P.metaOff, s));
+        CK(h->vpStart.upload(P.vpStart, s));
+        CK(h->vpSlot.upload(P.vpSlot, s));
+        CK(h->part.alloc(std::max<size_t>(P.clVerts.size(), 1)));
+        h->launchesPerSubstep = 2;
+        CK(cudaStreamSynchronize(s));
+        return TETSIM_OK;
+    }
     CornerTable t = build_reference_table(h->N, h->M, tetIds.data(), h->opt.referenceTableBug != 0, 36);
     CK(h->tStart.upload(t.start, s));
     CK(h->tEnt.upload(t.ent, s));
@@ -489,6 +529,15 @@ int build_polar(tetsim *h, const std::vector<int> &tetIds) {
     h->launchesPerSubstep = 3;
     CK(cudaStreamSynchronize(s));
     return TETSIM_OK;
+}
+
+PolarTileArgs polar_tile_args(const tetsim *h) {
+    const ClusterPlan &P = h->plan;
+    PolarTileArgs a{};
+    a.x4 = h->x4.p; a.tets = h->tileTets.p; a.meta = h->tileMeta.p; a.metaOff = h->metaOff.p;
+    a.numTiles = P.numClusters; a.metaStride = P.metaStride; a.metaValOff = P.metaValOff;
+    a.maxTileVertsPad = P.maxTileVertsPad; a.maxTileEntries = P.maxTileEntries; a.part = h->part.p;
+    return a;
 }
 
 // ---- substep scheduling --------------------------------------------------------------------------
@@ -682,6 +731,14 @@ int enqueue_substeps(tetsim *h, int count) {
                 }
                 break;
             case TETSIM_POLAR_JACOBI:
+                if (h->polarTiled) {
+                    if (step == 0) { K->polar_integrate(s, h->nInt, h->x4.p, h->prev4.p, h->vel4.p, sp); h->enq++; }
+                    launch_polar_tiles(s, h->plan.T, polar_tile_args(h));
+                    launch_polar_vertex_tiles(s, h->nInt, step + 1 < count ? 2 : 1, h->x4.p, h->prev4.p, h->vel4.p, h->vpStart.p,
+                                              h->vpSlot.p, h->part.p, vid, sp);
+                    h->enq += 2;
+                    break;
+                }
                 h->enq += 3;
                 K->polar_integrate(s, h->nInt, h->x4.p, h->prev4.p, h->vel4.p, sp);
                 K->polar_tet(s, h->M, h->x4.p, h->ids.p, h->rest.p, h->quat.p);
@@ -951,7 +1008,13 @@ int tetsim_create(const float *verts, int32_t numVerts, const int32_t *tetIds, i
 
         // ---- solver-specific build (decides the internal vertex numbering) ----
         int rc = TETSIM_OK;
+        {   // polar: the tiled kernels in FAST arithmetic unless a particle has more corners than the reference's 36 table slots
+            const char *csr = getenv("TETSIM_POLAR_CSR");
+            h->polarTiled = opt.solver == TETSIM_POLAR_JACOBI && opt.arithmetic == TETSIM_ARITH_FAST_F32 && h->maxValence <= 36 &&
+                            numTets > 0 && !(csr && csr[0] == '1');
+        }
         if (opt.solver == TETSIM_NH_GS_EXACT || opt.solver == TETSIM_NH_GS_COLOR) rc = build_gs(h, hv, ht);
+        else if (h->polarTiled) rc = plan_polar_tiles(h, hv, ht);
         else if (clustered) {
             if (opt.worldSize > 1 && opt.exchange != 2) {
                 if (!g_nccl.load()) return fail(TETSIM_E_NCCL, g_nccl.why);
@@ -1124,6 +1187,26 @@ int tetsim_get_polar_state(tetsim_t *h, float *rest12, float *quat4) {
     if (h->opt.solver != TETSIM_POLAR_JACOBI) return fail(TETSIM_E_STATE, "not a POLAR_JACOBI handle");
     DeviceGuard g(h->device);
     CK(cudaStreamSynchronize(h->stream));
+    if (h->polarTiled) {  // tile-major planes -> the caller's tet order
+        const ClusterPlan &P = h->plan;
+        const size_t T = (size_t)P.T;
+        std::vector<unsigned char> blocks(h->tileTets.bytes());
+        if (!blocks.empty()) CK(cudaMemcpy(blocks.data(), h->tileTets.p, blocks.size(), cudaMemcpyDeviceToHost));
+        for (size_t r = 0; r < P.recordTet.size(); r++) {
+            const int e = P.recordTet[r];
+            if (e < 0) continue;
+            const unsigned char *tb = blocks.data() + (r / T) * T * 96;
+            const size_t t = r % T;
+            if (rest12) {
+                const float *R0 = reinterpret_cast<const float *>(tb) + 4 * t, *R1 = reinterpret_cast<const float *>(tb + T * 16) + 4 * t,
+                            *R2 = reinterpret_cast<const float *>(tb + T * 32) + 4 * t;
+                float *o = rest12 + 12 * (size_t)e;
+                for (int k = 0; k < 4; k++) { o[k] = R0[k]; o[4 + k] = R1[k]; o[8 + k] = R2[k]; }
+            }
+            if (quat4) memcpy(quat4 + 4 * (size_t)e, tb + T * 48 + 16 * t, 16);
+        }
+        return TETSIM_OK;
+    }
     if (rest12) {
         std::vector<float4> r(4 * (size_t)h->M);
         if (h->M) CK(cudaMemcpy(r.data(), h->rest.p, h->rest.bytes(), cudaMemcpyDeviceToHost));
@@ -1268,7 +1351,39 @@ int tetsim_get_info(tetsim_t *h, TetSimInfo *info) {
 
 int tetsim_time_kernel(tetsim_t *h, int32_t reps, double *msPerLaunch, int64_t *algorithmicBytes) {
     if (!h || !msPerLaunch || reps < 1) return fail(TETSIM_E_INVALID, "bad argument");
-    if (!h->clustered) return fail(TETSIM_E_STATE, "tetsim_time_kernel times the clustered Jacobi tile kernel only");
+    if (h->polarTiled) {
+        // k_polar_tiles advances the per-tet goal corners and quaternions: snapshot them, time, put them back
+        DeviceGuard g(h->device);
+        cudaStream_t s = h->stream;
+        DevBuf<unsigned char> keep;
+        CK(keep.alloc(h->tileTets.n));
+        CK(cudaMemcpyAsync(keep.p, h->tileTets.p, h->tileTets.bytes(), cudaMemcpyDeviceToDevice, s));
+        const PolarTileArgs pa = polar_tile_args(h);
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        // every timed launch starts from the same state (a second launch on unchanged positions would find its rotation
+        // already extracted and leave the iteration early): restore the snapshot, untimed, before each one
+        launch_polar_tiles(s, h->plan.T, pa);
+        float ms = 0.f;
+        for (int r = 0; r < reps; r++) {
+            CK(cudaMemcpyAsync(h->tileTets.p, keep.p, h->tileTets.bytes(), cudaMemcpyDeviceToDevice, s));
+            CK(cudaEventRecord(e0, s));
+            launch_polar_tiles(s, h->plan.T, pa);
+            CK(cudaEventRecord(e1, s));
+            CK(cudaEventSynchronize(e1));
+            float one = 0.f;
+            CK(cudaEventElapsedTime(&one, e0, e1));
+            ms += one;
+        }
+        CK(cudaMemcpyAsync(h->tileTets.p, keep.p, h->tileTets.bytes(), cudaMemcpyDeviceToDevice, s));
+        CK(cudaStreamSynchronize(s));
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        CK(cudaGetLastError());
+        *msPerLaunch = (double)ms / reps;
+        if (algorithmicBytes) *algorithmicBytes = 148ll * h->M + 32ll * h->nInt;   // SURVEY.md section 8(d), polar variant
+        return TETSIM_OK;
+    }
+    if (!h->clustered) return fail(TETSIM_E_STATE, "tetsim_time_kernel times the tile kernels only (FAST Jacobi or FAST polar handles)");
     DeviceGuard g(h->device);
     cudaStream_t s = h->stream;
     const ClusterPlan &P = h->plan;
