@@ -251,21 +251,25 @@ __global__ void k_gs_body(const BodyDesc *__restrict__ bodies, const int *__rest
     // the first record of level l+1 is loaded into registers before level l is solved.
     int4 rI = make_int4(0, 0, 0, 0);
     float4 rA = make_float4(0.f, 0.f, 0.f, 0.f), rB = rA, rC = rA;
+    int rO = 0;   // the tet's caller index (volError slot) travels with the record: a load of order[] inside the level would sit on its path
     if (nLev > 0 && sLevel[0] + tid < sLevel[1]) {
         const int t = sLevel[0] + tid;
         rI = I[t]; rA = ldg4(A + t); rB = ldg4(B + t); rC = ldg4(C + t);
+        if (volTerm) rO = order[t];
     }
     for (int l = 0; l < nLev; l++) {
         const int b = sLevel[l], e = sLevel[l + 1];
         const int4 cI = rI;
         const float4 cA = rA, cB = rB, cC = rC;
+        const int cO = rO;
         if (l + 1 < nLev && e + tid < sLevel[l + 2]) {  // prefetch for the next level
             const int t = e + tid;
             rI = I[t]; rA = ldg4(A + t); rB = ldg4(B + t); rC = ldg4(C + t);
+            if (volTerm) rO = order[t];
         }
         if (b + tid < e) {
             double vm1 = gs_solve_one<EXACT>(sx, cI, cA, cB, cC, sp);
-            if (volTerm) volTerm[order[b + tid]] = vm1;
+            if (volTerm) volTerm[cO] = vm1;
         }
         for (int t = b + tid + nt; t < e; t += nt) {  // levels wider than the CTA (rare)
             double vm1 = gs_solve_one<EXACT>(sx, I[t], ldg4(A + t), ldg4(B + t), ldg4(C + t), sp);

@@ -252,7 +252,7 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
     sync();
 
     const SubstepParams *sp = a.sp;
-    const float alphaDev = sp->alphaDev, alphaVol = sp->alphaVol, gammaVol = sp->gammaVol;
+    const float alphaDev = sp->alphaDev * 6.0f, alphaVol = sp->alphaVol * 6.0f, gammaVol = sp->gammaVol;  // invRestVolume = 6 det Q
     // fused peer push: the epoch does not change while this kernel runs (its last CTA advances it) -- read it once
     const uint4 *pushRec = PEER ? a.px->pushRec : nullptr;
     const unsigned pushEpoch = PEER ? *reinterpret_cast<volatile unsigned *>(a.px->self + kPeerCtlOff) + 1u : 0u;
@@ -312,7 +312,7 @@ __device__ __forceinline__ void tile_worker(const TileArgs &a, unsigned char *ws
             const int t = tid + NT * u;
             if (DBG && (dbg & 8)) {  // measurement only: synthetic record, no HBM stream
                 const float f = 1.0f + 1e-3f * (float)(t & 7);
-                rA[u] = make_float4(f, 0.01f, 0.02f, f); rB[u] = make_float4(0.03f, f, 6.0f, 1.0f);
+                rA[u] = make_float4(f, 0.01f, 0.02f, f); rB[u] = make_float4(0.03f, f, 1.0f, 1.0f);
                 rC[u] = make_float4(__uint_as_float(((t * 16) & 0x3ff) | (((t * 16 + 16) & 0x3ff) << 16)),
                                     __uint_as_float(((t * 16 + 32) & 0x3ff) | (((t * 16 + 48) & 0x3ff) << 16)),
                                     __uint_as_float((unsigned)(t * 64) | (unsigned)(t * 64 + 16) << 16),
@@ -660,7 +660,10 @@ __global__ void k_build_tiles(int numRecords, const int *__restrict__ order, con
                 b[i][j] = (double)q[i] * (double)q[j] + (double)q[3 + i] * (double)q[3 + j] + (double)q[6 + i] * (double)q[6 + j];
         const float rv = irv[e];
         A = make_float4((float)b[0][0], (float)b[0][1], (float)b[0][2], (float)b[1][1]);
-        B = make_float4((float)b[1][2], (float)b[2][2], rv, rv / 6.0f);  // det Q = 1 / det Dm = invRestVolume / 6
+        const float dq = rv / 6.0f;  // det Q = 1 / det Dm = invRestVolume / 6
+        // a zero-volume rest tet (1 / V = inf) stays an all-zero record: no correction, like the reference's early returns
+        if (fabsf(rv) < INFINITY && rv == rv) B = make_float4((float)b[1][2], (float)b[2][2], dq * dq, dq);
+        else A = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     reinterpret_cast<float4 *>(tb)[t] = A;
     reinterpret_cast<float4 *>(tb + T * 16)[t] = B;
@@ -850,6 +853,171 @@ __global__ void k_peer_reduce(PeerArgs a) {
 }
 void launch_peer_reduce(cudaStream_t s, const PeerArgs &a) {
     if (a.numBoundary > 0) k_peer_reduce<<<cdiv(a.numBoundary, 256), 256, 0, s>>>(a);
+}
+
+// =================================================================================================
+// Gauss-Seidel in the reference order, FAST arithmetic: one CTA per body, FOUR LANES PER TET.
+//
+// The exact-order sweep is a chain of dependency levels (Dragon: 703 levels of <= 22 tets, 5.5 on average), so a substep
+// costs (levels) x (latency of one tet's solve), whatever the width of the machine.  k_gs_body (kernels.cuh) runs one tet
+// per thread: ~350 dependent-ish instructions, ~1,070 cycles per level.  Here a tet is solved by a quad of lanes -- lane c
+// of the quad owns component c of every vector (x, y, z; the fourth lane idles with zeros) -- in the rest-metric form of
+// the tile kernel (nh_solve_tile): per lane ~95 instructions; the 3x3 algebra that couples components (||F||^2, the
+// weighted gradient norms, the cofactors, det F) crosses lanes with warp shuffles: two butterfly reductions of two values
+// each and one rotation of the three updated edge vectors.  Corner displacements are added in place in shared memory
+// (tets of one level share no vertex).  Records (metric, det Q, 4 body-local vertex ids) come from L2 with the next
+// level's record prefetched into registers, as in k_gs_body.
+// =================================================================================================
+struct QuadRec { float4 A, B; int4 I; };   // A = (B00,B01,B02,B11)  B = (B12,B22,detQ, caller tet index as bits)  I = body-local vertex ids
+
+__device__ __forceinline__ float quad_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+}
+
+// All 32 lanes call this together (full-mask shuffles); `valid` quads store.  Returns det F - 1 (lane-uniform in the quad).
+__device__ __forceinline__ float gs_solve_quad(float4 *sx, const QuadRec &r, bool valid, int c, int lane, float alphaDev,
+                                               float alphaVol, float gammaVol) {
+    const float *f = reinterpret_cast<const float *>(sx);
+    const int cc = c < 3 ? c : 0;
+    const float m = c < 3 ? 1.0f : 0.0f;                        // the idle fourth lane carries zeros through the algebra
+    const float q0 = f[4 * r.I.x + cc] * m, q1 = f[4 * r.I.y + cc] * m, q2 = f[4 * r.I.z + cc] * m, q3 = f[4 * r.I.w + cc] * m;
+    const float w0 = f[4 * r.I.x + 3], w1 = f[4 * r.I.y + 3], w2 = f[4 * r.I.z + 3], w3 = f[4 * r.I.w + 3];
+    float P0 = q1 - q0, P1 = q2 - q0, P2 = q3 - q0;
+    const float G1 = fmaf(P2, r.A.z, fmaf(P1, r.A.y, P0 * r.A.x));
+    const float G2 = fmaf(P2, r.B.x, fmaf(P1, r.A.w, P0 * r.A.y));
+    const float G3 = fmaf(P2, r.B.y, fmaf(P1, r.B.x, P0 * r.A.z));
+    const float nG0 = G1 + G2 + G3;
+    const float rs2 = quad_sum(fmaf(P2, G3, fmaf(P1, G2, P0 * G1)));
+    const float wG = quad_sum(fmaf(w3, G3 * G3, fmaf(w2, G2 * G2, fmaf(w1, G1 * G1, w0 * (nG0 * nG0)))));
+    const float detQ = r.B.z, irv = 6.0f * detQ;   // 1 / V = 6 det Q
+    const float r1 = rs2 * rcp_approx(fmaf(alphaDev * irv, rs2, wG));
+    const float s = (rs2 > 0.0f && wG > 0.0f) ? -r1 : 0.0f;
+    const float e1 = G1 * (s * w1), e2 = G2 * (s * w2), e3 = G3 * (s * w3), d0 = nG0 * (-(s * w0));
+    P0 = P0 + e1 - d0; P1 = P1 + e2 - d0; P2 = P2 + e3 - d0;
+    // cofactors: component c of a x b needs components c+1, c+2 of a and b -- held by the two other lanes of the quad
+    const int base = lane & ~3, l1 = base | (c < 3 ? (c + 1) % 3 : 0), l2 = base | (c < 3 ? (c + 2) % 3 : 0);
+    const float P0a = __shfl_sync(0xffffffffu, P0, l1), P0b = __shfl_sync(0xffffffffu, P0, l2);
+    const float P1a = __shfl_sync(0xffffffffu, P1, l1), P1b = __shfl_sync(0xffffffffu, P1, l2);
+    const float P2a = __shfl_sync(0xffffffffu, P2, l1), P2b = __shfl_sync(0xffffffffu, P2, l2);
+    const float c1 = (P1a * P2b - P1b * P2a) * m, c2 = (P2a * P0b - P2b * P0a) * m, c3 = (P0a * P1b - P0b * P1a) * m;
+    const float nc0 = c1 + c2 + c3;
+    const float vol = quad_sum(P0 * c1) * detQ;
+    const float wC = quad_sum(fmaf(w3, c3 * c3, fmaf(w2, c2 * c2, fmaf(w1, c1 * c1, w0 * (nc0 * nc0)))));
+    const float C = vol - gammaVol;
+    const float wt = (detQ * detQ) * wC;   // the true weighted gradient norm: the reference's `w == 0 -> return` (:184) tests this
+    const float r2 = (C * detQ) * rcp_approx(fmaf(alphaVol, irv, wt));
+    const float t = (C != 0.0f && wt > 0.0f) ? -r2 : 0.0f;
+    if (valid && c < 3) {
+        float *g = reinterpret_cast<float *>(sx);
+        g[4 * r.I.x + c] = q0 + fmaf(nc0, -(t * w0), d0);
+        g[4 * r.I.y + c] = q1 + fmaf(c1, t * w1, e1);
+        g[4 * r.I.z + c] = q2 + fmaf(c2, t * w2, e2);
+        g[4 * r.I.w + c] = q3 + fmaf(c3, t * w3, e3);
+    }
+    return vol - 1.0f;
+}
+
+__global__ void k_gs_body_quads(const BodyDesc *__restrict__ bodies, const int *__restrict__ levelStart,
+                                float4 *__restrict__ x4, float4 *__restrict__ prev4, float4 *__restrict__ vel4,
+                                const int4 *__restrict__ I, const float4 *__restrict__ A, const float4 *__restrict__ B,
+                                const int *__restrict__ order, double *__restrict__ volTerm,
+                                const SubstepParams *__restrict__ sp, const int *__restrict__ vertId) {
+    extern __shared__ float4 sxq[];
+    const BodyDesc bd = bodies[blockIdx.x];
+    const int nv = bd.vertEnd - bd.vertBegin;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, c = tid & 3, quad = tid >> 2, nq = nt >> 2;
+    const float dt = sp->dtF, gDt = sp->gDt;
+    for (int j = tid; j < nv; j += nt) {   // predict (simulate() :198-202)
+        const int i = bd.vertBegin + j;
+        float4 x = x4[i], v = vel4[i];
+        prev4[i] = x;
+        v.y += gDt;
+        x.x = fmaf(v.x, dt, x.x); x.y = fmaf(v.y, dt, x.y); x.z = fmaf(v.z, dt, x.z);
+        sxq[j] = x;
+    }
+    int *sLevel = reinterpret_cast<int *>(sxq + nv);
+    const int nLev = bd.levelEnd - bd.levelBegin;
+    for (int j = tid; j <= nLev; j += nt) sLevel[j] = levelStart[bd.levelBegin + j];
+    __syncthreads();
+    const float alphaDev = sp->alphaDev, alphaVol = sp->alphaVol, gammaVol = sp->gammaVol;
+    const QuadRec zero = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), make_int4(0, 0, 0, 0)};
+    auto fetch = [&](int t) { QuadRec r; r.A = ldg4(A + t); r.B = ldg4(B + t); r.I = __ldg(I + t); return r; };
+    // A level lasts ~300 cycles, an L2 hit ~700-1000: the record a quad needs at level l is loaded FOUR levels earlier into
+    // a ring of four register sets (the level loop is unrolled by four so the ring is addressed statically).  With the
+    // one-level look-ahead of k_gs_body the sweep ran at one L2 latency per level.
+    auto fetch_level = [&](int l) {
+        if (l < nLev) { const int t = sLevel[l] + quad; if (t < sLevel[l + 1]) return fetch(t); }
+        return zero;
+    };
+    auto do_level = [&](int l, QuadRec &ring) {
+        const int b = sLevel[l], e = sLevel[l + 1];
+        const QuadRec cur = ring;
+        ring = fetch_level(l + 4);
+        if (b + (tid & ~31) / 4 < e) {   // warp-uniform: this warp has a tet in the first pass
+            const bool valid = b + quad < e;
+            const float vm1 = gs_solve_quad(sxq, cur, valid, c, lane, alphaDev, alphaVol, gammaVol);
+            if (volTerm && valid && c == 0) volTerm[__float_as_int(cur.B.w)] = (double)vm1;   // tet index rides in the record: no load on the level's path
+        }
+        for (int t0 = b + nq; t0 < e; t0 += nq) {   // levels wider than the CTA's quads (block-uniform trip count)
+            if (t0 + (tid & ~31) / 4 < e) {
+                const bool valid = t0 + quad < e;
+                const QuadRec r = valid ? fetch(t0 + quad) : zero;
+                const float vm1 = gs_solve_quad(sxq, r, valid, c, lane, alphaDev, alphaVol, gammaVol);
+                if (volTerm && valid && c == 0) volTerm[__float_as_int(r.B.w)] = (double)vm1;
+            }
+        }
+        __syncthreads();
+    };
+    QuadRec R0 = fetch_level(0), R1 = fetch_level(1), R2 = fetch_level(2), R3 = fetch_level(3);
+    for (int l = 0; l < nLev; l += 4) {
+        do_level(l, R0);
+        if (l + 1 < nLev) do_level(l + 1, R1);
+        if (l + 2 < nLev) do_level(l + 2, R2);
+        if (l + 3 < nLev) do_level(l + 3, R3);
+    }
+    for (int j = tid; j < nv; j += nt) {   // post (simulate() :213-239)
+        const int i = bd.vertBegin + j;
+        float4 x = sxq[j], p = prev4[i], v;
+        v.w = 0.0f;
+        post_vertex<false>(vertId ? vertId[i] : i, x, p, v, sp);
+        x4[i] = x;
+        vel4[i] = v;
+    }
+}
+
+void launch_gs_body_quads(cudaStream_t s, int numBodies, int threads, size_t smemBytes, const BodyDesc *bodies,
+                          const int *levelStart, float4 *x4, float4 *prev4, float4 *vel4, const int4 *I, const float4 *A,
+                          const float4 *B, const int *order, double *volTerm, const SubstepParams *sp, const int *vertId) {
+    if (numBodies <= 0) return;
+    static size_t configured[64] = {0};
+    size_t &cfg = configured[current_device()];
+    if (smemBytes > 48 * 1024 && smemBytes > cfg) {
+        cudaFuncSetAttribute(k_gs_body_quads, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
+        cfg = smemBytes;
+    }
+    k_gs_body_quads<<<numBodies, threads, smemBytes, s>>>(bodies, levelStart, x4, prev4, vel4, I, A, B, order, volTerm, sp, vertId);
+}
+
+// Level-sorted GS stream in the rest-metric form: A = (B00,B01,B02,B11), B = (B12,B22,detQ, caller tet index), B = Q Q^T.
+__global__ void k_build_stream_metric(int count, const int *__restrict__ order, const float *__restrict__ Q9,
+                                      const float *__restrict__ irv, float4 *__restrict__ A, float4 *__restrict__ B) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int e = order ? order[i] : i;
+    const float *q = Q9 + 9 * (size_t)e;
+    double b[3][3];
+    for (int r = 0; r < 3; r++)
+        for (int k = r; k < 3; k++)
+            b[r][k] = (double)q[r] * (double)q[k] + (double)q[3 + r] * (double)q[3 + k] + (double)q[6 + r] * (double)q[6 + k];
+    const float rv = irv[e];
+    const bool ok = fabsf(rv) < INFINITY && rv == rv;   // a zero-volume rest tet is a no-op, like the reference's C == 0 / w == 0 exits
+    A[i] = ok ? make_float4((float)b[0][0], (float)b[0][1], (float)b[0][2], (float)b[1][1]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    B[i] = make_float4(ok ? (float)b[1][2] : 0.f, ok ? (float)b[2][2] : 0.f, ok ? rv / 6.0f : 0.f, __int_as_float(e));
+}
+void launch_build_stream_metric(cudaStream_t s, int count, const int *order, const float *Q9, const float *irv, float4 *A, float4 *B) {
+    if (count > 0) k_build_stream_metric<<<cdiv(count, 256), 256, 0, s>>>(count, order, Q9, irv, A, B);
 }
 
 // =================================================================================================

@@ -144,6 +144,12 @@ constexpr int kPeerK = 16;                // most tile partials a rank may hold 
 void launch_peer_push(cudaStream_t, const PeerArgs &a);
 void launch_peer_reduce(cudaStream_t, const PeerArgs &a);
 
+// ---- FAST-only: Gauss-Seidel in the reference order with four lanes per tet (kernels_fast.cu) ----
+void launch_gs_body_quads(cudaStream_t, int numBodies, int threads, size_t smemBytes, const BodyDesc *bodies, const int *levelStart,
+                          float4 *x4, float4 *prev4, float4 *vel4, const int4 *I, const float4 *A, const float4 *B,
+                          const int *order, double *volTerm, const SubstepParams *sp, const int *vertId);
+void launch_build_stream_metric(cudaStream_t, int count, const int *order, const float *Q9, const float *irv, float4 *A, float4 *B);
+
 // ---- FAST-only throughput path of the polar solver: tiled shape matching (kernels_fast.cu) ----
 struct PolarTileArgs {
     const float4 *x4;

@@ -139,6 +139,7 @@ struct tetsim {
     int numLevels = 0, maxLevelSize = 0, numComponents = 1, numBodies = 0, bodyThreads = 0;
     size_t bodySmem = 0;
     bool bodyKernel = false;
+    bool gsQuads = false;                 // FAST GS: k_gs_body_quads (four lanes per tet, rest-metric stream)
     DevBuf<double> volTerm, volOut;
     bool trackVol = false;
     // Jacobi gather path
@@ -385,9 +386,19 @@ int build_gs(tetsim *h, const std::vector<float> &verts, const std::vector<int> 
     CK(h->I.upload(I, s));
     CK(h->levelStart.upload(h->h_levelStart, s));
     if (h->bodyKernel) CK(h->bodies.upload(bodies, s));
-    CK(h->A.alloc((size_t)M)); CK(h->B.alloc((size_t)M)); CK(h->C.alloc((size_t)M));
-    CK(cudaMemsetAsync(h->C.p, 0, h->C.bytes(), s));
-    launch_build_stream(s, M, h->order.p, h->Q9.p, h->irv.p, h->A.p, h->B.p, h->C.p);
+    CK(h->A.alloc((size_t)M)); CK(h->B.alloc((size_t)M));
+    // FAST arithmetic, one CTA per body: the four-lanes-per-tet kernel on the rest-metric stream (k_gs_body_quads)
+    // (narrow levels only: the exact-order schedule has <= 22 tets per level on Dragon; a colour class of 228 tets keeps one thread per tet)
+    h->gsQuads = h->bodyKernel && h->opt.arithmetic == TETSIM_ARITH_FAST_F32 && h->maxLevelSize <= 64;
+    if (const char *e = getenv("TETSIM_GS_NO_QUADS")) if (e[0] == '1') h->gsQuads = false;
+    if (h->gsQuads) {
+        launch_build_stream_metric(s, M, h->order.p, h->Q9.p, h->irv.p, h->A.p, h->B.p);
+        h->bodyThreads = std::max(64, std::min(512, 32 * ((4 * h->maxLevelSize + 31) / 32)));
+    } else {
+        CK(h->C.alloc((size_t)M));
+        CK(cudaMemsetAsync(h->C.p, 0, h->C.bytes(), s));
+        launch_build_stream(s, M, h->order.p, h->Q9.p, h->irv.p, h->A.p, h->B.p, h->C.p);
+    }
     if (h->trackVol) { CK(h->volTerm.alloc((size_t)M)); CK(cudaMemsetAsync(h->volTerm.p, 0, h->volTerm.bytes(), s)); }
     (void)verts;
     return TETSIM_OK;
@@ -614,6 +625,10 @@ int enqueue_substeps(tetsim *h, int count) {
             case TETSIM_NH_GS_COLOR:
                 if (h->bodyKernel) {
                     h->enq += h->numBodies > 0;
+                    if (h->gsQuads)
+                        launch_gs_body_quads(s, h->numBodies, h->bodyThreads, h->bodySmem, h->bodies.p, h->levelStart.p, h->x4.p,
+                                             h->prev4.p, h->vel4.p, h->I.p, h->A.p, h->B.p, h->order.p, h->volTerm.p, sp, vid);
+                    else
                     K->gs_body(s, h->numBodies, h->bodyThreads, h->bodySmem, h->bodies.p, h->levelStart.p, h->x4.p,
                                h->prev4.p, h->vel4.p, h->I.p, h->A.p, h->B.p, h->C.p, h->order.p, h->volTerm.p, sp, vid);
                 } else {
