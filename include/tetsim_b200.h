@@ -204,9 +204,19 @@ int tetsim_end_grab(tetsim_t *h);
 /* updateVisMesh, src/Softbody.js:259-277: barycentric skinning of the embedded surface mesh.
  * visVerts = (tetNr, b0, b1, b2) per surface vertex; triIds may be NULL/0 to skip the normals
  * (three@0.160.0 BufferGeometry.computeVertexNormals, three.module.js:11125-11215).
- * The surface mesh is uploaded on the first call and cached until the pointers/counts change. */
+ * The surface mesh is uploaded on the first call and cached; the cache is keyed on the arrays' CONTENT (a 64-bit hash
+ * per call), so mutating visVerts / triIds in place, or a new array at the same address, is picked up. */
 int tetsim_skin(tetsim_t *h, const float *visVerts, int32_t numVis, const int32_t *triIds, int32_t numTris,
                 float *outPos, float *outNormals);
+
+/* The WebGL variant's render-time skinning, i.e. the vertex shader SoftBodyGPU patches into its vis material
+ * (src/SoftbodyGPU.js:424-448): position = ((p0 b0 + p1 b1) + p2 b2) + p3 (1 - (b0 + b1 + b2)) in f32, and -- instead of
+ * computeVertexNormals every frame -- normal = Rotate(rest normal, quaternion of the surface vertex's tet).
+ * restNormals = 3*numVis floats: the normals computeVertexNormals left in the geometry at construction (:484-485 via
+ * updateVisMesh :685; tetsim_skin on the initial state returns exactly those); NULL / outNormals NULL skips the normals.
+ * POLAR_JACOBI handles only.  The surface mesh is cached by content, like tetsim_skin. */
+int tetsim_skin_gpu(tetsim_t *h, const float *visVerts, int32_t numVis, const float *restNormals, float *outPos,
+                    float *outNormals);
 
 int tetsim_get_info(tetsim_t *h, TetSimInfo *info);
 /* Measurement aid for bench.py's roofline line: launches the dominant kernel of the handle (the

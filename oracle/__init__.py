@@ -189,6 +189,18 @@ def vertex_normals(pos, tri_ids) -> np.ndarray:
     return out
 
 
+def polar_skin(vis_verts, tet_ids, pos, quat, rest_normals=None):
+    """The WebGL variant's vertex-shader skinning (src/SoftbodyGPU.js:424-448): (positions, normals or None)."""
+    vv = _f32(vis_verts).reshape(-1)
+    n = vv.size // 4
+    out = np.zeros(3 * n, np.float32)
+    nrm = np.zeros(3 * n, np.float32) if rest_normals is not None else None
+    rn = _f32(rest_normals).reshape(-1) if rest_normals is not None else None
+    lib().oracle_polar_skin(n, _p(vv, C.c_float), _p(_i32(tet_ids).reshape(-1), C.c_int), _p(_f32(pos).reshape(-1), C.c_float),
+                            _p(_f32(quat).reshape(-1), C.c_float), _p(rn, C.c_float), _p(out, C.c_float), _p(nrm, C.c_float))
+    return out, nrm
+
+
 class PolarOracle:
     """State + substep of the reference's ``SoftBodyGPU`` (src/SoftbodyGPU.js), CPU restatement in f32."""
 

@@ -223,3 +223,28 @@ void oracle_polar_simulate(int numVerts, int numTets, float *pos, float *prev, f
         st3(vel, i, v);
     }
 }
+
+/* The WebGL variant's render-time skinning of the embedded surface mesh (vertex shader patched into the vis material,
+ * src/SoftbodyGPU.js:424-448): per surface vertex (tetNr, b0, b1, b2)
+ *   lastTetWeight = 1.0 - (b0 + b1 + b2)                                   (:431; note the grouping, unlike the CPU class)
+ *   position = ((p0 * b0 + p1 * b1) + p2 * b2) + p3 * lastTetWeight        (:432-435, vec4 arithmetic, f32)
+ *   normal   = Rotate(objectNormal, tetQuaternion)                         (:438; objectNormal = the rest-pose vertex normal
+ *              computeVertexNormals() left in the geometry at construction, :484-485 + :685)
+ * Same f32 reading of GLSL as the passes above (every operation separately rounded). */
+void oracle_polar_skin(int numVis, const float *visVerts, const int *tetIds, const float *pos, const float *quat,
+                       const float *restNormals, float *outPos, float *outNrm) {
+    for (int i = 0; i < numVis; i++) {
+        const int e = (int)visVerts[4 * i];
+        const float b0 = visVerts[4 * i + 1], b1 = visVerts[4 * i + 2], b2 = visVerts[4 * i + 3];
+        const float b3 = 1.0f - ((b0 + b1) + b2);
+        const v3 p0 = ld3(pos, (size_t)tetIds[4 * e]), p1 = ld3(pos, (size_t)tetIds[4 * e + 1]);
+        const v3 p2 = ld3(pos, (size_t)tetIds[4 * e + 2]), p3 = ld3(pos, (size_t)tetIds[4 * e + 3]);
+        const v3 r = add3(add3(add3(mul3(p0, b0), mul3(p1, b1)), mul3(p2, b2)), mul3(p3, b3));
+        outPos[3 * i] = r.x; outPos[3 * i + 1] = r.y; outPos[3 * i + 2] = r.z;
+        if (outNrm) {
+            const v4 q = {quat[4 * e], quat[4 * e + 1], quat[4 * e + 2], quat[4 * e + 3]};
+            const v3 n = rotate(ld3(restNormals, (size_t)i), q);
+            outNrm[3 * i] = n.x; outNrm[3 * i + 1] = n.y; outNrm[3 * i + 2] = n.z;
+        }
+    }
+}

@@ -472,6 +472,41 @@ def test_skinning_and_normals(dragon):
     assert np.max(np.abs(fast.visMesh.positions - skinned)) < 1e-6
 
 
+def test_gpu_variant_skinning_quaternion_normals(dragon):
+    """N1, second half: the WebGL class never calls computeVertexNormals per frame; its vertex shader blends positions in
+    f32 and rotates the REST normal by the tet's quaternion (src/SoftbodyGPU.js:424-448).  BITEXACT: bit-identical to the
+    oracle's restatement of that shader; FAST (tiled solver, quaternions read from the tile blocks): within tolerance."""
+    vis, tri, ids = dragon["vis_verts"], dragon["vis_tri_ids"], dragon["tet_ids"]
+    ref = oracle.PolarOracle(dragon["tet_verts"], ids)
+    rest_pos = oracle.skin(vis, ids, ref.pos)
+    rest_nrm = oracle.vertex_normals(rest_pos, tri)
+    p = dict(ts.DEFAULT_PHYSICS_PARAMS, numSubsteps=20)
+    ex = ts.SoftBodyGPU(dragon["tet_verts"], ids, dragon["tet_edge_ids"], dict(p), vis, tri, arithmetic="bitexact")
+    fa = ts.SoftBodyGPU(dragon["tet_verts"], ids, dragon["tet_edge_ids"], dict(p), vis, tri, arithmetic="fast", cluster_size=128)
+    assert_bit_equal(ex.restNormals, rest_nrm, "rest normals (constructor)")
+    for _ in range(2):
+        ex.step(p); fa.step(p)
+        for _ in range(20):
+            ref.simulate(DT1200)
+    want_pos, want_nrm = oracle.polar_skin(vis, ids, ref.pos, ref.quat, rest_nrm)
+    ex.renderVisMesh()
+    assert_bit_equal(ex.visMesh.positions, want_pos, "shader positions")
+    assert_bit_equal(ex.visMesh.normals, want_nrm, "quaternion-rotated normals")
+    assert np.max(np.abs(want_nrm - rest_nrm)) > 1e-6            # the body has started to rotate locally: not a no-op
+    fa.renderVisMesh()
+    assert np.max(np.abs(fa.visMesh.positions - want_pos)) <= 1e-4
+    assert np.max(np.abs(fa.visMesh.normals - want_nrm)) <= 1e-3
+    # the cache follows the CONTENT of visVerts: an in-place edit is picked up
+    fa.visVerts[1:4] = (0.25, 0.25, 0.25)
+    fa.renderVisMesh()
+    e = int(vis[0]); q = ref.pos.reshape(-1, 3)[ids.reshape(-1, 4)[e]].astype(np.float64)
+    assert np.allclose(fa.visMesh.positions[:3], q.mean(axis=0), atol=1e-4)
+    with pytest.raises(ts.TetSimError):
+        check_body = ts.SoftBody(dragon["tet_verts"], ids, None, None)
+        _ = ts._capi.check(ts._capi.lib().tetsim_skin_gpu(check_body._h, ts._capi.ptr(fa.visVerts), fa.numVisVerts, None,
+                                                          ts._capi.ptr(fa.visMesh.positions), None))
+
+
 def test_errors_are_loud(dragon):
     v, t = dragon["tet_verts"], dragon["tet_ids"].copy()
     t[5] = 99999

@@ -32,7 +32,7 @@ SYMBOLS = [
     "tetsim_level_schedule", "tetsim_greedy_colors", "tetsim_plan_partition", "tetsim_plan_halo",
     "tetsim_get_positions_async", "tetsim_wait_positions", "tetsim_get_resident_ids", "tetsim_set_state_resident",
     "tetsim_get_positions_resident", "tetsim_get_positions_resident_async", "tetsim_nearest_vertex", "tetsim_set_grab",
-    "tetsim_connected_components",
+    "tetsim_connected_components", "tetsim_skin_gpu",
 ]
 
 
@@ -134,6 +134,7 @@ def lib() -> C.CDLL:
     L.tetsim_move_grabbed.argtypes = [vp, dblp]
     L.tetsim_end_grab.argtypes = [vp]
     L.tetsim_skin.argtypes = [vp, vp, C.c_int32, vp, C.c_int32, vp, vp]
+    L.tetsim_skin_gpu.argtypes = [vp, vp, C.c_int32, vp, vp, vp]
     L.tetsim_get_info.argtypes = [vp, C.POINTER(TetSimInfo)]
     L.tetsim_time_kernel.argtypes = [vp, C.c_int32, dblp, C.POINTER(C.c_int64)]
     L.tetsim_nccl_unique_id.argtypes = [vp]

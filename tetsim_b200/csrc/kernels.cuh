@@ -455,6 +455,32 @@ __global__ void k_skin(int nVis, const float4 *__restrict__ vis, const int4 *__r
     }
 }
 
+// The WebGL variant's vertex-shader skinning (src/SoftbodyGPU.js:424-448): position = ((p0 b0 + p1 b1) + p2 b2) + p3 (1 - (b0 + b1 + b2))
+// in f32, normal = Rotate(rest normal, quaternion of the surface vertex's tet).  quatOf(e) abstracts where the tet's
+// quaternion lives (a plain array in the reference-structure solver, the tile blocks in the tiled one).
+template <bool EXACT>
+__global__ void k_skin_polar(int nVis, const float4 *__restrict__ vis, const int4 *__restrict__ ids, const float4 *__restrict__ x4,
+                             const float4 *__restrict__ quat, const unsigned char *__restrict__ tileTets, const int *__restrict__ tetRecord,
+                             int T, const float *__restrict__ restNrm, float *__restrict__ outPos, float *__restrict__ outNrm) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nVis) return;
+    const float4 vv = vis[i];
+    const int e = (int)vv.x;
+    const int4 id = ids[e];
+    const float4 p0 = x4[id.x], p1 = x4[id.y], p2 = x4[id.z], p3 = x4[id.w];
+    const float b0 = vv.y, b1 = vv.z, b2 = vv.w, b3 = 1.0f - ((b0 + b1) + b2);
+    outPos[3 * (size_t)i] = ((p0.x * b0 + p1.x * b1) + p2.x * b2) + p3.x * b3;   // EXACT: this unit is compiled with -fmad=false
+    outPos[3 * (size_t)i + 1] = ((p0.y * b0 + p1.y * b1) + p2.y * b2) + p3.y * b3;
+    outPos[3 * (size_t)i + 2] = ((p0.z * b0 + p1.z * b1) + p2.z * b2) + p3.z * b3;
+    if (outNrm) {
+        float4 q4;
+        if (tetRecord) { const int r = tetRecord[e]; q4 = *reinterpret_cast<const float4 *>(tileTets + (size_t)(r / T) * T * 96 + (size_t)T * 48 + (size_t)(r % T) * 16); }
+        else q4 = quat[e];
+        const V3 n = pl_rotate({restNrm[3 * (size_t)i], restNrm[3 * (size_t)i + 1], restNrm[3 * (size_t)i + 2]}, {q4.x, q4.y, q4.z, q4.w});
+        outNrm[3 * (size_t)i] = n.x; outNrm[3 * (size_t)i + 1] = n.y; outNrm[3 * (size_t)i + 2] = n.z;
+    }
+}
+
 template <bool EXACT>
 __global__ void k_normals(int nVis, const float *__restrict__ pos, const int *__restrict__ tri,
                           const int *__restrict__ vtStart, const int *__restrict__ vtEnt, float *__restrict__ nrm) {

@@ -40,6 +40,8 @@ struct KernelTable {
     void (*skin)(cudaStream_t, int nVis, const float4 *vis, const int4 *ids, const float4 *x4, float *out);
     void (*normals)(cudaStream_t, int nVis, const float *pos, const int *tri, const int *vtStart, const int *vtEnt,
                     float *nrm);
+    void (*skin_polar)(cudaStream_t, int nVis, const float4 *vis, const int4 *ids, const float4 *x4, const float4 *quat,
+                       const unsigned char *tileTets, const int *tetRecord, int T, const float *restNrm, float *outPos, float *outNrm);
 };
 
 const KernelTable *exact_kernels();

@@ -71,6 +71,10 @@ struct Launchers {
     static void skin(cudaStream_t s, int nVis, const float4 *vis, const int4 *ids, const float4 *x4, float *out) {
         if (nVis > 0) k_skin<E><<<cdiv(nVis, TB), TB, 0, s>>>(nVis, vis, ids, x4, out);
     }
+    static void skin_polar(cudaStream_t s, int nVis, const float4 *vis, const int4 *ids, const float4 *x4, const float4 *quat,
+                           const unsigned char *tileTets, const int *tetRecord, int T, const float *restNrm, float *outPos, float *outNrm) {
+        if (nVis > 0) k_skin_polar<E><<<cdiv(nVis, TB), TB, 0, s>>>(nVis, vis, ids, x4, quat, tileTets, tetRecord, T, restNrm, outPos, outNrm);
+    }
     static void normals(cudaStream_t s, int nVis, const float *pos, const int *tri, const int *vtStart,
                         const int *vtEnt, float *nrm) {
         if (nVis > 0) k_normals<E><<<cdiv(nVis, TB), TB, 0, s>>>(nVis, pos, tri, vtStart, vtEnt, nrm);
@@ -78,7 +82,7 @@ struct Launchers {
     static const KernelTable *table() {
         static const KernelTable t = {init_tets,  init_mass,     predict,         post,      gs_level,
                                       gs_body,    gs_body_max_smem, jacobi_tet,   jacobi_gather,
-                                      polar_integrate, polar_tet, polar_vertex,   skin,      normals};
+                                      polar_integrate, polar_tet, polar_vertex,   skin,      normals, skin_polar};
         return &t;
     }
 };

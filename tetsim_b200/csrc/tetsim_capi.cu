@@ -176,8 +176,11 @@ struct tetsim {
     DevBuf<float4> visV;
     DevBuf<int> visTri, vtStart, vtEnt;
     DevBuf<float> visPos, visNrm;
-    const void *visKeyV = nullptr, *visKeyT = nullptr;
-    int visN = 0, visT = 0;
+    uint64_t visHashV = 0, visHashT = 0;   // content hashes of the cached surface mesh (a pointer is no identity: arrays get mutated in place)
+    int visN = -1, visT = -1;
+    DevBuf<float> visRestNrm;              // rest-pose normals of the WebGL variant's skinning (tetsim_skin_gpu)
+    uint64_t visHashN = 0;
+    DevBuf<int> tetRecord;                 // tiled polar solver: caller tet -> record slot (where its quaternion lives)
     // graphs
     std::map<int, cudaGraphExec_t> graphs;
     std::map<int, int64_t> graphLaunches;   // kernels inside each captured graph
@@ -1117,6 +1120,7 @@ void tetsim_destroy(tetsim_t *h) {
     for (auto *b : f4) b->release();
     DevBuf<int> *i1[] = {&h->vertId, &h->cStart, &h->cEnt, &h->order, &h->levelStart, &h->vpStart, &h->vpSlot, &h->tStart, &h->tEnt, &h->grabOut, &h->visTri, &h->vtStart, &h->vtEnt};
     for (auto *b : i1) b->release();
+    h->visRestNrm.release(); h->tetRecord.release();
     DevBuf<float> *f1[] = {&h->Q9, &h->irv, &h->invMass, &h->invVal, &h->stageIn[0], &h->stageIn[1], &h->stageOut[0], &h->stageOut[1], &h->visPos, &h->visNrm};
     for (auto *b : f1) b->release();
     h->ids.release(); h->I.release(); h->bodies.release(); h->volTerm.release(); h->volOut.release();
@@ -1283,6 +1287,61 @@ int tetsim_end_grab(tetsim_t *h) {
     return TETSIM_OK;
 }
 
+// 64-bit content hash (word-wise multiply-xorshift; ~1 GB/s per core is plenty for a 0.5 MB surface mesh per frame)
+static uint64_t content_hash(const void *data, size_t bytes) {
+    const unsigned char *p = static_cast<const unsigned char *>(data);
+    uint64_t hsh = 0x9e3779b97f4a7c15ull ^ bytes;
+    size_t i = 0;
+    for (; i + 8 <= bytes; i += 8) { uint64_t w; memcpy(&w, p + i, 8); hsh = (hsh ^ w) * 0xff51afd7ed558ccdull; hsh ^= hsh >> 32; }
+    for (; i < bytes; i++) { hsh = (hsh ^ p[i]) * 0x100000001b3ull; }
+    return hsh;
+}
+
+// The embedded surface mesh on the device, re-uploaded whenever its CONTENT changes.
+static int ensure_vis(tetsim *h, const float *visVerts, int32_t numVis) {
+    const uint64_t hv = content_hash(visVerts, (size_t)numVis * 16);
+    if (numVis == h->visN && hv == h->visHashV) return TETSIM_OK;
+    for (int i = 0; i < numVis; i++) {
+        float t = visVerts[4 * (size_t)i];
+        if (!(t >= 0.0f && t < (float)h->M)) return fail(TETSIM_E_INVALID, "visVerts tet index out of range");
+    }
+    CK(h->visV.alloc((size_t)numVis));
+    if (numVis) CK(cudaMemcpyAsync(h->visV.p, visVerts, (size_t)numVis * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+    CK(h->visPos.alloc(3 * (size_t)std::max(numVis, 1)));
+    CK(h->visNrm.alloc(3 * (size_t)std::max(numVis, 1)));
+    h->visHashV = hv; h->visN = numVis; h->visT = -1; h->visHashN = 0;
+    return TETSIM_OK;
+}
+
+int tetsim_skin_gpu(tetsim_t *h, const float *visVerts, int32_t numVis, const float *restNormals, float *outPos, float *outNormals) {
+    if (!h || !visVerts || !outPos || numVis < 0) return fail(TETSIM_E_INVALID, "null argument");
+    if (h->opt.solver != TETSIM_POLAR_JACOBI) return fail(TETSIM_E_STATE, "tetsim_skin_gpu rotates normals by the tets' quaternions: POLAR_JACOBI handles only");
+    DeviceGuard g(h->device);
+    cudaStream_t s = h->stream;
+    if (int rc = ensure_vis(h, visVerts, numVis)) return rc;
+    const bool wantN = outNormals && restNormals;
+    if (wantN) {
+        const uint64_t hn = content_hash(restNormals, (size_t)numVis * 12);
+        if (hn != h->visHashN || h->visRestNrm.n != 3 * (size_t)std::max(numVis, 1)) {
+            CK(h->visRestNrm.alloc(3 * (size_t)std::max(numVis, 1)));
+            if (numVis) CK(cudaMemcpyAsync(h->visRestNrm.p, restNormals, (size_t)numVis * 12, cudaMemcpyHostToDevice, s));
+            h->visHashN = hn;
+        }
+        if (h->polarTiled && h->tetRecord.n == 0) {   // caller tet -> record slot of the tile blocks
+            std::vector<int> rec((size_t)std::max(h->M, 1), 0);
+            for (size_t r = 0; r < h->plan.recordTet.size(); r++) if (h->plan.recordTet[r] >= 0) rec[h->plan.recordTet[r]] = (int)r;
+            CK(h->tetRecord.upload(rec, s));
+        }
+    }
+    h->K->skin_polar(s, numVis, h->visV.p, h->ids.p, h->x4.p, h->quat.p, h->tileTets.p, h->polarTiled ? h->tetRecord.p : nullptr,
+                     h->plan.T, h->visRestNrm.p, h->visPos.p, wantN ? h->visNrm.p : nullptr);
+    if (numVis) CK(cudaMemcpyAsync(outPos, h->visPos.p, 3 * (size_t)numVis * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (wantN && numVis) CK(cudaMemcpyAsync(outNormals, h->visNrm.p, 3 * (size_t)numVis * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));
+    return TETSIM_OK;
+}
+
 int tetsim_skin(tetsim_t *h, const float *visVerts, int32_t numVis, const int32_t *triIds, int32_t numTris,
                 float *outPos, float *outNormals) {
     if (!h || !visVerts || !outPos || numVis < 0) return fail(TETSIM_E_INVALID, "null argument");
@@ -1290,18 +1349,9 @@ int tetsim_skin(tetsim_t *h, const float *visVerts, int32_t numVis, const int32_
     DeviceGuard g(h->device);
     cudaStream_t s = h->stream;
     const bool wantN = outNormals && triIds && numTris > 0;
-    if (visVerts != h->visKeyV || numVis != h->visN) {
-        for (int i = 0; i < numVis; i++) {
-            float t = visVerts[4 * (size_t)i];
-            if (!(t >= 0.0f && t < (float)h->M)) return fail(TETSIM_E_INVALID, "visVerts tet index out of range");
-        }
-        CK(h->visV.alloc((size_t)numVis));
-        if (numVis) CK(cudaMemcpyAsync(h->visV.p, visVerts, (size_t)numVis * sizeof(float4), cudaMemcpyHostToDevice, s));
-        CK(h->visPos.alloc(3 * (size_t)std::max(numVis, 1)));
-        CK(h->visNrm.alloc(3 * (size_t)std::max(numVis, 1)));
-        h->visKeyV = visVerts; h->visN = numVis; h->visKeyT = nullptr;
-    }
-    if (wantN && (triIds != h->visKeyT || numTris != h->visT)) {
+    if (int rc = ensure_vis(h, visVerts, numVis)) return rc;
+    const uint64_t ht = wantN ? content_hash(triIds, (size_t)numTris * 12) : 0;
+    if (wantN && (ht != h->visHashT || numTris != h->visT)) {
         // vertex -> triangles, each (vertex, triangle) pair once, ascending triangle order
         std::vector<int> start((size_t)numVis + 1, 0), ent;
         for (int t = 0; t < numTris; t++) {
@@ -1329,7 +1379,7 @@ int tetsim_skin(tetsim_t *h, const float *visVerts, int32_t numVis, const int32_
         CK(h->vtStart.upload(start, s));
         CK(h->vtEnt.upload(ent, s));
         CK(cudaStreamSynchronize(s));
-        h->visKeyT = triIds; h->visT = numTris;
+        h->visHashT = ht; h->visT = numTris;
     }
     h->K->skin(s, numVis, h->visV.p, h->ids.p, h->x4.p, h->visPos.p);
     if (numVis) CK(cudaMemcpyAsync(outPos, h->visPos.p, 3 * (size_t)numVis * sizeof(float), cudaMemcpyDeviceToHost, s));

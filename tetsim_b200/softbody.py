@@ -307,6 +307,9 @@ class SoftBodyGPU(_Body):
                  world=None, **kw):
         kw.setdefault("solver", "polar")
         super().__init__(vertices, tetIds, tetEdgeIds, physicsParams, visVerts, visTriIds, visMaterial, world, **kw)
+        # the constructor ends with computeVertexNormals() + updateVisMesh() on the rest pose (src/SoftbodyGPU.js:484-485):
+        # those normals stay in the geometry as `objectNormal` and the vertex shader rotates them by the tets' quaternions
+        self.restNormals = self.visMesh.normals.copy()
 
     def simulate(self, dt, physicsParams=None):
         pp = physicsParams if physicsParams is not None else self.physicsParams
@@ -315,6 +318,15 @@ class SoftBodyGPU(_Body):
 
     def endFrame(self):  # src/SoftbodyGPU.js:643-647: only toggles the edge mesh; the vis mesh is skinned at render time
         self.edgeMesh.visible = bool(self.physicsParams.get("ShowTetMesh", False))
+
+    def renderVisMesh(self):
+        """What the vis material's patched vertex shader does at render time (src/SoftbodyGPU.js:424-448): barycentric
+        skinning in f32 and normal = Rotate(rest normal, tet quaternion); fills visMesh.positions / visMesh.normals."""
+        if not self.numVisVerts:
+            return
+        want_n = self.visTriIds is not None
+        check(_capi.lib().tetsim_skin_gpu(self._h, ptr(self.visVerts), self.numVisVerts, ptr(self.restNormals) if want_n else None,
+                                          ptr(self.visMesh.positions), ptr(self.visMesh.normals) if want_n else None))
 
     def readToCPU(self, variable="pos", buffer=None):
         """src/SoftbodyGPU.js:649-653; returns RGBA-strided floats like readRenderTargetPixels."""
