@@ -121,3 +121,32 @@ def test_mesh_generators():
     v2, t2 = mesh.tile_bodies(d["tet_verts"], d["tet_ids"], 8, 8, y_shift=-0.4)
     assert t2.size // 4 == 245760 and v2.size // 3 == 78976          # BASELINE config 5 (64 copies)
     assert t2.max() == 78975
+
+
+def test_js_host_shim_typechecks_and_matches_the_wrapper():
+    """N4 (JS host integration) cannot be executed here -- no Node, no JS engine -- so it is checked statically:
+    the N-API shim compiles (-fsyntax-only) against the documented Node-API signatures, every native.* call of the
+    wrapper classes is exported by the shim, every C entry point the shim calls is declared by the header, and the
+    wrapper exposes every member the reference's callers touch (src/main.js:53-68,82,88; src/Softbody.js:445-469;
+    src/SoftbodyGPU.js:792-824)."""
+    js = os.path.join(ROOT, "tetsim_b200", "js")
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-DTETSIM_NAPI_TYPECHECK",
+                        "-I" + os.path.join(ROOT, "include"), "-I" + js, os.path.join(js, "tetsim_napi.cc")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    shim = open(os.path.join(js, "tetsim_napi.cc")).read()
+    mjs = open(os.path.join(js, "softbody.mjs")).read()
+    exported = set(re.findall(r'\{"(\w+)", nullptr,', shim))
+    used = set(re.findall(r"native\.(\w+)", mjs))
+    assert used and used <= exported, used - exported
+    header = open(os.path.join(ROOT, "include", "tetsim_b200.h")).read()
+    for sym in set(re.findall(r"\b(tetsim_\w+)\s*\(", shim)) - {"tetsim_napi"}:
+        assert re.search(r"\b%s\s*\(" % sym, header), sym
+    for member in ("edgeMesh", "visMesh", "userData = this", "updateEdgeMesh()", "updateVisMesh()", "endFrame()", "simulate(dt, physicsParams)",
+                   "startGrab(pos)", "moveGrabbed(pos)", "endGrab()", "readToCPU(variable, buffer)", "get pos()", "get prevPos()", "get vel()",
+                   "get invMass()", "get invRestPose()", "get invRestVolume()", "get volError()", "numParticles", "numElems", "grabId", "grabPos",
+                   "export class SoftBody ", "export class SoftBodyGPU "):
+        assert member in mjs, member
+    # braces / parentheses balance (the cheapest syntax check available without an engine)
+    code = re.sub(r"//[^\n]*", "", mjs)
+    for a, b in ("{}", "()", "[]"):
+        assert code.count(a) == code.count(b), (a, code.count(a), code.count(b))

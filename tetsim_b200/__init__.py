@@ -5,7 +5,7 @@ mesh inputs.  No CPU fallback: using a body without the built library and a B200
 """
 from ._capi import (ARITH_BITEXACT, ARITH_FAST_F32, NH_GS_COLOR, NH_GS_EXACT, NH_JACOBI, POLAR_JACOBI, TetSimError,
                     greedy_colors, level_schedule)
-from .softbody import DEFAULT_PHYSICS_PARAMS, SoftBody, SoftBodyGPU
+from .softbody import DEFAULT_PHYSICS_PARAMS, SoftBody, SoftBodyGPU, default_physics_params
 from . import mesh
 
 __all__ = ["SoftBody", "SoftBodyGPU", "DEFAULT_PHYSICS_PARAMS", "TetSimError", "mesh", "level_schedule",

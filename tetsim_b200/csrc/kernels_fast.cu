@@ -1,5 +1,7 @@
 // kernels_fast.cu -- FAST_F32 flavour (FMA contraction on) + the clustered Jacobi throughput path
 // + small utility kernels.  sm_100a only.
+#include <mutex>
+
 #include "table.cuh"
 
 namespace tsim {
@@ -531,11 +533,13 @@ size_t jacobi_tiles_smem(int clusterSize, const TileArgs &a) {
 // Launch configuration is cached per (kernel instantiation, device): attributes such as the dynamic
 // shared-memory opt-in are per device, and a process may hold handles on several GPUs.
 struct LaunchCache { size_t smem = 0; int n = 0, sms = 0; };
+static std::mutex g_launchMu;   // handles on different host threads share the per-device launch caches below
 static int current_device() { int d = 0; cudaGetDevice(&d); return d < 0 || d >= 64 ? 0 : d; }
 
 template <int T, int S, int MINB, bool DBG = false>
 static void launch_tiles_T(cudaStream_t s, const TileArgs &a) {
     const size_t smem = tile_smem_bytes<T, S>(a);
+    std::lock_guard<std::mutex> lk(g_launchMu);
     static LaunchCache cache[64];
     LaunchCache &lc = cache[current_device()];
     if (smem != lc.smem) {
@@ -555,6 +559,7 @@ static void launch_tiles_T(cudaStream_t s, const TileArgs &a) {
 template <int T, int TPT, int S, int MINB, bool PEER = false>
 static void launch_tilesN(cudaStream_t s, const TileArgs &a) {
     const size_t smem = tile_smem_bytes<T, S>(a);
+    std::lock_guard<std::mutex> lk(g_launchMu);
     static LaunchCache cache[64];
     LaunchCache &lc = cache[current_device()];
     if (smem != lc.smem) {
@@ -575,6 +580,7 @@ static void launch_tilesN(cudaStream_t s, const TileArgs &a) {
 template <int TPL, int S>
 static void launch_warptiles(cudaStream_t s, const TileArgs &a) {
     const size_t perWarp = tile_smem_bytes<32 * TPL, S>(a);
+    std::lock_guard<std::mutex> lk(g_launchMu);
     static LaunchCache cache[64];
     LaunchCache &lc = cache[current_device()];
     if (perWarp != lc.smem) {
@@ -991,6 +997,7 @@ void launch_gs_body_quads(cudaStream_t s, int numBodies, int threads, size_t sme
                           const int *levelStart, float4 *x4, float4 *prev4, float4 *vel4, const int4 *I, const float4 *A,
                           const float4 *B, const int *order, double *volTerm, const SubstepParams *sp, const int *vertId) {
     if (numBodies <= 0) return;
+    std::lock_guard<std::mutex> lk(g_launchMu);
     static size_t configured[64] = {0};
     size_t &cfg = configured[current_device()];
     if (smemBytes > 48 * 1024 && smemBytes > cfg) {
@@ -1091,6 +1098,7 @@ size_t polar_tiles_smem(const PolarTileArgs &a) {
 void launch_polar_tiles(cudaStream_t s, int clusterSize, const PolarTileArgs &a) {
     if (a.numTiles <= 0) return;
     const size_t smem = polar_tiles_smem(a);
+    std::lock_guard<std::mutex> lk(g_launchMu);
 #define PT_CASE(T_)                                                                                                   \
     case T_: {                                                                                                        \
         static size_t set[64];                                                                                        \

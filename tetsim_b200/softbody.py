@@ -23,12 +23,17 @@ from . import _capi
 from ._capi import (ARITH_BITEXACT, ARITH_FAST_F32, NH_GS_COLOR, NH_GS_EXACT, NH_JACOBI, POLAR_JACOBI, TetSimError,
                     check, default_options, default_params, ptr)
 
-# src/main.js:22-36
-DEFAULT_PHYSICS_PARAMS = {
-    "gravity": -9.81, "timeScale": 1.0, "timeStep": 1.0 / 60.0, "numSubsteps": 10, "dt": 1.0 / 600.0,
-    "friction": 1000.0, "density": 1000.0, "devCompliance": 1.0 / 100000.0, "volCompliance": 0.0,
-    "worldBounds": [-2.5, -1.0, -2.5, 2.5, 10.0, 2.5], "computeNormals": True, "ShowTetMesh": False,
-}
+def default_physics_params(cpu_sim: bool = True) -> dict:
+    """The physicsParams object of src/main.js:22-36: numSubsteps is 5 with ?cpu=true (SoftBody) and 20 otherwise (SoftBodyGPU)."""
+    n = 5 if cpu_sim else 20
+    return {
+        "gravity": -9.81, "timeScale": 1.0, "timeStep": 1.0 / 60.0, "numSubsteps": n, "dt": 1.0 / (60.0 * n),
+        "friction": 1000.0, "density": 1000.0, "devCompliance": 1.0 / 100000.0, "volCompliance": 0.0,
+        "worldBounds": [-2.5, -1.0, -2.5, 2.5, 10.0, 2.5], "computeNormals": True, "ShowTetMesh": False, "cpuSim": cpu_sim,
+    }
+
+
+DEFAULT_PHYSICS_PARAMS = default_physics_params(True)
 
 _SOLVERS = {"gs_exact": NH_GS_EXACT, "gs_color": NH_GS_COLOR, "jacobi": NH_JACOBI, "polar": POLAR_JACOBI}
 _ARITH = {"fast": ARITH_FAST_F32, "bitexact": ARITH_BITEXACT}
@@ -48,7 +53,7 @@ class _Body:
                  world=None, *, solver=None, arithmetic="fast", iters=1, deterministic=True, reference_table_bug=True,
                  reorder=True, cluster_size=256, track_vol_error=None, device=-1, stream=0, rank=0, world_size=1,
                  nccl_unique_id=None, exchange="allreduce"):
-        self.physicsParams = physicsParams if physicsParams is not None else dict(DEFAULT_PHYSICS_PARAMS)
+        self.physicsParams = physicsParams if physicsParams is not None else default_physics_params(self._default_solver != "polar")
         v = np.ascontiguousarray(vertices, np.float32).reshape(-1)
         t = np.ascontiguousarray(tetIds, np.int32).reshape(-1)
         if v.size % 3 or t.size % 4:
