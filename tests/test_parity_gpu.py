@@ -482,7 +482,7 @@ def test_gpu_variant_skinning_quaternion_normals(dragon):
     rest_nrm = oracle.vertex_normals(rest_pos, tri)
     p = dict(ts.DEFAULT_PHYSICS_PARAMS, numSubsteps=20)
     ex = ts.SoftBodyGPU(dragon["tet_verts"], ids, dragon["tet_edge_ids"], dict(p), vis, tri, arithmetic="bitexact")
-    fa = ts.SoftBodyGPU(dragon["tet_verts"], ids, dragon["tet_edge_ids"], dict(p), vis, tri, arithmetic="fast", cluster_size=128)
+    fa = ts.SoftBodyGPU(dragon["tet_verts"], ids, dragon["tet_edge_ids"], dict(p), vis.copy(), tri, arithmetic="fast", cluster_size=128)
     assert_bit_equal(ex.restNormals, rest_nrm, "rest normals (constructor)")
     for _ in range(2):
         ex.step(p); fa.step(p)
@@ -496,7 +496,8 @@ def test_gpu_variant_skinning_quaternion_normals(dragon):
     fa.renderVisMesh()
     assert np.max(np.abs(fa.visMesh.positions - want_pos)) <= 1e-4
     assert np.max(np.abs(fa.visMesh.normals - want_nrm)) <= 1e-3
-    # the cache follows the CONTENT of visVerts: an in-place edit is picked up
+    # the cache follows the CONTENT of visVerts (the body keeps a reference to the caller's array, like src/Softbody.js:46):
+    # an in-place edit is picked up
     fa.visVerts[1:4] = (0.25, 0.25, 0.25)
     fa.renderVisMesh()
     e = int(vis[0]); q = ref.pos.reshape(-1, 3)[ids.reshape(-1, 4)[e]].astype(np.float64)
