@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", default="407,64,64", help="beam cells x,y,z (default = 10,002,432 tets)")
+    ap.add_argument("--jitter", type=float, default=0.0, help="displace the beam's interior vertices by +-jitter*h (numpy default_rng(1234)); "
+                    "0 = the regular Kuhn grid of BASELINE config 4")
     ap.add_argument("--substeps", type=int, default=20, help="substeps per step (frame)")
     ap.add_argument("--iters", type=int, default=1)
     ap.add_argument("--cluster-size", type=int, default=0, help="tets per tile (default 512 for the NH tile kernel -- measured fastest, profiles/r2_tile_experiments.txt -- and 256 for the polar tile kernel)")
@@ -327,7 +329,7 @@ def main():
     dt = FRAME_DT / args.substeps
     from tetsim_b200 import mesh
 
-    mesh_name = "beam %dx%dx%d cells Kuhn-split" % cells
+    mesh_name = "beam %dx%dx%d cells Kuhn-split" % cells + (", interior vertices jittered +-%.2f h" % args.jitter if args.jitter else "")
     workload = "%s, NH Jacobi iters=%d, dt=1/%d, %d substeps/step" % (mesh_name, args.iters, round(1.0 / dt), args.substeps)
     if polar:
         workload = "%s, polar-decomposition shape-matching Jacobi (SoftBodyGPU, src/SoftbodyGPU.js:59-376), dt=1/%d, %d substeps/step" % (
@@ -337,7 +339,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        verts, tets = mesh.make_beam(cells)
+        verts, tets = mesh.make_beam(cells, jitter=args.jitter)
         M = tets.size // 4
         import oracle
         ref = oracle.PolarOracle(verts, tets) if polar else oracle.SoftBodyOracle(verts, tets)
@@ -380,7 +382,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     assert args.gpus == world, "--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)" % (args.gpus, world)
 
-    verts, tets = mesh.make_beam(cells)
+    verts, tets = mesh.make_beam(cells, jitter=args.jitter)
     N, M = verts.size // 3, tets.size // 4
     def make_nccl_id():
         buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -617,6 +619,9 @@ def main():
                        "boundary_verts": info["boundaryVerts"], "boundary_tiles_rank0": info["boundaryTiles"], "deterministic": not args.atomic,
                        "parallelism": ("tet-partition x%d (RCB), %s of boundary dx per iteration, overlapped with interior tiles" % (world, {"allreduce": "ncclAllReduce", "halo": "neighbour ncclSend/ncclRecv", "peer": "fused peer-memory exchange: the tile kernel stores its boundary partials into the sharers' buffers (cudaIpc over NVLink, no NCCL on the data path)"}[args.exchange])) if world > 1 else "single GPU",
                        "exchange": args.exchange if world > 1 else None,
+                       "nvlink_bytes_per_iteration": (info["boundaryVerts"] * 2.4 * 32 * 1 if world > 1 and args.exchange == "peer" else None),
+                       "nvlink_bytes_note": ("peer exchange: every tile partial of a rank-shared vertex (about 2.4 per vertex and rank on this mesh) is one 32-byte "
+                                             "tagged entry stored into each OTHER sharer's buffer; figure = boundary_verts x 2.4 x 32 B x (sharers - 1 = 1 for planar cuts), per direction and iteration, all cuts together") if world > 1 else None,
                        "l2": "working set per substep (%.0f MB) exceeds the 126 MB L2; no flush needed" % ((56.0 * M + 144.0 * N) / 1e6)},
             "scalar_constraints_per_s_M": 2 * value,
             "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,

@@ -688,3 +688,32 @@ def test_config4_bench_configuration_100_substeps():
     for _ in range(5):
         sb2.step(p)
     assert_bit_equal(sb2.pos, sb.pos, "run-to-run")
+
+
+def test_jacobi_against_the_reference_answer_is_quantified():
+    """The headline algorithm (Jacobi Neo-Hookean) is not the reference's (sequential Gauss-Seidel, README.md:25 says so):
+    bench.py tabulates how far Jacobi(iters) lands from the reference-order Gauss-Seidel answer after 100 substeps on
+    Dragon (configs.jacobi_vs_gs).  Here: the table exists for iters = 1..16, every entry is finite and at the percent
+    level -- the same size as what merely re-ordering the Gauss-Seidel sweep does (6e-3 .. 1e-2) --
+    and more iterations do not make it worse than the single-iteration figure by more than 2x."""
+    import sys
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        t = bench.jacobi_vs_gs(stream)
+    errs = {int(k): v["vec_rel_err"] for k, v in t["by_iters"].items()}
+    assert sorted(errs) == [1, 2, 4, 8, 16]
+    assert all(np.isfinite(e) and 1e-4 < e < 5e-2 for e in errs.values()), errs
+    assert max(errs.values()) <= 2.0 * errs[1] + 1e-3, errs
+    assert 0.12 < t["free_fall_drop_m"] < 0.15    # 100 substeps of 1/600 s: g t^2 / 2 = 0.136 m
+    # re-ordering the reference's own sweep (greedy colour order) moves the answer by the same order of magnitude
+    m = mesh.load_dragon()
+    a = new_body(m, solver="gs_exact", arithmetic="bitexact")
+    b = new_body(m, solver="gs_color", arithmetic="bitexact")
+    for _ in range(100):
+        a.simulate(DT600)
+        b.simulate(DT600)
+    reorder = vec_rel_err(b.pos, a.pos)
+    assert 1e-3 < reorder < 5e-2 and min(errs.values()) < 10 * reorder, (reorder, errs)
