@@ -5,8 +5,11 @@ ctypes bindings over ``oracle/liboracle.so`` (built from ``softbody_oracle.c`` a
 ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import this package; nothing
 under ``tetsim_b200/`` does.
 
-PARITY UNPINNED: the reference (zalo/TetSim) has no tests or golden vectors and is JavaScript +
-GLSL, which this image cannot execute.  See the header of ``softbody_oracle.c``.
+PARITY PINNED TO THE REFERENCE'S OWN TEXT: the reference (zalo/TetSim) has no tests or golden vectors and is
+JavaScript + GLSL, which this image cannot execute; ``tools/transpile_reference.py`` and ``tools/transpile_shaders.py``
+re-emit it mechanically as Python (``oracle/_ref/``, run under ``oracle/jsrt.py`` / ``oracle/glslrt.py``), and the vectors
+that produces (``tests/golden/ref_golden.npz``) are what the C restatements here must reproduce bit for bit
+(``tests/test_reference_pin.py``).  See the headers of ``softbody_oracle.c`` and ``polar_oracle.c``.
 """
 from __future__ import annotations
 

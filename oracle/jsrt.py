@@ -46,6 +46,17 @@ def _mod(a, b):
         return NaN
 
 
+def _truthy(x):
+    """JS ToBoolean for the values in play: false, 0, NaN (= undefined here), null and '' are falsy."""
+    if x is None or x is False:
+        return False
+    if isinstance(x, float):
+        return x == x and x != 0.0
+    if isinstance(x, (int, str)):
+        return bool(x)
+    return True
+
+
 class _Indexable:
     __slots__ = ("_a",)
 
@@ -126,6 +137,10 @@ class JSArray(_Indexable):
     def slice(self, begin=0, end=None):
         return JSArray(self._a[int(begin):] if end is None else self._a[int(begin):int(end)])
 
+    def push(self, *items):
+        self._a.extend(items)
+        return len(self._a)
+
 
 class JSObject:
     """A plain JS object: property access by name, missing properties are undefined."""
@@ -137,6 +152,12 @@ class JSObject:
         if name.startswith("__"):
             raise AttributeError(name)
         return undefined
+
+    def __getitem__(self, key):   # obj['name'] and obj["a" + b]
+        return getattr(self, str(key))
+
+    def __setitem__(self, key, value):
+        setattr(self, str(key), value)
 
 
 class Math:
@@ -234,7 +255,16 @@ class _Object3D:
         self.layers = _Layers()
 
 
+class _Vector3:
+    def __init__(self, x=0.0, y=0.0, z=0.0):
+        self.x, self.y, self.z = x, y, z
+
+
+NearestFilter = 1003   # three.js constant; only stored by addVariable
+
+
 class THREE:
+    Vector3 = _Vector3
     BufferGeometry = _BufferGeometry
     BufferAttribute = _BufferAttribute
     LineSegments = _Object3D

@@ -7,7 +7,8 @@ any earlier tet sharing a vertex), and each level is processed as one vectorised
 tets inside a level share no vertex and every earlier conflicting tet is in an earlier level, the
 result must equal the sequential sweep bit for bit -- which is what tests/test_oracle.py asserts
 against the C restatement.  Agreement of two differently written restatements is the only pin
-available: the reference has no tests and cannot be executed in this image (PARITY UNPINNED).
+available in round 1: the reference has no tests and cannot be executed in this image (since round 2 the oracle is also
+pinned to the mechanically transpiled reference, tests/test_reference_pin.py).
 
 JS arithmetic rule: f32 arrays, f64 expressions, one f32 rounding per store.
 Reference lines: src/Softbody.js:60-87 (init), :91-166 (solveElem), :168-193 (applyToElem),

@@ -7,15 +7,22 @@
  * of each dependency, `prev_<dep>` is the alternate target, and the written variable flips).
  * NOT part of the product: only tests/, smoke() and bench.py's CPU-baseline legs may load it.
  *
- * PARITY UNPINNED: the reference has no tests or golden vectors and cannot be executed here
- * (no JS engine / WebGL).  GLSL ES 3.00 `highp float` leaves the precision of sin(), normalize(),
- * length() and the freedom to fuse multiply-adds to the driver, so "the reference's bits" are not
- * defined even in principle; this file fixes one IEEE-754 binary32 reading:
+ * PARITY PINNED TO THE REFERENCE'S OWN TEXT, UP TO THE FLOAT MODEL (round 2).  The reference has no tests or golden vectors
+ * and cannot be executed here (no JS engine / WebGL).  tools/transpile_reference.py (JavaScript: initPhysics, simulate, the
+ * GPGPU runtime's addVariable / addPass / compute) and tools/transpile_shaders.py (GLSL: the seven passes) re-emit the
+ * WHOLE solver mechanically as Python; oracle/ref_runner.py executes it texel by texel and tests/test_reference_pin.py
+ * requires this file to reproduce positions, prevPos, velocities, quaternions and goal corners BIT FOR BIT (Dragon in
+ * free fall, a beam with floor contact and friction).  What a transpile cannot settle: GLSL ES 3.00 `highp float` leaves
+ * the precision of sin(), normalize(), length() and the freedom to fuse multiply-adds to the driver, so "the reference's
+ * bits" are not defined even in principle; this file and the transpiled shaders' runtime (oracle/glslrt.py) fix ONE
+ * IEEE-754 binary32 reading:
  *   - every operation is a separately rounded f32 operation, left to right (no FMA:
  *     compile with -ffp-contract=off),
  *   - length(v) = sqrtf(dot(v,v)), normalize(v) = v / length(v) (IEEE divide),
  *   - sin(x) = (float)sin((double)x),
  *   - clamp(x,lo,hi) = fminf(fmaxf(x,lo),hi).
+ * Deliberate departures from the shader text (not exercised by the pinned scenarios): the grab uses the particle's linear
+ * index instead of the broken indexFromUV decode (src/SoftbodyGPU.js:336-338), the bounds are a parameter (:347).
  * The CUDA path's BITEXACT mode performs the same operations and must match bit for bit.
  */
 #include <math.h>

@@ -131,3 +131,112 @@ class RefSoftBodyGPUInit:
         if k is not None:
             t = t[k]
         return _np(t.image.data)
+
+
+class RefSoftBodyGPU:
+    """The WHOLE WebGL solver executed from the reference's text: SoftBodyGPU.initPhysics + simulate (src/SoftbodyGPU.js:487-641)
+    and MultiTargetGPUComputationRenderer.addVariable / addPass / compute (src/MultiTargetGPUComputationRenderer.js:144-176,
+    272-306) transpiled from JavaScript, the seven passes (src/SoftbodyGPU.js:59-376) transpiled from GLSL, wired exactly as the
+    constructor wires them (the addVariable / addPass / uniform lines are extracted from its text: shaders_ref.VARIABLES,
+    PASSES, UNIFORM_BINDINGS).  Hand-written here: the allocation of the textures (constructor :11-43), what init() does to
+    the render targets and sampler uniforms (:192-257), and doRenderTarget = "run the fragment shader for every texel".
+    Slow (pure Python, one fragment at a time): use for a few substeps."""
+
+    def __init__(self, verts, tet_ids, params: dict):
+        from . import glslrt
+        self.glsl = glslrt
+        sh = self.sh = _mod("shaders_ref")
+        init = RefSoftBodyGPUInit(verts, tet_ids, float(params.get("density", 1000.0)))
+        js = self.js = init.js
+        self.W = W = init.texDim
+        js.physicsParams = js_params(dict(params, dt=params.get("dt", 1.0 / 1200.0)))
+        gpu = js.gpuCompute = _mod("gpucompute_ref").MultiTargetGPUComputationRenderer()
+        gpu.variables, gpu.passes = jsrt.JSArray(), jsrt.JSArray()
+        gpu.createShaderMaterial = lambda src: jsrt.JSObject(uniforms=jsrt.JSObject(), fragmentShader=src)
+        gpu.doRenderTarget = self._render
+        for member, texname, initmember, count in sh.VARIABLES:                      # :49-55
+            setattr(js, member, gpu.addVariable(texname, getattr(js, initmember), count if count else jsrt.undefined))
+        for pname, var, deps, outs, unis in sh.PASSES:                               # :59-376, in addPass order
+            p = gpu.addPass(getattr(js, var), jsrt.JSArray(getattr(js, d) for d in deps), pname)
+            p.material.run = getattr(sh, pname)
+            setattr(js, pname, p)
+        for pname, uname, expr in sh.UNIFORM_BINDINGS:                               # material.uniforms[...] = { value: ... }
+            getattr(js, pname).material.uniforms[uname] = jsrt.JSObject(value=self._value(expr))
+        # init(), src/MultiTargetGPUComputationRenderer.js:192-257: two render targets per variable, both holding the initial
+        # texture; a sampler uniform per dependency (and prev_ for dependencies other than the written variable)
+        for v in gpu.variables:
+            for k in range(2):
+                v.renderTargets[k] = jsrt.JSObject(texture=self._clone(v.initialValueTexture))
+        for p in gpu.passes:
+            for d in p.dependencies:
+                p.material.uniforms[d.name] = jsrt.JSObject(value=None)
+                if d.name != p.variable.name:
+                    p.material.uniforms["prev_" + d.name] = jsrt.JSObject(value=None)
+
+    def _value(self, expr):
+        if expr.startswith("this."):
+            o = self.js
+            for part in expr[5:].split("."):
+                o = getattr(o, part)
+            return o
+        if expr.startswith("new THREE.Vector3"):
+            return jsrt.THREE.Vector3(*[float(x) for x in expr[expr.index("(") + 1:expr.rindex(")")].split(",")])
+        return float(expr)
+
+    def _sampler(self, t):
+        if isinstance(t, self.glsl.Sampler):
+            return t
+        if isinstance(t, jsrt.JSArray):
+            return [self._sampler(x) for x in t]
+        if not hasattr(t, "_sampler"):                      # a DataTexture filled by initPhysics: image.data, W x W RGBA
+            t._sampler = self.glsl.Sampler(_np(t.image.data), self.W, self.W)
+        return t._sampler
+
+    def _clone(self, t):
+        if isinstance(t, jsrt.JSArray):
+            return jsrt.JSArray(self._clone(x) for x in t)
+        return self.glsl.Sampler(_np(t.image.data).copy(), self.W, self.W)
+
+    def _render(self, material, output):
+        g0 = {}
+        for name, u in vars(material.uniforms).items():
+            v = u.value
+            if isinstance(v, (int, float)):
+                v = self.glsl.F(v)
+            elif isinstance(v, jsrt._Vector3):
+                v = self.glsl.vec3(v.x, v.y, v.z)
+            elif v is not None:
+                v = self._sampler(v)
+            g0[name] = v
+        targets = output.texture if isinstance(output.texture, jsrt.JSArray) else [output.texture]
+        W = self.W
+        res = self.glsl.vec2(float(W), float(W))
+        for y in range(W):
+            for x in range(W):
+                g = jsrt.JSObject(gl_FragCoord=self.glsl.vec4(x + 0.5, y + 0.5, 0.0, 1.0), resolution=res, **g0)
+                outs = material.run(g)
+                for t, o in zip(targets, outs):
+                    t.data[y, x, :] = o.d
+
+    def simulate(self, dt, params: dict | None = None):
+        if params is not None:
+            for k, v in params.items():
+                if k != "worldBounds":
+                    setattr(self.js.physicsParams, k, float(v) if isinstance(v, (int, float)) and not isinstance(v, bool) else v)
+        self.js.simulate(float(dt), self.js.physicsParams)
+
+    def _var(self, member, k=None):
+        v = getattr(self.js, member)
+        t = self.js.gpuCompute.getCurrentRenderTarget(v).texture
+        if k is not None:
+            t = t[k]
+        return t.data.reshape(-1, 4)
+
+    def _n(self):
+        return int(self.js.numParticles), int(self.js.numElems)
+
+    pos = property(lambda s: s._var("pos")[: s._n()[0], :3].reshape(-1).copy())
+    prevPos = property(lambda s: s._var("prevPos")[: s._n()[0], :3].reshape(-1).copy())
+    vel = property(lambda s: s._var("vel")[: s._n()[0], :3].reshape(-1).copy())
+    quat = property(lambda s: s._var("quats")[: s._n()[1], :].reshape(-1).copy())
+    rest = property(lambda s: np.stack([s._var("elems", k)[: s._n()[1], :3] for k in range(4)], axis=1).reshape(-1).copy())

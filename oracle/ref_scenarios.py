@@ -57,3 +57,15 @@ def run(sc, body, read, on_save):
         body.simulate(sc["dt"], sc["params"])
         if s + 1 in sc["save"]:
             on_save(s + 1, read(body))
+
+
+def polar_scenarios(dragon_verts, dragon_tets, mesh):
+    """(name, (verts, tets), physicsParams, substeps, checkpoints) for the WebGL solver (SoftBodyGPU), dt = 1/1200 (its default
+    20 substeps per frame).  No grab: the shader's indexFromUV decode pins the wrong particle (src/SoftbodyGPU.js:336-338, its
+    own comment says so) and is deliberately not replicated; bounds are the shader's hard-coded ones (:347) = the defaults."""
+    beam = mesh.make_beam((3, 2, 2), h=0.2, y0=0.0008, jitter=0.2)
+    return [
+        ("polar_dragon", (dragon_verts, dragon_tets), _p(), 10, (1, 5, 10)),
+        # floor contact within the run, friction below the min(1, dt * friction) knee, other gravity
+        ("polar_beam", beam, _p(friction=300.0, gravity=-12.0), 40, (1, 20, 40)),
+    ]

@@ -5,10 +5,13 @@
  * class SoftBody in src/Softbody.js.  It is NOT part of the product: only tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or known-answer fixtures for
- * this path, and no JavaScript engine exists in the build image, so the reference itself cannot
- * be executed.  The oracle is pinned only against (i) a second, independently structured numpy
- * restatement (oracle/oracle_np.py), (ii) analytic properties and (iii) a finite-difference XPBD projection of the
+ * PARITY PINNED TO THE REFERENCE'S OWN TEXT (round 2).  The reference ships no tests or golden vectors and no JavaScript
+ * engine exists in the build image, so it cannot be executed as is; instead tools/transpile_reference.py mechanically
+ * re-emits src/Softbody.js (class SoftBody, every method) as Python under JS number semantics (oracle/jsrt.py),
+ * tools/make_ref_golden.py executes that on Dragon (free fall, contact + clamp, compliance, grab) and commits
+ * tests/golden/ref_golden.npz, and tests/test_reference_pin.py requires this file to reproduce every vector BIT FOR BIT
+ * (and re-runs the transpile live where /root/reference exists).  Older pins stay: (i) a second, independently structured
+ * numpy restatement (oracle/oracle_np.py), (ii) analytic properties and (iii) a finite-difference XPBD projection of the
  * published constraint functions (tests/test_oracle.py).
  *
  * Arithmetic rule being restated (JavaScript typed-array semantics):

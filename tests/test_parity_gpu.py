@@ -664,6 +664,25 @@ def test_cuda_init_skinning_and_polar_init_equal_the_transpiled_reference(dragon
     assert_bit_equal(g.quats.reshape(M, 4), REF_GOLD["gpu_quats0"].reshape(-1, 4)[:M], "quats0")
 
 
+@pytest.mark.parametrize("which", [0, 1], ids=["polar_dragon", "polar_beam"])
+def test_cuda_bitexact_reproduces_the_transpiled_webgl_solver(dragon, which):
+    """SoftBodyGPU in BITEXACT arithmetic against vectors produced by executing the reference's own JavaScript + GLSL
+    (transpiled, tools/transpile_reference.py + tools/transpile_shaders.py): bit for bit, the oracle not involved."""
+    name, (v, t), params, steps, save = ref_scenarios.polar_scenarios(dragon["tet_verts"], dragon["tet_ids"], mesh)[which]
+    p = dict(ts.default_physics_params(False), **params)
+    sb = ts.SoftBodyGPU(v, t, None, p, arithmetic="bitexact", reference_table_bug=True)
+    M = t.size // 4
+    for s in range(1, steps + 1):
+        sb.simulate((1.0 / 60.0) / 20, p)
+        if s in save:
+            assert_bit_equal(sb.pos, REF_GOLD["%s_pos_%d" % (name, s)], "%s pos @%d" % (name, s))
+            assert_bit_equal(sb.prevPos, REF_GOLD["%s_prev_%d" % (name, s)], "%s prevPos @%d" % (name, s))
+            assert_bit_equal(sb.vel, REF_GOLD["%s_vel_%d" % (name, s)], "%s vel @%d" % (name, s))
+            assert_bit_equal(sb.quats, REF_GOLD["%s_quat_%d" % (name, s)], "%s quats @%d" % (name, s))
+            assert_bit_equal(sb.elems, REF_GOLD["%s_rest_%d" % (name, s)], "%s elems @%d" % (name, s))
+    assert sb.quats.size == 4 * M
+
+
 def test_config4_bench_configuration_100_substeps():
     """BASELINE config 4 exactly as bench.py runs it -- T = 512 tiles, 20-substep CUDA graphs (tetsim_step, post of one
     substep fused with the predict of the next), dt = 1/1200, iters = 1 -- on a JITTERED 1,038,336-tet beam, 100 substeps

@@ -9,8 +9,10 @@ scenarios of oracle/ref_scenarios.py on that code and committed tests/golden/ref
     the initPhysics arrays, skinning) and the polar oracle's reverse table must equal the reference's 9 x RGBA tables.
   * CPU, when /root/reference is present (this container): the transpile is re-run from scratch and executed live
     against the oracle, and its first checkpoints must equal the committed fixture (the fixture is not stale).
-  * GPU: tests/test_parity_gpu.py::test_cuda_bitexact_reproduces_the_transpiled_reference runs the same scenarios
-    through the C ABI.
+  * The WebGL solver likewise: JavaScript (initPhysics, simulate, the GPGPU runtime's compute) AND the seven GLSL passes are
+    transpiled and executed texel by texel; the polar oracle reproduces those vectors bit for bit.
+  * GPU: tests/test_parity_gpu.py::test_cuda_bitexact_reproduces_the_transpiled_reference (and ..._webgl_solver) run the same
+    scenarios through the C ABI.
 """
 import os
 
@@ -118,19 +120,65 @@ def test_live_transpile_matches_oracle_and_fixture(dragon):
         assert np.array_equal(g.tex("particleToElemVertsTable", k), GOLD["gpu_table_%d" % k])
 
 
+def _polar_cases(dragon):
+    return ref_scenarios.polar_scenarios(dragon["tet_verts"], dragon["tet_ids"], mesh)
+
+
+@pytest.mark.parametrize("which", [0, 1], ids=["polar_dragon", "polar_beam"])
+def test_polar_oracle_reproduces_the_transpiled_webgl_solver(dragon, which):
+    """The WHOLE WebGL substep executed from the reference's text -- SoftBodyGPU.initPhysics + simulate and the GPGPU
+    runtime's addVariable / addPass / compute transpiled from JavaScript, the seven passes transpiled from GLSL
+    (tools/transpile_shaders.py), run texel by texel -- produced these vectors; the C restatement (oracle/polar_oracle.c)
+    must reproduce positions, prevPos, velocities, quaternions and goal corners BIT FOR BIT, free fall and floor contact."""
+    name, (v, t), params, steps, save = _polar_cases(dragon)[which]
+    po = oracle.PolarOracle(v, t, reference_table_bug=True, **params)
+    for s in range(1, steps + 1):
+        po.simulate(ref_scenarios.FRAME_DT / 20, params)
+        if s in save:
+            for k, a in dict(pos=po.pos, prev=po.prevPos, vel=po.vel, quat=po.quat, rest=po.rest).items():
+                assert_bit_equal(a, GOLD["%s_%s_%d" % (name, k, s)], "%s %s @%d" % (name, k, s))
+    if which == 1:
+        assert np.any(po.pos[1::3] == 0.0), "the beam is meant to reach the floor"
+
+
+@pytest.mark.skipif(not ref_runner.reference_present(), reason="/root/reference is only present in the build container")
+def test_live_transpiled_webgl_solver_matches_polar_oracle(dragon):
+    """Re-run both transpilers (JavaScript and GLSL) on the reference's text and execute the result: a 12-tet body for 12
+    substeps equals the polar oracle bit for bit, and the first checkpoint of the committed beam fixture is reproduced."""
+    assert ref_runner.ensure()
+    v, t = mesh.make_beam((2, 1, 1), h=0.25, y0=0.004)
+    v = v.copy()
+    v[1::3] += np.float32(0.01) * np.arange(v.size // 3, dtype=np.float32)
+    params = dict(ref_scenarios.DEFAULTS)
+    ref = ref_runner.RefSoftBodyGPU(v, t, params)
+    po = oracle.PolarOracle(v, t, reference_table_bug=True)
+    for _ in range(12):
+        ref.simulate(ref_scenarios.FRAME_DT / 20, params)
+        po.simulate(ref_scenarios.FRAME_DT / 20)
+    for k, a, b in (("pos", ref.pos, po.pos), ("prev", ref.prevPos, po.prevPos), ("vel", ref.vel, po.vel), ("quat", ref.quat, po.quat),
+                    ("rest", ref.rest, po.rest)):
+        assert_bit_equal(a, b, k)
+    name, (bv, bt), bp, _, _ = _polar_cases(dragon)[1]
+    ref = ref_runner.RefSoftBodyGPU(bv, bt, bp)
+    ref.simulate(ref_scenarios.FRAME_DT / 20, bp)
+    assert_bit_equal(ref.pos, GOLD["polar_beam_pos_1"], "fixture pos @1")
+    assert_bit_equal(ref.rest, GOLD["polar_beam_rest_1"], "fixture rest @1")
+
+
 def test_transpiler_rejects_what_it_does_not_understand(tmp_path):
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools"))
-    try:
-        import transpile_reference as tr
-    finally:
-        sys.path.pop(0)
+    import transpile_reference as tr
     for bad in ("f() { while (1) { } }", "f() { let a = 1; for (let i = 0; i < 2; i++) { let a = 2; } }", "f(a) { a[0] = b = 1; }",
                 "f(a) { x = ++a; }", "f() { for (;;) { continue; } }"):
         p = tmp_path / "x.js"
         p.write_text("class K {\n %s \n}\n" % bad)
         with pytest.raises(tr.Unsupported):
             tr.transpile_class(str(p), "K")
+    import transpile_shaders as tsh
+    for bad in ("void main() { while (true) { } }", "void main() { float a = b ? 1.0 : ; }", "void main() { discard; }", "struct S { float a; };"):
+        with pytest.raises(tsh.Unsupported):
+            tsh.transpile_shader("x", bad, [])
     # and the evaluation-order rule that matters (src/Softbody.js:350-355: dst[dnr] = f(dst[dnr++]))
     p = tmp_path / "y.js"
     p.write_text("class K {\n f(d, n) { d[n] = 10 + d[n++]; return n; }\n}\n")

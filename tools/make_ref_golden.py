@@ -61,6 +61,17 @@ def main():
         out["gpu_elems0_%d" % k] = g.tex("elems0", k)
     for name in ("pos0", "vel0", "invMass", "invRestVolumeAndColor", "elemToParticlesTable", "quats0"):
         out["gpu_" + name] = g.tex(name)
+    # ---- the WebGL solver, whole substeps: initPhysics + simulate + the GPGPU runtime's compute() transpiled from JavaScript,
+    # the seven passes transpiled from GLSL (tools/transpile_shaders.py), executed texel by texel (oracle/ref_runner.py) ----
+    from tetsim_b200 import mesh as tmesh
+    for name, (pv, pt), params, steps, save in ref_scenarios.polar_scenarios(V, T, tmesh):
+        body = ref_runner.RefSoftBodyGPU(pv, pt, params)
+        for s in range(1, steps + 1):
+            body.simulate(ref_scenarios.FRAME_DT / 20, params)
+            if s in save:
+                for k, a in dict(pos=body.pos, prev=body.prevPos, vel=body.vel, quat=body.quat, rest=body.rest).items():
+                    out["%s_%s_%d" % (name, k, s)] = a
+        print("%-12s %3d substeps  %.1f s" % (name, steps, time.time() - t0), flush=True)
     path = os.path.join(ROOT, "tests", "golden", "ref_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays")

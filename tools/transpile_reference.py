@@ -309,6 +309,18 @@ class Parser:
                     self.eat(",")
             self.eat("]")
             return ("array", elems)
+        if tk[1] == "{":          # object literal { key: expr, ... } (only reachable in expression position)
+            props = []
+            while not self.at("}"):
+                k = self.eat()
+                if k[0] not in ("name", "str"):
+                    raise Unsupported("line %d: object key %r" % (k[2], k[1]))
+                self.eat(":")
+                props.append((k[1] if k[0] == "name" else k[1][1:-1], self.parse_assign()))
+                if self.at(","):
+                    self.eat(",")
+            self.eat("}")
+            return ("object", props)
         raise Unsupported("line %d: unexpected %r" % (tk[2], tk[1]))
 
 
@@ -365,9 +377,11 @@ class Emitter:
             return self.ex(e[1]) + "(" + ", ".join(self.ex(a) for a in e[2]) + ")"
         if k == "array":
             return "JSArray([" + ", ".join(self.ex(a) for a in e[1]) + "])"
+        if k == "object":
+            return "JSObject(" + ", ".join("%s=%s" % (ident(n), self.ex(v)) for n, v in e[1]) + ")"
         if k == "unary":
             if e[1] == "!":
-                return "(not " + self.ex(e[2]) + ")"
+                return "(not _truthy(" + self.ex(e[2]) + "))"
             return "(" + e[1] + self.ex(e[2]) + ")"
         if k == "postfix":
             if e[2][0] != "name":
@@ -380,15 +394,17 @@ class Emitter:
                 return "_div(%s, %s)" % (l, r)
             if op == "%":
                 return "_mod(%s, %s)" % (l, r)
-            if op == "&&":
-                return "(%s and %s)" % (l, r)
+            if op == "&&":   # JS truthiness (NaN / undefined are falsy), operand values returned like JS does
+                t = self.new_tmp()
+                return "(%s if _truthy(%s := %s) else %s)" % (r, t, l, t)
             if op == "||":
-                return "(%s or %s)" % (l, r)
+                t = self.new_tmp()
+                return "(%s if _truthy(%s := %s) else %s)" % (t, t, l, r)
             if op in CMP:
                 return "(%s %s %s)" % (l, CMP[op], r)
             return "(%s %s %s)" % (l, op, r)   # + - * : left-associative tree, parenthesised as parsed
         if k == "cond":
-            return "(%s if %s else %s)" % (self.ex(e[2]), self.ex(e[1]), self.ex(e[3]))
+            return "(%s if _truthy(%s) else %s)" % (self.ex(e[2]), self.ex(e[1]), self.ex(e[3]))
         if k == "assign":
             raise Unsupported("assignment used as a value")
         raise Unsupported("expression kind %r" % (k,))
@@ -447,7 +463,7 @@ class Emitter:
             else:
                 self.out(d, self.ex(e))
         elif k == "if":
-            self.out(d, "if %s:" % self.ex(s[1]))
+            self.out(d, "if _truthy(%s):" % self.ex(s[1]))
             self.body(d + 1, s[2], scope)
             if s[3] is not None:
                 self.out(d, "else:")
@@ -456,7 +472,7 @@ class Emitter:
             inner = {n: "outer" for n in scope}
             if s[1] is not None:
                 self.stmt(d, s[1], inner)
-            self.out(d, "while %s:" % (self.ex(s[2]) if s[2] is not None else "True"))
+            self.out(d, "while %s:" % ("_truthy(%s)" % self.ex(s[2]) if s[2] is not None else "True"))
             self.body(d + 1, s[4], inner)
             if s[3] is not None:
                 self.stmt(d + 1, ("expr", s[3]), inner)
@@ -562,6 +578,34 @@ def method_spans(body, line0):
     return out
 
 
+def function_members(src, names):
+    """`this.NAME = function (args) { body }` inside a constructor (src/MultiTargetGPUComputationRenderer.js) -> {NAME: (method text, line)}."""
+    out = {}
+    for n in names:
+        m = re.search(r"this\.%s\s*=\s*function\s*\(([^)]*)\)\s*\{" % re.escape(n), src)
+        if not m:
+            raise Unsupported("function member %s not found" % n)
+        depth, k = 1, m.end()
+        while depth:
+            depth += {"{": 1, "}": -1}.get(src[k], 0)
+            k += 1
+        out[n] = ("%s(%s) {%s" % (n, m.group(1), src[m.end():k]), src.count("\n", 0, m.start()) + 1)
+    return out
+
+
+def transpile_members(path, cls, names, rel=None):
+    src = open(path).read()
+    spans = function_members(src, names)
+    em = Emitter()
+    em.out(0, "class %s:" % cls)
+    for n in names:
+        text, ln = spans[n]
+        methods = Parser(tokenize(text + "}", ln)).parse_class_body()
+        em.out(1, "# %s:%d" % (rel or path, ln))
+        em.method(*methods[0][:3])
+    return "\n".join(em.lines), {n: spans[n][1] for n in names}
+
+
 def transpile_class(path, cls, only=None, rel=None):
     src = open(path).read()
     body, line0 = class_span(src, cls)
@@ -585,11 +629,11 @@ def transpile_class(path, cls, only=None, rel=None):
 HEADER = '''"""GENERATED by tools/transpile_reference.py from %s -- do not edit, do not commit.
 Token-for-token re-emission of the reference's own text; JS semantics live in oracle/jsrt.py."""
 from oracle.jsrt import *  # noqa: F401,F403
-from oracle.jsrt import _div, _mod  # noqa: F401
+from oracle.jsrt import _div, _mod, _truthy  # noqa: F401
 
 '''
 
-GPU_METHODS = ["initPhysics", "updateVisMesh", "startGrab", "moveGrabbed", "endGrab", "vecSetZero", "vecCopy", "vecAdd",
+GPU_METHODS = ["initPhysics", "simulate", "updateVisMesh", "startGrab", "moveGrabbed", "endGrab", "vecSetZero", "vecCopy", "vecAdd",
                "vecSetDiff", "vecDistSquared", "matGetDeterminant"]
 
 
@@ -605,6 +649,13 @@ def generate(ref="/root/reference", out=None):
     text, lines = transpile_class(os.path.join(ref, "src", "SoftbodyGPU.js"), "SoftBodyGPU", GPU_METHODS, "src/SoftbodyGPU.js")
     open(os.path.join(out, "softbodygpu_ref.py"), "w").write(HEADER % "src/SoftbodyGPU.js (class SoftBodyGPU: initPhysics, grab, vec*/mat*)" + text + "\n")
     report["SoftBodyGPU"] = lines
+    text, lines = transpile_members(os.path.join(ref, "src", "MultiTargetGPUComputationRenderer.js"), "MultiTargetGPUComputationRenderer",
+                                    ["addVariable", "addPass", "compute", "getCurrentRenderTarget"], "src/MultiTargetGPUComputationRenderer.js")
+    open(os.path.join(out, "gpucompute_ref.py"), "w").write(HEADER % "src/MultiTargetGPUComputationRenderer.js (addVariable, addPass, compute, getCurrentRenderTarget)" + text + "\n")
+    report["MultiTargetGPUComputationRenderer"] = lines
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import transpile_shaders
+    report["GLSL passes"] = transpile_shaders.generate(ref, out)
     return out, report
 
 
