@@ -53,7 +53,7 @@ def parse():
                     "0 = the regular Kuhn grid of BASELINE config 4")
     ap.add_argument("--substeps", type=int, default=20, help="substeps per step (frame)")
     ap.add_argument("--iters", type=int, default=1)
-    ap.add_argument("--cluster-size", type=int, default=0, help="tets per tile (default 512 for the NH tile kernel -- measured fastest, profiles/r2_tile_experiments.txt -- and 256 for the polar tile kernel)")
+    ap.add_argument("--cluster-size", type=int, default=0, help="tets per tile (default 512 for the NH tile kernel -- measured fastest, profiles/r2_tile_experiments.txt -- and 128 for the polar tile kernel)")
     ap.add_argument("--no-reorder", action="store_true")
     ap.add_argument("--atomic", action="store_true", help="deterministic=0: REDG flush instead of per-tile partials")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
@@ -320,7 +320,7 @@ def main():
         args.exchange = "peer"
     polar = args.workload == "polar"
     if not args.cluster_size:
-        args.cluster_size = 256 if polar else 512
+        args.cluster_size = 128 if polar else 512
     if polar:
         args.no_configs = True
     cells = tuple(int(c) for c in args.cells.split(","))

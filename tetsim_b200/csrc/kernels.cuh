@@ -474,7 +474,7 @@ __global__ void k_skin_polar(int nVis, const float4 *__restrict__ vis, const int
     outPos[3 * (size_t)i + 2] = ((p0.z * b0 + p1.z * b1) + p2.z * b2) + p3.z * b3;
     if (outNrm) {
         float4 q4;
-        if (tetRecord) { const int r = tetRecord[e]; q4 = *reinterpret_cast<const float4 *>(tileTets + (size_t)(r / T) * T * 96 + (size_t)T * 48 + (size_t)(r % T) * 16); }
+        if (tetRecord) { const int r = tetRecord[e]; q4 = *reinterpret_cast<const float4 *>(tileTets + (size_t)(r / T) * T * 80 + (size_t)T * 48 + (size_t)(r % T) * 16); }
         else q4 = quat[e];
         const V3 n = pl_rotate({restNrm[3 * (size_t)i], restNrm[3 * (size_t)i + 1], restNrm[3 * (size_t)i + 2]}, {q4.x, q4.y, q4.z, q4.w});
         outNrm[3 * (size_t)i] = n.x; outNrm[3 * (size_t)i + 1] = n.y; outNrm[3 * (size_t)i + 2] = n.z;

@@ -1031,9 +1031,10 @@ void launch_build_stream_metric(cudaStream_t s, int count, const int *order, con
 // Tiled polar-decomposition shape matching (SoftBodyGPU, src/SoftbodyGPU.js:59-376) -- the throughput form of BASELINE
 // config 2.  Same tiling as the Neo-Hookean tile kernel (ClusterPlan: Hilbert-ordered tiles, vertex tile staged in shared
 // memory, grouped-row corner buffer); per tet it streams what the reference keeps in its `elems` / `quats` render targets:
-//   tile block, T * 96 B, plane-major:  R0 R1 R2 (goal corners, 12 floats, read AND written back -- the reference rotates
-//   its rest tet incrementally, :253-262), Qt (quaternion, read + written), C (4 vertex slots + 4 corner destinations),
-//   E (x = rest volume V, negative = "drop corner 0", the reference's table quirk :568; 0 = unused record slot).
+//   tile block, T * 80 B, plane-major:  R0 R1 R2 (goal corners, 12 floats, read AND written back -- the reference rotates
+//   its rest tet incrementally, :253-262), Qt (quaternion, read + written), C (4 vertex slots + 4 corner destinations);
+//   plus one float per record, vol[] = rest volume V (negative = "drop corner 0", the reference's table quirk :568;
+//   0 = unused record slot) -- 84 B read + 64 B written per tet, the 148 B of the algorithmic figure.
 // K3 + K4 run per tet in registers (polar_solve), every corner's goal * V and V go to the corner buffer (STS.128, .w = V --
 // the reference's vec4(goal, V), :259-262), per-tile-vertex sums leave as one float4 partial (sum goal V, sum V).  K5's
 // per-particle gather over <= 36 scattered texels becomes a sum of ~2.4 tile partials in k_polar_vertex_tiles, so the
@@ -1051,15 +1052,16 @@ __global__ void __launch_bounds__(T) k_polar_tiles(PolarTileArgs a) {
     const int mlen = (int)(a.metaOff[tile + 1] - a.metaOff[tile]);
     for (int i = tid; i < mlen; i += T) reinterpret_cast<uint4 *>(sm)[i] = __ldg(mg + i);
     // this tet's record (coalesced LDG.128 per plane), in flight while the vertex tile is gathered
-    unsigned char *tb = a.tets + (size_t)tile * T * 96;
+    unsigned char *tb = a.tets + (size_t)tile * T * 80;
     const float4 r0 = ldg_stream4(tb + tid * 16), r1 = ldg_stream4(tb + T * 16 + tid * 16), r2 = ldg_stream4(tb + T * 32 + tid * 16);
-    const float4 qt = ldg_stream4(tb + T * 48 + tid * 16), cc = ldg_stream4(tb + T * 64 + tid * 16), ee = ldg_stream4(tb + T * 80 + tid * 16);
+    const float4 qt = ldg_stream4(tb + T * 48 + tid * 16), cc = ldg_stream4(tb + T * 64 + tid * 16);
+    const float vol = __ldg(a.vol + (size_t)tile * T + tid);
     __syncthreads();
     const int v0 = reinterpret_cast<const int *>(sm)[0], nl = reinterpret_cast<const int *>(sm)[1];
     const int *ids = reinterpret_cast<const int *>(sm + reinterpret_cast<const int *>(sm)[3]);
     for (int j = tid; j < nl; j += T) sx[j] = a.x4[ids[j]];
     __syncthreads();
-    if (ee.x != 0.0f) {
+    if (vol != 0.0f) {
         const unsigned s01 = __float_as_uint(cc.x), s23 = __float_as_uint(cc.y), d01 = __float_as_uint(cc.z), d23 = __float_as_uint(cc.w);
         const unsigned char *sxb = reinterpret_cast<const unsigned char *>(sx);
         const float4 p0 = *reinterpret_cast<const float4 *>(sxb + (s01 & 0xffffu)), p1 = *reinterpret_cast<const float4 *>(sxb + (s01 >> 16));
@@ -1072,7 +1074,7 @@ __global__ void __launch_bounds__(T) k_polar_tiles(PolarTileArgs a) {
         reinterpret_cast<float4 *>(tb + T * 16)[tid] = make_float4(last[1].y, last[1].z, last[2].x, last[2].y);
         reinterpret_cast<float4 *>(tb + T * 32)[tid] = make_float4(last[2].z, last[3].x, last[3].y, last[3].z);
         reinterpret_cast<float4 *>(tb + T * 48)[tid] = make_float4(q.x, q.y, q.z, q.w);
-        const float V = fabsf(ee.x), V0 = ee.x < 0.0f ? 0.0f : V;   // corner 0 of tet 0 is dropped from its particle's average (:568)
+        const float V = fabsf(vol), V0 = vol < 0.0f ? 0.0f : V;   // corner 0 of tet 0 is dropped from its particle's average (:568)
         *reinterpret_cast<float4 *>(sdx + (d01 & 0xffffu)) = make_float4(last[0].x * V0, last[0].y * V0, last[0].z * V0, V0);
         *reinterpret_cast<float4 *>(sdx + (d01 >> 16)) = make_float4(last[1].x * V, last[1].y * V, last[1].z * V, V);
         *reinterpret_cast<float4 *>(sdx + (d23 & 0xffffu)) = make_float4(last[2].x * V, last[2].y * V, last[2].z * V, V);
@@ -1161,34 +1163,35 @@ void launch_polar_vertex_tiles(cudaStream_t s, int N, int mode, float4 *x4, floa
 template <int T>
 __global__ void k_build_polar_tiles(int numRecords, const int *__restrict__ order, const float4 *__restrict__ x4, const int4 *__restrict__ ids,
                                     const float *__restrict__ irv, const uint4 *__restrict__ aux, int dropTet0Corner0,
-                                    unsigned char *__restrict__ tets) {
+                                    unsigned char *__restrict__ tets, float *__restrict__ vol) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= numRecords) return;
     const int tile = r / T, t = r % T;
-    unsigned char *tb = tets + (size_t)tile * T * 96;
+    unsigned char *tb = tets + (size_t)tile * T * 80;
     const int e = order[r];
-    float4 R0 = make_float4(0.f, 0.f, 0.f, 0.f), R1 = R0, R2 = R0, Q = make_float4(0.f, 0.f, 0.f, 1.f), E = R0;
+    float4 R0 = make_float4(0.f, 0.f, 0.f, 0.f), R1 = R0, R2 = R0, Q = make_float4(0.f, 0.f, 0.f, 1.f);
+    float Vs = 0.0f;
     if (e >= 0) {
         const int4 id = ids[e];
         const float4 a0 = x4[id.x], a1 = x4[id.y], a2 = x4[id.z], a3 = x4[id.w];
         R0 = make_float4(a0.x, a0.y, a0.z, a1.x); R1 = make_float4(a1.y, a1.z, a2.x, a2.y); R2 = make_float4(a2.z, a3.x, a3.y, a3.z);
         const float V = __fdiv_rn(1.0f, irv[e]);   // the shader's 1.0 / invRestVolume, :220
-        E.x = (dropTet0Corner0 && e == 0) ? -V : V;
+        Vs = (dropTet0Corner0 && e == 0) ? -V : V;
     }
     reinterpret_cast<float4 *>(tb)[t] = R0;
     reinterpret_cast<float4 *>(tb + T * 16)[t] = R1;
     reinterpret_cast<float4 *>(tb + T * 32)[t] = R2;
     reinterpret_cast<float4 *>(tb + T * 48)[t] = Q;
     reinterpret_cast<uint4 *>(tb + T * 64)[t] = aux[r];
-    reinterpret_cast<float4 *>(tb + T * 80)[t] = E;
+    vol[r] = Vs;
 }
 void launch_build_polar_tiles(cudaStream_t s, int clusterSize, int numRecords, const int *order, const float4 *x4, const int4 *ids,
-                              const float *irv, const uint4 *aux, int dropTet0Corner0, unsigned char *tets) {
+                              const float *irv, const uint4 *aux, int dropTet0Corner0, unsigned char *tets, float *vol) {
     if (numRecords <= 0) return;
     const int g = cdiv(numRecords, 256);
-    if (clusterSize == 128) k_build_polar_tiles<128><<<g, 256, 0, s>>>(numRecords, order, x4, ids, irv, aux, dropTet0Corner0, tets);
-    else if (clusterSize == 256) k_build_polar_tiles<256><<<g, 256, 0, s>>>(numRecords, order, x4, ids, irv, aux, dropTet0Corner0, tets);
-    else k_build_polar_tiles<512><<<g, 256, 0, s>>>(numRecords, order, x4, ids, irv, aux, dropTet0Corner0, tets);
+    if (clusterSize == 128) k_build_polar_tiles<128><<<g, 256, 0, s>>>(numRecords, order, x4, ids, irv, aux, dropTet0Corner0, tets, vol);
+    else if (clusterSize == 256) k_build_polar_tiles<256><<<g, 256, 0, s>>>(numRecords, order, x4, ids, irv, aux, dropTet0Corner0, tets, vol);
+    else k_build_polar_tiles<512><<<g, 256, 0, s>>>(numRecords, order, x4, ids, irv, aux, dropTet0Corner0, tets, vol);
 }
 
 // =================================================================================================

@@ -155,7 +155,8 @@ void launch_build_stream_metric(cudaStream_t, int count, const int *order, const
 // ---- FAST-only throughput path of the polar solver: tiled shape matching (kernels_fast.cu) ----
 struct PolarTileArgs {
     const float4 *x4;
-    unsigned char *tets;            // [numTiles * T * 96] R0 R1 R2 Qt C E planes per tile (read and written)
+    unsigned char *tets;            // [numTiles * T * 80] R0 R1 R2 Qt C planes per tile (read and written)
+    const float *vol;               // [numTiles * T] rest volume per record (negative: drop corner 0; 0: unused slot)
     const unsigned char *meta;      // the ClusterPlan's per-tile metadata blocks
     const uint32_t *metaOff;
     int numTiles, metaStride, metaValOff, maxTileVertsPad, maxTileEntries;
@@ -167,7 +168,7 @@ size_t polar_tiles_smem(const PolarTileArgs &a);
 void launch_polar_vertex_tiles(cudaStream_t, int N, int mode, float4 *x4, float4 *prev4, float4 *vel4, const int *vpStart,
                                const int *vpSlot, const float4 *part, const int *vertId, const SubstepParams *sp);
 void launch_build_polar_tiles(cudaStream_t, int clusterSize, int numRecords, const int *order, const float4 *x4, const int4 *ids,
-                              const float *irv, const uint4 *aux, int dropTet0Corner0, unsigned char *tets);
+                              const float *irv, const uint4 *aux, int dropTet0Corner0, unsigned char *tets, float *vol);
 
 // ---- utility kernels (kernels_fast.cu) ----
 void launch_pack3(cudaStream_t, int N, const float4 *src, const int *perm, float *dst3);       // dst[perm[i]] = src[i].xyz

@@ -148,6 +148,7 @@ struct tetsim {
     ClusterPlan plan;
     DevBuf<int> vpStart, vpSlot;
     DevBuf<unsigned char> tileTets, tileMeta;
+    DevBuf<float> tileVol;                // tiled polar solver: rest volume per record
     DevBuf<uint32_t> metaOff;
     DevBuf<float4> part, acc, bsum;
     DevBuf<float> invVal;
@@ -520,8 +521,9 @@ int build_polar(tetsim *h, const std::vector<int> &tetIds) {
         DevBuf<uint4> aux;
         CK(aux.alloc(nRec));
         if (nRec) CK(cudaMemcpyAsync(aux.p, P.recordAux.data(), nRec * sizeof(uint4), cudaMemcpyHostToDevice, s));
-        CK(h->tileTets.alloc(nRec * 96));
-        launch_build_polar_tiles(s, P.T, (int)nRec, h->order.p, h->x4.p, h->ids.p, h->irv.p, aux.p, h->opt.referenceTableBug != 0, h->tileTets.p);
+        CK(h->tileTets.alloc(nRec * 80));
+        CK(h->tileVol.alloc(std::max<size_t>(nRec, 1)));
+        launch_build_polar_tiles(s, P.T, (int)nRec, h->order.p, h->x4.p, h->ids.p, h->irv.p, aux.p, h->opt.referenceTableBug != 0, h->tileTets.p, h->tileVol.p);
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(s));
         aux.release();
@@ -548,7 +550,7 @@ int build_polar(tetsim *h, const std::vector<int> &tetIds) {
 PolarTileArgs polar_tile_args(const tetsim *h) {
     const ClusterPlan &P = h->plan;
     PolarTileArgs a{};
-    a.x4 = h->x4.p; a.tets = h->tileTets.p; a.meta = h->tileMeta.p; a.metaOff = h->metaOff.p;
+    a.x4 = h->x4.p; a.tets = h->tileTets.p; a.vol = h->tileVol.p; a.meta = h->tileMeta.p; a.metaOff = h->metaOff.p;
     a.numTiles = P.numClusters; a.metaStride = P.metaStride; a.metaValOff = P.metaValOff;
     a.maxTileVertsPad = P.maxTileVertsPad; a.maxTileEntries = P.maxTileEntries; a.part = h->part.p;
     return a;
@@ -1120,7 +1122,7 @@ void tetsim_destroy(tetsim_t *h) {
     for (auto *b : f4) b->release();
     DevBuf<int> *i1[] = {&h->vertId, &h->cStart, &h->cEnt, &h->order, &h->levelStart, &h->vpStart, &h->vpSlot, &h->tStart, &h->tEnt, &h->grabOut, &h->visTri, &h->vtStart, &h->vtEnt};
     for (auto *b : i1) b->release();
-    h->visRestNrm.release(); h->tetRecord.release();
+    h->visRestNrm.release(); h->tetRecord.release(); h->tileVol.release();
     DevBuf<float> *f1[] = {&h->Q9, &h->irv, &h->invMass, &h->invVal, &h->stageIn[0], &h->stageIn[1], &h->stageOut[0], &h->stageOut[1], &h->visPos, &h->visNrm};
     for (auto *b : f1) b->release();
     h->ids.release(); h->I.release(); h->bodies.release(); h->volTerm.release(); h->volOut.release();
@@ -1214,7 +1216,7 @@ int tetsim_get_polar_state(tetsim_t *h, float *rest12, float *quat4) {
         for (size_t r = 0; r < P.recordTet.size(); r++) {
             const int e = P.recordTet[r];
             if (e < 0) continue;
-            const unsigned char *tb = blocks.data() + (r / T) * T * 96;
+            const unsigned char *tb = blocks.data() + (r / T) * T * 80;
             const size_t t = r % T;
             if (rest12) {
                 const float *R0 = reinterpret_cast<const float *>(tb) + 4 * t, *R1 = reinterpret_cast<const float *>(tb + T * 16) + 4 * t,
