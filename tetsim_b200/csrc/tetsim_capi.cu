@@ -398,6 +398,7 @@ int build_gs(tetsim *h, const std::vector<float> &verts, const std::vector<int> 
     if (h->gsQuads) {
         launch_build_stream_metric(s, M, h->order.p, h->Q9.p, h->irv.p, h->A.p, h->B.p);
         h->bodyThreads = std::max(64, std::min(512, 32 * ((4 * h->maxLevelSize + 31) / 32)));
+        if (const char *e = getenv("TETSIM_GS_THREADS")) { const int v = atoi(e); if (v >= 32 && v <= 1024 && v % 32 == 0) h->bodyThreads = v; }
     } else {
         CK(h->C.alloc((size_t)M));
         CK(cudaMemsetAsync(h->C.p, 0, h->C.bytes(), s));
