@@ -359,8 +359,15 @@ __device__ __forceinline__ Q4 pl_extract_rotation(const V3 A[3], Q4 q) {  // ext
 // exit `w < 1e-9` (:131) is unreachable in float32 once |A| ~ edge^2 (the residual rotation of a converged iterate is
 // ~1e-7), so its last five or six of nine iterations only stir rounding noise.  kPolarEps is the measured trade-off:
 // tests/test_parity_gpu.py keeps the result within the polar tolerance of the oracle (which always runs the shader's loop).
+// The floor scales with the mesh: A = sum (cur - cc)(last - lc)^T is built from positions that carry half an ulp of |x|
+// each, so omega = num / den cannot be known better than ~ 2^-24 |x| / L (L^2 = sum |last - lc|^2 ~ den): on the Dragon
+// (|x| ~ 1, edges ~ 0.1) that IS ~1e-6, on the 1 cm beam it is ~1e-5, where a fixed 1e-6 never triggers and all nine
+// iterations run.  noise2 = (k 2^-24)^2 |cc|^2 (k = 4; TETSIM_POLAR_NOISE_K overrides, 0 = fixed floor only); the loop leaves
+// when |omega|^2 den < noise2 or |omega| < kPolarEps.  Measured (profiles/r2_polar_exit_rule.txt): no visible change of the
+// error against the nine-iteration BITEXACT path for k = 0..8; kernel 0.416 -> 0.300 ms in free fall, 0.50 -> 0.42 ms on the
+// crumpling beam (the reference's iteration converges only linearly there, so most warps still need all nine).
 constexpr float kPolarEps = 1.0e-6f;
-__device__ __forceinline__ Q4 pl_extract_rotation_fast(const V3 A[3], Q4 q) {
+__device__ __forceinline__ Q4 pl_extract_rotation_fast(const V3 A[3], Q4 q, float noise2) {
     for (int iter = 0; iter < 9; iter++) {
         const float xx = q.x * q.x, yy = q.y * q.y, zz = q.z * q.z, xy = q.x * q.y, xz = q.x * q.z, yz = q.y * q.z;
         const float wx = q.w * q.x, wy = q.w * q.y, wz = q.w * q.z;
@@ -371,7 +378,7 @@ __device__ __forceinline__ Q4 pl_extract_rotation_fast(const V3 A[3], Q4 q) {
         const float den = pl_dot(X, A[0]) + pl_dot(Y, A[1]) + pl_dot(Z, A[2]) + 0.000000001f;
         const V3 omega = pl_mul(num, __fdividef(1.0f, fabsf(den)));
         const float w2 = pl_dot(omega, omega);
-        if (w2 < kPolarEps * kPolarEps) break;
+        if (w2 < kPolarEps * kPolarEps || w2 * fabsf(den) < noise2) break;
         const float rw = rsqrtf(w2), w = w2 * rw, half = w * 0.5f;
         const float s = __sinf(half) * rw, c = __sinf(half + 1.57f);   // the shader's cosine, :108
         const Q4 dq = {omega.x * s, omega.y * s, omega.z * s, c};
@@ -381,7 +388,7 @@ __device__ __forceinline__ Q4 pl_extract_rotation_fast(const V3 A[3], Q4 q) {
 }
 // K3 + K4 for one tet: cur[4] current corner positions, last[4] in/out goal corners, quat in/out.
 template <bool EXACT, bool TILED = false>
-__device__ __forceinline__ void polar_solve(const V3 cur[4], V3 last[4], Q4 &quat) {
+__device__ __forceinline__ void polar_solve(const V3 cur[4], V3 last[4], Q4 &quat, float noiseK2 = 0.0f) {
     V3 cc = pl_mul(pl_add(pl_add(pl_add(cur[0], cur[1]), cur[2]), cur[3]), 0.25f);
     V3 lc = pl_mul(pl_add(pl_add(pl_add(last[0], last[1]), last[2]), last[3]), 0.25f);
     V3 A[3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
@@ -393,7 +400,7 @@ __device__ __forceinline__ void polar_solve(const V3 cur[4], V3 last[4], Q4 &qua
         A[2] = pl_add(A[2], pl_mul(c, l.z));
     }
     Q4 ident = {0.0f, 0.0f, 0.0f, 1.0f};
-    Q4 rot = (!EXACT && TILED) ? pl_extract_rotation_fast(A, ident) : pl_extract_rotation<EXACT>(A, ident);
+    Q4 rot = (!EXACT && TILED) ? pl_extract_rotation_fast(A, ident, noiseK2 * pl_dot(cc, cc)) : pl_extract_rotation<EXACT>(A, ident);
     Q4 qOld = quat;
     Q4 qNew = pl_normalize<EXACT>(pl_qmul(rot, qOld));  // :181
     quat = qNew;

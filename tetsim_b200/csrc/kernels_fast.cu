@@ -1069,7 +1069,7 @@ __global__ void __launch_bounds__(T) k_polar_tiles(PolarTileArgs a) {
         const V3 cur[4] = {{p0.x, p0.y, p0.z}, {p1.x, p1.y, p1.z}, {p2.x, p2.y, p2.z}, {p3.x, p3.y, p3.z}};
         V3 last[4] = {{r0.x, r0.y, r0.z}, {r0.w, r1.x, r1.y}, {r1.z, r1.w, r2.x}, {r2.y, r2.z, r2.w}};
         Q4 q = {qt.x, qt.y, qt.z, qt.w};
-        polar_solve<false, true>(cur, last, q);
+        polar_solve<false, true>(cur, last, q, a.noiseK2);
         reinterpret_cast<float4 *>(tb)[tid] = make_float4(last[0].x, last[0].y, last[0].z, last[1].x);
         reinterpret_cast<float4 *>(tb + T * 16)[tid] = make_float4(last[1].y, last[1].z, last[2].x, last[2].y);
         reinterpret_cast<float4 *>(tb + T * 32)[tid] = make_float4(last[2].z, last[3].x, last[3].y, last[3].z);

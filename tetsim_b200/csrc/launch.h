@@ -161,6 +161,7 @@ struct PolarTileArgs {
     const uint32_t *metaOff;
     int numTiles, metaStride, metaValOff, maxTileVertsPad, maxTileEntries;
     float4 *part;                   // per tile vertex: (sum goal * V, sum V)
+    float noiseK2;                  // (k 2^-24)^2: the rotation extraction's mesh-scaled exit (device_math.cuh); 0 = fixed floor only
 };
 void launch_polar_tiles(cudaStream_t, int clusterSize, const PolarTileArgs &a);
 size_t polar_tiles_smem(const PolarTileArgs &a);

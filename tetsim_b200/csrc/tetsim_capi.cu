@@ -554,6 +554,9 @@ PolarTileArgs polar_tile_args(const tetsim *h) {
     a.x4 = h->x4.p; a.tets = h->tileTets.p; a.vol = h->tileVol.p; a.meta = h->tileMeta.p; a.metaOff = h->metaOff.p;
     a.numTiles = P.numClusters; a.metaStride = P.metaStride; a.metaValOff = P.metaValOff;
     a.maxTileVertsPad = P.maxTileVertsPad; a.maxTileEntries = P.maxTileEntries; a.part = h->part.p;
+    float k = 4.0f;
+    if (const char *e = getenv("TETSIM_POLAR_NOISE_K")) k = (float)atof(e);
+    a.noiseK2 = (k * 5.9604645e-8f) * (k * 5.9604645e-8f);
     return a;
 }
 
@@ -1402,7 +1405,7 @@ int tetsim_get_info(tetsim_t *h, TetSimInfo *info) {
     info->solver = h->opt.solver; info->arithmetic = h->opt.arithmetic; info->iters = h->opt.iters;
     info->numLevels = h->numLevels; info->maxLevelSize = h->maxLevelSize;
     info->numComponents = h->numComponents; info->bodyKernel = h->bodyKernel ? 1 : 0;
-    info->numClusters = h->plan.numClusters; info->clusterSize = h->clustered ? h->plan.T : 0;
+    info->numClusters = h->plan.numClusters; info->clusterSize = (h->clustered || h->polarTiled) ? h->plan.T : 0;
     info->localTets = h->clustered ? h->plan.localTets : h->M;
     info->localVerts = h->nInt;
     info->boundaryVerts = h->plan.numBoundary;
