@@ -726,23 +726,9 @@ __global__ void __launch_bounds__(256) k_jacobi_apply(int begin, int end, ApplyA
         a.acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         sx = s.x; sy = s.y; sz = s.z;
     } else {
-        // one coalesced 16-byte record names the vertex's (on average 2.4) tile partials: the partial loads leave together
-        // instead of behind a vpStart -> vpSlot -> part chain of three dependent misses
-        const int4 s4 = __ldg(a.vp4 + i);
-        float4 p0, p1, p2, p3;
-        if (s4.x >= 0) p0 = ldg4(a.part + s4.x);
-        if (s4.y >= 0) p1 = ldg4(a.part + s4.y);
-        if (s4.z >= 0) p2 = ldg4(a.part + s4.z);
-        if (s4.w >= 0) p3 = ldg4(a.part + s4.w);
-        if (s4.x >= 0) { sx += p0.x; sy += p0.y; sz += p0.z; }
-        if (s4.y >= 0) { sx += p1.x; sy += p1.y; sz += p1.z; }
-        if (s4.z >= 0) { sx += p2.x; sy += p2.y; sz += p2.z; }
-        if (s4.w >= 0) { sx += p3.x; sy += p3.y; sz += p3.z; }
-        if (s4.w < -1) {
-            for (int j = -(s4.w + 2); j < a.vpStart[i + 1]; j++) {
-                float4 s = ldg4(a.part + a.vpSlot[j]);
-                sx += s.x; sy += s.y; sz += s.z;
-            }
+        for (int j = a.vpStart[i]; j < a.vpStart[i + 1]; j++) {
+            float4 s = ldg4(a.part + a.vpSlot[j]);
+            sx += s.x; sy += s.y; sz += s.z;
         }
     }
     float4 x = a.x4[i];
@@ -1133,26 +1119,14 @@ void launch_polar_tiles(cudaStream_t s, int clusterSize, const PolarTileArgs &a)
 template <int MODE>
 __global__ void k_polar_vertex_tiles(int N, float4 *__restrict__ x4, float4 *__restrict__ prev4, float4 *__restrict__ vel4,
                                      const int *__restrict__ vpStart, const int *__restrict__ vpSlot,
-                                     const int4 *__restrict__ vp4, const float4 *__restrict__ part,
-                                     const int *__restrict__ vertId, const SubstepParams *__restrict__ sp) {
+                                     const float4 *__restrict__ part, const int *__restrict__ vertId,
+                                     const SubstepParams *__restrict__ sp) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     float sx = 0.0f, sy = 0.0f, sz = 0.0f, sw = 0.0f;
-    const int4 s4 = __ldg(vp4 + i);   // ApplyArgs::vp4: the partial loads leave together
-    float4 p0, p1, p2, p3;
-    if (s4.x >= 0) p0 = ldg4(part + s4.x);
-    if (s4.y >= 0) p1 = ldg4(part + s4.y);
-    if (s4.z >= 0) p2 = ldg4(part + s4.z);
-    if (s4.w >= 0) p3 = ldg4(part + s4.w);
-    if (s4.x >= 0) { sx += p0.x; sy += p0.y; sz += p0.z; sw += p0.w; }
-    if (s4.y >= 0) { sx += p1.x; sy += p1.y; sz += p1.z; sw += p1.w; }
-    if (s4.z >= 0) { sx += p2.x; sy += p2.y; sz += p2.z; sw += p2.w; }
-    if (s4.w >= 0) { sx += p3.x; sy += p3.y; sz += p3.z; sw += p3.w; }
-    if (s4.w < -1) {
-        for (int j = -(s4.w + 2); j < vpStart[i + 1]; j++) {
-            const float4 s = ldg4(part + vpSlot[j]);
-            sx += s.x; sy += s.y; sz += s.z; sw += s.w;
-        }
+    for (int j = vpStart[i]; j < vpStart[i + 1]; j++) {
+        const float4 s = ldg4(part + vpSlot[j]);
+        sx += s.x; sy += s.y; sz += s.z; sw += s.w;
     }
     float4 x = x4[i];
     const float4 p = prev4[i];
@@ -1179,10 +1153,10 @@ __global__ void k_polar_vertex_tiles(int N, float4 *__restrict__ x4, float4 *__r
     x4[i] = x;
 }
 void launch_polar_vertex_tiles(cudaStream_t s, int N, int mode, float4 *x4, float4 *prev4, float4 *vel4, const int *vpStart,
-                               const int *vpSlot, const int4 *vp4, const float4 *part, const int *vertId, const SubstepParams *sp) {
+                               const int *vpSlot, const float4 *part, const int *vertId, const SubstepParams *sp) {
     if (N <= 0) return;
-    if (mode == 2) k_polar_vertex_tiles<2><<<cdiv(N, 256), 256, 0, s>>>(N, x4, prev4, vel4, vpStart, vpSlot, vp4, part, vertId, sp);
-    else k_polar_vertex_tiles<1><<<cdiv(N, 256), 256, 0, s>>>(N, x4, prev4, vel4, vpStart, vpSlot, vp4, part, vertId, sp);
+    if (mode == 2) k_polar_vertex_tiles<2><<<cdiv(N, 256), 256, 0, s>>>(N, x4, prev4, vel4, vpStart, vpSlot, part, vertId, sp);
+    else k_polar_vertex_tiles<1><<<cdiv(N, 256), 256, 0, s>>>(N, x4, prev4, vel4, vpStart, vpSlot, part, vertId, sp);
 }
 
 // Tile blocks of the polar solver from the caller-order rest data: record r = tet order[r] (or an unused slot).

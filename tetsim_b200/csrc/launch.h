@@ -79,8 +79,6 @@ void launch_build_tiles(cudaStream_t, int clusterSize, int numRecords, const int
 struct ApplyArgs {
     float4 *x4, *prev4, *vel4;
     const int *vpStart, *vpSlot;    // vertex -> partial-sum slots (CSR into part[])
-    const int4 *vp4;                // the same list as ONE 16-byte record per vertex: up to four slots (-1 = none); a vertex
-                                    // with more than four keeps three and .w = -(j + 2), j = CSR index of its fourth entry
     const float4 *part;
     float4 *acc;                    // atomic-flush accumulator (read and re-zeroed) or NULL
     const float *invVal;            // 1 / valence
@@ -169,7 +167,7 @@ void launch_polar_tiles(cudaStream_t, int clusterSize, const PolarTileArgs &a);
 size_t polar_tiles_smem(const PolarTileArgs &a);
 // mode 1: K5 + K6 + K7; mode 2: + K1 + K2 of the next substep
 void launch_polar_vertex_tiles(cudaStream_t, int N, int mode, float4 *x4, float4 *prev4, float4 *vel4, const int *vpStart,
-                               const int *vpSlot, const int4 *vp4, const float4 *part, const int *vertId, const SubstepParams *sp);
+                               const int *vpSlot, const float4 *part, const int *vertId, const SubstepParams *sp);
 void launch_build_polar_tiles(cudaStream_t, int clusterSize, int numRecords, const int *order, const float4 *x4, const int4 *ids,
                               const float *irv, const uint4 *aux, int dropTet0Corner0, unsigned char *tets, float *vol);
 

@@ -147,7 +147,6 @@ struct tetsim {
     // Jacobi cluster path
     ClusterPlan plan;
     DevBuf<int> vpStart, vpSlot;
-    DevBuf<int4> vp4;                      // ApplyArgs::vp4
     DevBuf<unsigned char> tileTets, tileMeta;
     DevBuf<float> tileVol;                // tiled polar solver: rest volume per record
     DevBuf<uint32_t> metaOff;
@@ -215,7 +214,7 @@ struct tetsim {
         return (int64_t)(x4.bytes() + prev4.bytes() + vel4.bytes() + vertId.bytes() + Q9.bytes() + irv.bytes() +
                          invMass.bytes() + ids.bytes() + cStart.bytes() + cEnt.bytes() + A.bytes() + B.bytes() +
                          C.bytes() + I.bytes() + order.bytes() + levelStart.bytes() + bodies.bytes() +
-                         volTerm.bytes() + dx.bytes() + vpStart.bytes() + vpSlot.bytes() + vp4.bytes() + tileTets.bytes() +
+                         volTerm.bytes() + dx.bytes() + vpStart.bytes() + vpSlot.bytes() + tileTets.bytes() +
                          tileMeta.bytes() + metaOff.bytes() + part.bytes() + acc.bytes() +
                          bsum.bytes() + invVal.bytes() + rest.bytes() + quat.bytes() + tStart.bytes() + tEnt.bytes() +
                          stageIn[0].bytes() + stageIn[1].bytes() + stageOut[0].bytes() + stageOut[1].bytes() + peerBuf.bytes() + pushRec.bytes() + visV.bytes() + visTri.bytes() + vtStart.bytes() + vtEnt.bytes() +
@@ -410,19 +409,6 @@ int build_gs(tetsim *h, const std::vector<float> &verts, const std::vector<int> 
     return TETSIM_OK;
 }
 
-// ApplyArgs::vp4 (launch.h): the vertex -> partial-slot list as one 16-byte record per vertex
-std::vector<int4> build_vp4(const ClusterPlan &P) {
-    std::vector<int4> v((size_t)P.numLocalVerts, make_int4(-1, -1, -1, -1));
-    for (int i = 0; i < P.numLocalVerts; i++) {
-        const int b = P.vpStart[(size_t)i], n = P.vpStart[(size_t)i + 1] - b;
-        int e[4] = {-1, -1, -1, -1};
-        for (int k = 0; k < n && k < 4; k++) e[k] = P.vpSlot[(size_t)b + k];
-        if (n > 4) e[3] = -(b + 3 + 2);   // the fourth and later entries through the CSR arrays
-        v[(size_t)i] = make_int4(e[0], e[1], e[2], e[3]);
-    }
-    return v;
-}
-
 int build_jacobi_gather(tetsim *h, const std::vector<int> &tetIds) {
     const int M = h->M;
     cudaStream_t s = h->stream;
@@ -462,7 +448,6 @@ int build_jacobi_cluster(tetsim *h, const std::vector<float> &verts, const std::
     CK(h->metaOff.upload(P.metaOff, s));
     CK(h->vpStart.upload(P.vpStart, s));
     CK(h->vpSlot.upload(P.vpSlot, s));
-    CK(h->vp4.upload(build_vp4(P), s));
     CK(h->invVal.upload(P.invValence, s));
     if (h->opt.deterministic) CK(h->part.alloc(P.clVerts.size()));
     else { CK(h->acc.alloc((size_t)P.numLocalVerts)); CK(cudaMemsetAsync(h->acc.p, 0, h->acc.bytes(), s)); }
@@ -547,7 +532,6 @@ int build_polar(tetsim *h, const std::vector<int> &tetIds) {
         CK(h->metaOff.upload(P.metaOff, s));
         CK(h->vpStart.upload(P.vpStart, s));
         CK(h->vpSlot.upload(P.vpSlot, s));
-        CK(h->vp4.upload(build_vp4(P), s));
         CK(h->part.alloc(std::max<size_t>(P.clVerts.size(), 1)));
         h->launchesPerSubstep = 2;
         CK(cudaStreamSynchronize(s));
@@ -681,7 +665,7 @@ int enqueue_substeps(tetsim *h, int count) {
                     ca.acc = h->acc.p; ca.volAcc = h->volTerm.p;
                     ApplyArgs aa{};
                     aa.x4 = h->x4.p; aa.prev4 = h->prev4.p; aa.vel4 = h->vel4.p;
-                    aa.vpStart = h->vpStart.p; aa.vpSlot = h->vpSlot.p; aa.vp4 = h->vp4.p; aa.part = h->part.p; aa.acc = h->acc.p;
+                    aa.vpStart = h->vpStart.p; aa.vpSlot = h->vpSlot.p; aa.part = h->part.p; aa.acc = h->acc.p;
                     aa.invVal = h->invVal.p; aa.sp = sp; aa.vertId = vid;
                     aa.boundaryBegin = P.numInterior;
                     const bool multi = h->opt.worldSize > 1 && P.numBoundary > 0;
@@ -775,7 +759,7 @@ int enqueue_substeps(tetsim *h, int count) {
                     if (step == 0) { K->polar_integrate(s, h->nInt, h->x4.p, h->prev4.p, h->vel4.p, sp); h->enq++; }
                     launch_polar_tiles(s, h->plan.T, polar_tile_args(h));
                     launch_polar_vertex_tiles(s, h->nInt, step + 1 < count ? 2 : 1, h->x4.p, h->prev4.p, h->vel4.p, h->vpStart.p,
-                                              h->vpSlot.p, h->vp4.p, h->part.p, vid, sp);
+                                              h->vpSlot.p, h->part.p, vid, sp);
                     h->enq += 2;
                     break;
                 }
@@ -1142,7 +1126,7 @@ void tetsim_destroy(tetsim_t *h) {
     for (auto *b : f4) b->release();
     DevBuf<int> *i1[] = {&h->vertId, &h->cStart, &h->cEnt, &h->order, &h->levelStart, &h->vpStart, &h->vpSlot, &h->tStart, &h->tEnt, &h->grabOut, &h->visTri, &h->vtStart, &h->vtEnt};
     for (auto *b : i1) b->release();
-    h->visRestNrm.release(); h->tetRecord.release(); h->tileVol.release(); h->vp4.release();
+    h->visRestNrm.release(); h->tetRecord.release(); h->tileVol.release();
     DevBuf<float> *f1[] = {&h->Q9, &h->irv, &h->invMass, &h->invVal, &h->stageIn[0], &h->stageIn[1], &h->stageOut[0], &h->stageOut[1], &h->visPos, &h->visNrm};
     for (auto *b : f1) b->release();
     h->ids.release(); h->I.release(); h->bodies.release(); h->volTerm.release(); h->volOut.release();
